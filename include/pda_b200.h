@@ -1,0 +1,99 @@
+/* pda_b200.h -- C ABI of libpda_b200.so: hand-written sm_100a kernels for the Probabilistic U-Net
+ * training / Monte-Carlo inference path of Probabilistic-Domain-Adaptation.
+ *
+ * The reference has no FFI for this path: its boundary is the Python nn.Module API of
+ * prob_utils.my_models.  Each entry point below therefore names the reference
+ * Python code whose ATen/cuDNN launches it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; buffers are owned by the caller
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *  - activations are NHWC bf16 ([B][H][W][C], C % 64 == 0); images / labels / outputs with C == 1 are fp32
+ *  - return value: PDA_OK (0) or a negative PDA_ERR_* code; pda_error_string() names it
+ */
+#ifndef PDA_B200_H_
+#define PDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDA_OK 0
+#define PDA_ERR_SHAPE (-1)     /* unsupported / inconsistent sizes */
+#define PDA_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define PDA_ERR_DRIVER (-3)    /* cuTensorMapEncodeTiled entry point not found */
+#define PDA_ERR_TENSORMAP (-4) /* TMA descriptor encoding failed */
+#define PDA_ERR_ARG (-5)       /* null pointer / bad flag */
+
+#define PDA_ABI_VERSION 1
+
+int pda_abi_version(void);
+const char* pda_error_string(int code);
+
+/* Weights of nn.Conv2d(cin, cout, 3): OIHW fp32 -> [cout][tap = ky*3+kx][cin] bf16 (K-major GEMM B operand).
+ * With rot180 != 0 the taps are reversed and cin/cout swapped ([cin][8-tap][cout]): the dgrad operand. */
+int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, void* stream);
+
+/* First layer of every net (cin = 1, or 2 for the posterior whose input is cat(patch, segm),
+ * probabilistic_unet.py:118): x0/x1 are fp32 [B][H][W] planes (x1 may be NULL), w is OIHW fp32.
+ * Replaces unet_blocks.py:19-20 / probabilistic_unet.py:56-57 for block 0.  out: NHWC bf16. */
+int pda_conv3x3_first(const float* x0, const float* x1, const float* w_oihw, const float* bias, void* out, int B,
+                      int H, int W, int cout, int relu, void* stream);
+
+/* conv3x3(pad 1) + bias (+ReLU) (+ 2x2 average pool) on tcgen05 tensor cores.
+ * Input = channel concat of src0 (c0 ch) and src1 (c1 ch, may be NULL/0) -- the torch.cat of
+ * unet_blocks.py:56 is never materialised.  out and/or out_pool may be NULL.
+ * Replaces unet_blocks.py:17-24 (DownConvBlock) and probabilistic_unet.py:53-61 (Encoder).
+ * bn_tile: 0 = auto, else 64/128/256 output channels per CTA. */
+int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                     void* out, void* out_pool, int B, int H, int W, int cout, int relu, int bn_tile, void* stream);
+
+/* Same contract on plain CUDA cores (one thread per output element).  Cross-check kernel for the
+ * parity tests; the product path never selects it implicitly. */
+int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
+                          const float* bias, void* out, void* out_pool, int B, int H, int W, int cout, int relu,
+                          void* stream);
+
+/* nn.AvgPool2d(2, 2, 0, ceil_mode=True) for even H, W (unet_blocks.py:17).  NHWC bf16. */
+int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream);
+
+/* F.interpolate(mode='bilinear', scale_factor=2, align_corners=True) (unet_blocks.py:51). NHWC bf16 (h,w)->(2h,2w) */
+int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w, int C, void* stream);
+
+/* AxisAlignedConvGaussian head (probabilistic_unet.py:126-137): mean over H then W of the encoder output
+ * enc [B][P][C] bf16, then the 1x1 conv C -> 2*latent (w_head [2L][C] fp32, b_head [2L]).
+ * scratch: fp32, at least B * pda_gauss_head_scratch_rows(P) * C elements.  out: [B][2L] fp32 = (mu | log_sigma). */
+int pda_gauss_head_scratch_rows(int P);
+int pda_gauss_head(const void* enc, const float* w_head, const float* b_head, float* scratch, float* mu_logsigma,
+                   int B, int P, int C, int latent, void* stream);
+
+/* z[s][b][:] = mu[b] + exp(log_sigma[b]) * eps[s][b]  (Normal.rsample, probabilistic_unet.py:302/349). */
+int pda_latent_samples(const float* mu_logsigma, const float* eps, float* z, int S, int B, int latent, void* stream);
+
+/* Analytic KL(q || p) of two diagonal Gaussians (probabilistic_unet.py:332), per batch element -> kl[B]. */
+int pda_kl_diag_gauss(const float* mu_logsigma_q, const float* mu_logsigma_p, float* kl, int B, int latent,
+                      void* stream);
+
+/* Fused Fcomb + sigmoid + cross-sample mean + consensus for S latent samples.
+ * Replaces S x Fcomb.forward (probabilistic_unet.py:200-214: tile, cat, 3 x conv1x1) and the consensus
+ * arithmetic of mean_teacher_trainer.py:74-86 (+ 3 copies) / punet_predictions.py:31-32,117-124.
+ *   feat [B][P][64] bf16, z [S][B][L] fp32,
+ *   w1 [64][64+L] (first 64 input channels = features, last L = z), b1[64], w2[64][64], b2[64], w3[64], b3[1]: fp32.
+ * Outputs (any may be NULL): mean_prob [B][P] fp32 = sum_s sigmoid(logit_s) / S;
+ *   cons_weight [B][P] fp32 = #{s: p_s >= upper or p_s <= lower} / S;  cons_mask [B][P] int64 = (count == S);
+ *   logits / probs [S][B][P] fp32 (per-sample, for sample()/reconstruct() and the parity tests). */
+int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
+                           float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
+                           float* logits, float* probs, void* stream);
+
+/* Mean-teacher EMA over many tensors in one launch: t = t*m + p*(1-m)  (mean_teacher_trainer.py:52-55,
+ * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
+int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDA_B200_H_ */

@@ -1,0 +1,71 @@
+"""Builds libpda_b200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+    python -m probabilistic_domain_adaptation_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libpda_b200.so")
+STAMP = os.path.join(PKG, ".libpda_b200.stamp")
+SOURCES = ["conv3x3_tc.cu", "misc_kernels.cu", "fcomb.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-DPDA_BUILD",
+    "-Xptxas", "-v",
+]
+
+
+def _digest():
+    h = hashlib.sha256()
+    root = os.path.dirname(PKG)
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(root, "include", "pda_b200.h")]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
+        os.makedirs(os.path.dirname(obj), exist_ok=True)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        sys.stderr.write(out.stdout)
+        raise RuntimeError("link failed")
+    with open(os.path.join(PKG, "build", "ptxas.log"), "w") as fh:
+        fh.write("\n".join(log))
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

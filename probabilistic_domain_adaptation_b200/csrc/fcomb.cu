@@ -1,0 +1,142 @@
+// Fused Fcomb (3 x conv1x1) + sigmoid + cross-sample mean + consensus weight/mask for S latent samples.
+//
+// Reference: S x Fcomb.forward (/root/reference/prob_utils/my_models/probabilistic_unet.py:200-214) followed by the
+// consensus arithmetic of prob_utils/my_trainer/mean_teacher_trainer.py:74-86.
+//
+// concat(F, z_s) . W1 = F . W1[:, :64]  +  z_s . W1[:, 64:]: the feature projection is computed ONCE per pixel and
+// each latent sample only contributes a per-(sample, image) bias vector; the tiled-z tensor and the 70-channel
+// concat are never materialised.  fp32 CUDA-core version (one pixel per thread): exact-order fp32 math, used as
+// the numerics baseline of the path; weights are read from shared memory as warp-wide broadcasts.
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace pda {
+
+constexpr int FC = 64;  // num_filters[0]: feature channels == hidden width (all reference scripts)
+
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(128)
+fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ w1,
+                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                const float* __restrict__ w3, const float* __restrict__ b3, int P, int S, int L, int B, float upper,
+                float lower, float* __restrict__ mean_prob, float* __restrict__ cons_weight,
+                int64_t* __restrict__ cons_mask, float* __restrict__ logits, float* __restrict__ probs) {
+  extern __shared__ __align__(16) float sm[];
+  float* w1f = sm;                 // [64][64]  w1f[j][i] = W1[j][i], i < 64
+  float* w2s = w1f + FC * FC;      // [64][64]
+  float* b2s = w2s + FC * FC;      // [64]
+  float* w3s = b2s + FC;           // [64]
+  float* bz = w3s + FC;            // [S][64]   b1[j] + sum_d W1[j][64+d] * z[s][b][d]
+  const int b = blockIdx.y;
+  const int kin = FC + L;
+  for (int i = threadIdx.x; i < FC * FC; i += blockDim.x) {
+    w1f[i] = w1[(i / FC) * kin + (i % FC)];
+    w2s[i] = w2[i];
+  }
+  for (int i = threadIdx.x; i < FC; i += blockDim.x) {
+    b2s[i] = b2[i];
+    w3s[i] = w3[i];
+  }
+  for (int i = threadIdx.x; i < S * FC; i += blockDim.x) {
+    const int s = i / FC, j = i % FC;
+    float acc = b1[j];
+    for (int d = 0; d < L; ++d) acc = fmaf(w1[j * kin + FC + d], z[((long long)s * B + b) * L + d], acc);
+    bz[i] = acc;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  const long long gp = (long long)b * P + pix;
+
+  // features of this pixel: 64 bf16 = 128 B
+  float f[FC];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(feat + gp * FC);
+#pragma unroll
+    for (int k = 0; k < FC / 8; ++k) {
+      const uint4 v = __ldg(src + k);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[8 * k + 2 * i] = t.x;
+        f[8 * k + 2 * i + 1] = t.y;
+      }
+    }
+  }
+  // sample-independent part of layer 1
+  float h1[FC];
+#pragma unroll 4
+  for (int j = 0; j < FC; ++j) {
+    const float4* wr = reinterpret_cast<const float4*>(w1f + j * FC);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < FC / 4; ++i) {
+      const float4 w = wr[i];
+      acc = fmaf(w.x, f[4 * i], acc);
+      acc = fmaf(w.y, f[4 * i + 1], acc);
+      acc = fmaf(w.z, f[4 * i + 2], acc);
+      acc = fmaf(w.w, f[4 * i + 3], acc);
+    }
+    h1[j] = acc;
+  }
+  const float b3v = b3[0];
+  float psum = 0.f;
+  int count = 0;
+  for (int s = 0; s < S; ++s) {
+    const float* bzs = bz + s * FC;
+    float a1[FC];
+#pragma unroll
+    for (int i = 0; i < FC; ++i) a1[i] = fmaxf(h1[i] + bzs[i], 0.f);
+    float logit = b3v;
+#pragma unroll 2
+    for (int j = 0; j < FC; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(w2s + j * FC);
+      float acc = b2s[j];
+#pragma unroll
+      for (int i = 0; i < FC / 4; ++i) {
+        const float4 w = wr[i];
+        acc = fmaf(w.x, a1[4 * i], acc);
+        acc = fmaf(w.y, a1[4 * i + 1], acc);
+        acc = fmaf(w.z, a1[4 * i + 2], acc);
+        acc = fmaf(w.w, a1[4 * i + 3], acc);
+      }
+      logit = fmaf(w3s[j], fmaxf(acc, 0.f), logit);
+    }
+    const float pr = sigmoid_f32(logit);
+    psum += pr;
+    count += (pr >= upper || pr <= lower) ? 1 : 0;
+    if (logits) logits[((long long)s * B + b) * P + pix] = logit;
+    if (probs) probs[((long long)s * B + b) * P + pix] = pr;
+  }
+  if (mean_prob) mean_prob[gp] = psum / (float)S;
+  if (cons_weight) cons_weight[gp] = (float)count / (float)S;
+  if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
+}
+
+}  // namespace pda
+
+using namespace pda;
+
+extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1,
+                                      const float* w2, const float* b2, const float* w3, const float* b3, int B, int P,
+                                      int S, int latent, float upper, float lower, float* mean_prob,
+                                      float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
+                                      void* stream) {
+  if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) return PDA_ERR_ARG;
+  if (B <= 0 || P <= 0 || S <= 0 || latent <= 0 || B > 65535) return PDA_ERR_SHAPE;
+  const size_t smem = (size_t)(2 * FC * FC + 2 * FC + S * FC) * sizeof(float);
+  if (smem > 200 * 1024) return PDA_ERR_SHAPE;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(fcomb_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return PDA_ERR_CUDA;
+    configured = smem;
+  }
+  dim3 grid((P + 127) / 128, B);
+  fcomb_mc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2,
+                                                             b2, w3, b3, P, S, latent, B, upper, lower, mean_prob,
+                                                             cons_weight, cons_mask, logits, probs);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}

@@ -1,0 +1,450 @@
+// HBM-bound helper kernels of the PUNet path: weight packing, first-layer direct conv, 2x2 average pool,
+// bilinear x2 upsample, Gaussian head (global mean + 1x1), latent sampling, KL, multi-tensor EMA,
+// and a plain CUDA-core conv3x3 used as the on-GPU cross-check of the tcgen05 kernel.
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace pda {
+
+// ------------------------------------------------------------------------------------------------
+// OIHW fp32 -> [cout][tap][cin] bf16   (rot180: [cin][8-tap][cout], the dgrad operand)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int cout, int cin,
+                              int rot180) {
+  const long long n = 9LL * cout * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the OUTPUT so writes are coalesced
+    if (!rot180) {
+      const int ci = i % cin;
+      const int tap = (i / cin) % 9;
+      const int co = i / (9LL * cin);
+      o[i] = __float2bfloat16(w[((long long)co * cin + ci) * 9 + tap]);
+    } else {
+      const int co = i % cout;
+      const int tap = (i / cout) % 9;
+      const int ci = i / (9LL * cout);
+      o[i] = __float2bfloat16(w[((long long)co * cin + ci) * 9 + (8 - tap)]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math.  8 output channels per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ w,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int cout,
+                  int relu) {
+  extern __shared__ float ws[];  // [cin][9][cout] + bias[cout]
+  const int cin = x1 ? 2 : 1;
+  for (int i = threadIdx.x; i < cout * cin * 9; i += blockDim.x) {
+    const int co = i / (cin * 9), r = i % (cin * 9);  // OIHW: (co, ci, tap)
+    ws[r * cout + co] = w[i];
+  }
+  float* bs = ws + cin * 9 * cout;
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) bs[i] = bias[i];
+  __syncthreads();
+  const int groups = cout >> 3;
+  const long long total = (long long)B * H * W * groups;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = t % groups;
+    const long long pix = t / groups;
+    const int x = pix % W;
+    const int y = (pix / W) % H;
+    const int b = pix / ((long long)W * H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* xp = (ci == 0 ? x0 : x1) + (long long)b * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + kx - 1;
+          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (long long)yy * W + xx) : 0.f;
+          const float* wr = ws + ((ci * 9 + ky * 3 + kx) * cout + g * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + pix * cout + g * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 average pool, NHWC bf16, 8 channels (16 B) per thread
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+__global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    const long long pix = t / C8;
+    const int x = pix % Wo;
+    const int y = (pix / Wo) % Ho;
+    const int b = pix / ((long long)Wo * Ho);
+    const long long base = (((long long)b * H + 2 * y) * W + 2 * x) * C8 + c;
+    float a[8], s[8];
+    unpack8(__ldg(in + base), s);
+    unpack8(__ldg(in + base + C8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += a[i];
+    unpack8(__ldg(in + base + (long long)W * C8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += a[i];
+    unpack8(__ldg(in + base + (long long)W * C8 + C8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = (s[i] + a[i]) * 0.25f;
+    out[t] = pack8(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=True (ATen upsample_bilinear2d arithmetic: src = dst*(in-1)/(out-1))
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h, int w, int C8) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)B * Ho * Wo * C8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    const long long pix = t / C8;
+    const int x = pix % Wo;
+    const int y = (pix / Wo) % Ho;
+    const int b = pix / ((long long)Wo * Ho);
+    const float sy = rh * y, sx = rw * x;
+    const int y1 = (int)sy, x1 = (int)sx;
+    const int yp = (y1 < h - 1) ? 1 : 0, xp = (x1 < w - 1) ? 1 : 0;
+    const float ly1 = sy - y1, lx1 = sx - x1;
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const uint4* p = in + (((long long)b * h + y1) * w + x1) * C8 + c;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    unpack8(__ldg(p), v00);
+    unpack8(__ldg(p + (long long)xp * C8), v01);
+    unpack8(__ldg(p + (long long)yp * w * C8), v10);
+    unpack8(__ldg(p + ((long long)yp * w + xp) * C8), v11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o[i] = ly0 * (lx0 * v00[i] + lx1 * v01[i]) + ly1 * (lx0 * v10[i] + lx1 * v11[i]);
+    out[t] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian head: deterministic two-stage spatial mean, then the 1x1 conv C -> 2L
+// ------------------------------------------------------------------------------------------------
+constexpr int HEAD_ROWS_PER_BLOCK = 64;  // pixels reduced per stage-1 block
+
+__global__ void __launch_bounds__(256)
+mean_partial_kernel(const __nv_bfloat162* __restrict__ enc, float* __restrict__ partial, int P, int C2, int nchunk) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * HEAD_ROWS_PER_BLOCK;
+  const int p1 = min(P, p0 + HEAD_ROWS_PER_BLOCK);
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    float sx = 0.f, sy = 0.f;
+    const __nv_bfloat162* src = enc + ((long long)b * P + p0) * C2 + c;
+    for (int p = p0; p < p1; ++p, src += C2) {
+      const float2 v = __bfloat1622float2(__ldg(src));
+      sx += v.x;
+      sy += v.y;
+    }
+    float* dst = partial + ((long long)b * nchunk + chunk) * (2 * C2) + 2 * c;
+    dst[0] = sx;
+    dst[1] = sy;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gauss_head_kernel(const float* __restrict__ partial, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int P, int C, int nchunk, int nout) {
+  extern __shared__ float mean_s[];  // [C]
+  const int b = blockIdx.x;
+  const float inv = 1.f / (float)P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nchunk; ++k) s += partial[((long long)b * nchunk + k) * C + c];
+    mean_s[c] = s * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int o = warp; o < nout; o += nwarp) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(mean_s[c], __ldg(w + (long long)o * C + c), s);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[(long long)b * nout + o] = s + bias[o];
+  }
+}
+
+__global__ void latent_samples_kernel(const float* __restrict__ mls, const float* __restrict__ eps,
+                                      float* __restrict__ z, int S, int B, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * B * L) return;
+  const int d = i % L, b = (i / L) % B;
+  z[i] = mls[b * 2 * L + d] + expf(mls[b * 2 * L + L + d]) * eps[i];
+}
+
+__global__ void kl_kernel(const float* __restrict__ q, const float* __restrict__ p, float* __restrict__ kl, int B,
+                          int L) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int d = 0; d < L; ++d) {
+    // torch.distributions.kl._kl_normal_normal
+    const float sq = expf(q[b * 2 * L + L + d]), sp = expf(p[b * 2 * L + L + d]);
+    const float r = sq / sp;
+    const float var_ratio = r * r;
+    const float dm = (q[b * 2 * L + d] - p[b * 2 * L + d]) / sp;
+    s += 0.5f * (var_ratio + dm * dm - 1.f - logf(var_ratio));
+  }
+  kl[b] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-tensor EMA: one 256-thread block per chunk of <= 65536 elements
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ema_kernel(const int64_t* __restrict__ table, float m, float om) {
+  const int64_t* e = table + 3LL * blockIdx.x;
+  float* t = reinterpret_cast<float*>(e[0]);
+  const float* s = reinterpret_cast<const float*>(e[1]);
+  const int n = (int)e[2];
+  if (((reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
+    const int n4 = n >> 2;
+    float4* t4 = reinterpret_cast<float4*>(t);
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 a = t4[i];
+      const float4 b = __ldg(s4 + i);
+      // same rounding as the reference's  t*m + p*(1-m)  (two products, one add; no fma contraction)
+      a.x = __fadd_rn(__fmul_rn(a.x, m), __fmul_rn(b.x, om));
+      a.y = __fadd_rn(__fmul_rn(a.y, m), __fmul_rn(b.y, om));
+      a.z = __fadd_rn(__fmul_rn(a.z, m), __fmul_rn(b.z, om));
+      a.w = __fadd_rn(__fmul_rn(a.w, m), __fmul_rn(b.w, om));
+      t4[i] = a;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x)
+      t[i] = __fadd_rn(__fmul_rn(t[i], m), __fmul_rn(s[i], om));
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] = __fadd_rn(__fmul_rn(t[i], m), __fmul_rn(s[i], om));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain CUDA-core conv3x3 (cross-check): one thread per (pixel, cout), fp32 accumulate over bf16 inputs
+// ------------------------------------------------------------------------------------------------
+__global__ void conv3x3_simt_kernel(const __nv_bfloat16* __restrict__ s0, int c0, const __nv_bfloat16* __restrict__ s1,
+                                    int c1, const __nv_bfloat16* __restrict__ wp, const float* __restrict__ bias,
+                                    __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int B, int H, int W,
+                                    int cout, int relu) {
+  const int ctot = c0 + c1;
+  const long long total = (long long)B * H * W * cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int co = t % cout;
+    const long long pix = t / cout;
+    const int x = pix % W;
+    const int y = (pix / W) % H;
+    const int b = pix / ((long long)W * H);
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const long long ip = ((long long)b * H + yy) * W + xx;
+      const __nv_bfloat16* wr = wp + ((long long)co * 9 + tap) * ctot;
+      for (int c = 0; c < c0; ++c) acc = fmaf(__bfloat162float(s0[ip * c0 + c]), __bfloat162float(wr[c]), acc);
+      for (int c = 0; c < c1; ++c) acc = fmaf(__bfloat162float(s1[ip * c1 + c]), __bfloat162float(wr[c0 + c]), acc);
+    }
+    acc += bias ? bias[co] : 0.f;
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (out) out[t] = __float2bfloat16(acc);
+    if (out_f32) out_f32[t] = acc;
+  }
+}
+
+__global__ void avgpool2_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H,
+                                            int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo * C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C;
+    const long long pix = t / C;
+    const int x = pix % Wo;
+    const int y = (pix / Wo) % Ho;
+    const int b = pix / ((long long)Wo * Ho);
+    const long long base = (((long long)b * H + 2 * y) * W + 2 * x) * C + c;
+    // same association as the tensor-core epilogue: (a + right) + (below + below-right)
+    const float s = (in[base] + in[base + C]) + (in[base + (long long)W * C] + in[base + (long long)W * C + C]);
+    out[t] = __float2bfloat16(0.25f * s);
+  }
+}
+
+static inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace pda
+
+using namespace pda;
+
+extern "C" {
+
+int pda_pack_conv3x3_weights(const float* w, void* o, int cout, int cin, int rot180, void* stream) {
+  if (!w || !o) return PDA_ERR_ARG;
+  if (cout <= 0 || cin <= 0) return PDA_ERR_SHAPE;
+  pack_w_kernel<<<grid_for(9LL * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, static_cast<__nv_bfloat16*>(o), cout, cin, rot180);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const float* bias, void* out, int B, int H,
+                      int W, int cout, int relu, void* stream) {
+  if (!x0 || !w || !bias || !out) return PDA_ERR_ARG;
+  if (cout <= 0 || (cout & 7) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
+  const int cin = x1 ? 2 : 1;
+  const size_t smem = (size_t)(cin * 9 * cout + cout) * sizeof(float);
+  if (smem > 48 * 1024) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * H * W * (cout >> 3);
+  conv_first_kernel<<<grid_for(total, 256, 148 * 8), 256, smem, (cudaStream_t)stream>>>(
+      x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                     void* out, void* out_pool, int B, int H, int W, int cout, int relu, int bn_tile, void* stream) {
+  if (!src0 || !w_packed || (!out && !out_pool) || (c1 > 0 && !src1)) return PDA_ERR_ARG;
+  return conv3x3_tc(src0, c0, src1, c1, w_packed, bias, out, out_pool, B, H, W, cout, relu, bn_tile,
+                    (cudaStream_t)stream);
+}
+
+int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
+                          const float* bias, void* out, void* out_pool, int B, int H, int W, int cout, int relu,
+                          void* stream) {
+  if (!src0 || !w_packed || (!out && !out_pool) || (c1 > 0 && !src1)) return PDA_ERR_ARG;
+  if (c0 <= 0 || c1 < 0 || cout <= 0) return PDA_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * H * W * cout;
+  float* tmp = nullptr;
+  if (out_pool) {
+    if ((H & 1) || (W & 1)) return PDA_ERR_SHAPE;
+    if (cudaMallocAsync(&tmp, total * sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
+  }
+  conv3x3_simt_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(src0), c0, static_cast<const __nv_bfloat16*>(src1), c1,
+      static_cast<const __nv_bfloat16*>(w_packed), bias, static_cast<__nv_bfloat16*>(out), tmp, B, H, W, cout, relu);
+  if (out_pool) {
+    avgpool2_f32_to_bf16_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(tmp, static_cast<__nv_bfloat16*>(out_pool),
+                                                                          B, H, W, cout);
+    cudaFreeAsync(tmp, st);
+  }
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  if (!in || !out) return PDA_ERR_ARG;
+  if ((H & 1) || (W & 1) || (C & 7) || B <= 0) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+  if (!in || !out) return PDA_ERR_ARG;
+  if ((C & 7) || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * (2 * h) * (2 * w) * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, C / 8);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_gauss_head_scratch_rows(int P) { return (P + HEAD_ROWS_PER_BLOCK - 1) / HEAD_ROWS_PER_BLOCK; }
+
+int pda_gauss_head(const void* enc, const float* w_head, const float* b_head, float* scratch, float* mu_logsigma,
+                   int B, int P, int C, int latent, void* stream) {
+  if (!enc || !w_head || !b_head || !scratch || !mu_logsigma) return PDA_ERR_ARG;
+  if (B <= 0 || P <= 0 || C <= 0 || (C & 1) || latent <= 0 || C * sizeof(float) > 48 * 1024) return PDA_ERR_SHAPE;
+  const int nchunk = pda_gauss_head_scratch_rows(P);
+  cudaStream_t st = (cudaStream_t)stream;
+  mean_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(static_cast<const __nv_bfloat162*>(enc), scratch, P, C / 2,
+                                                       nchunk);
+  gauss_head_kernel<<<B, 256, C * sizeof(float), st>>>(scratch, w_head, b_head, mu_logsigma, P, C, nchunk,
+                                                       2 * latent);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_latent_samples(const float* mls, const float* eps, float* z, int S, int B, int latent, void* stream) {
+  if (!mls || !eps || !z) return PDA_ERR_ARG;
+  const int n = S * B * latent;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  latent_samples_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mls, eps, z, S, B, latent);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_kl_diag_gauss(const float* q, const float* p, float* kl, int B, int latent, void* stream) {
+  if (!q || !p || !kl) return PDA_ERR_ARG;
+  if (B <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  kl_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q, p, kl, B, latent);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream) {
+  if (!table) return PDA_ERR_ARG;
+  if (n_chunks <= 0) return PDA_ERR_SHAPE;
+  // the reference multiplies by the python doubles m and (1. - m), each rounded to fp32 by ATen
+  ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, (float)momentum, (float)(1.0 - momentum));
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_abi_version(void) { return PDA_ABI_VERSION; }
+
+const char* pda_error_string(int code) {
+  switch (code) {
+    case PDA_OK: return "ok";
+    case PDA_ERR_SHAPE: return "unsupported or inconsistent shape";
+    case PDA_ERR_CUDA: return "CUDA runtime error";
+    case PDA_ERR_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    case PDA_ERR_TENSORMAP: return "TMA tensor map encoding failed";
+    case PDA_ERR_ARG: return "invalid argument";
+    default: return "unknown error";
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""Host-side mirror of prob_utils/my_models/unet_blocks.py on the sm_100a kernels.
+
+The nn.Conv2d / nn.ReLU / nn.AvgPool2d children exist only as PARAMETER CONTAINERS so that
+state_dict keys, parameter order and module paths are identical to the reference
+(/root/reference/prob_utils/my_models/unet_blocks.py:7-59); they are never called.  All arithmetic
+goes through libpda_b200 (tcgen05 implicit-GEMM conv, fused bias/ReLU/pool, bilinear upsample).
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..autograd_ops import conv3x3_first_op, conv3x3_op, avgpool2_op, upsample2x_op
+from .utils import init_weights
+
+
+def as_nhwc(x):
+    """Logical NCHW tensor (any dtype / memory format) -> contiguous (B,H,W,C) bf16."""
+    if x.dtype == torch.bfloat16 and x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1)
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def as_nchw(x_nhwc):
+    """(B,H,W,C) bf16 -> logical (B,C,H,W) view (channels_last strides, no copy)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def _check_spatial(h, w, levels):
+    div = 2 ** (levels - 1)
+    if w % div:
+        # same exception type as the reference's width check (unet_blocks.py:55)
+        raise AssertionError(f"width {w} is not divisible by {div}: up/bridge widths would differ")
+    if h % div:
+        raise RuntimeError(f"height {h} is not divisible by {div}: Sizes of tensors must match except in dimension 1")
+
+
+def run_conv_stack(convs, x, first_input=None, pool_last=False, keep_full=True, src1=None):
+    """Runs conv3x3+ReLU for every nn.Conv2d container in `convs`.
+
+    x: NHWC bf16 input of the first conv, or None when `first_input` = (x0, x1) fp32 planes feed a
+    cin<=2 first layer.  src1: optional second K-segment (channel concat) of the first conv.
+    Returns (full, pooled) of the last conv.
+    """
+    full, pooled = x, None
+    for j, conv in enumerate(convs):
+        last = j == len(convs) - 1
+        if j == 0 and first_input is not None:
+            full = conv3x3_first_op(first_input[0], first_input[1], conv.weight, conv.bias)
+            if last and pool_last:
+                pooled = avgpool2_op(full)
+            continue
+        full, pooled = conv3x3_op(full, src1 if j == 0 else None, conv, relu=True,
+                                  want_full=(keep_full or not last), want_pool=(last and pool_last))
+    return full, pooled
+
+
+class DownConvBlock(nn.Module):
+    """(optional 2x2 average pool ->) 3 x [conv3x3 + ReLU]; reference: unet_blocks.py:7-31."""
+
+    def __init__(self, input_dim, output_dim, initializers, padding, pool=True):
+        super().__init__()
+        if not padding:
+            raise NotImplementedError("only padding=True (the reference's sole configuration) is implemented")
+        mods = []
+        if pool:
+            mods.append(nn.AvgPool2d(kernel_size=2, stride=2, padding=0, ceil_mode=True))
+        dims = [input_dim, output_dim, output_dim, output_dim]
+        for j in range(3):
+            mods.append(nn.Conv2d(dims[j], dims[j + 1], kernel_size=3, stride=1, padding=1))
+            mods.append(nn.ReLU(inplace=True))
+        self.layers = nn.Sequential(*mods)
+        self.layers.apply(init_weights)
+        self.pool = pool
+        self.input_dim = input_dim
+
+    def convs(self):
+        return [m for m in self.layers if isinstance(m, nn.Conv2d)]
+
+    def forward(self, patch):
+        """patch: logical NCHW.  Stand-alone use; Unet.forward fuses the pool into the producer instead."""
+        if self.input_dim <= 2:
+            planes = patch.float()
+            x1 = planes[:, 1:2].contiguous() if self.input_dim == 2 else None
+            if self.pool:
+                raise NotImplementedError("pooled block with <=2 input channels does not occur in the reference")
+            full, _ = run_conv_stack(self.convs(), None, first_input=(planes[:, 0:1].contiguous(), x1))
+            return as_nchw(full)
+        x = as_nhwc(patch)
+        if self.pool:
+            x = avgpool2_op(x)
+        full, _ = run_conv_stack(self.convs(), x)
+        return as_nchw(full)
+
+
+class UpConvBlock(nn.Module):
+    """bilinear x2 (align_corners=True) + channel concat [up, bridge] + 3 x [conv3x3 + ReLU];
+    reference: unet_blocks.py:34-59.  The concat is never materialised: the first conv reads the
+    upsampled tensor and the bridge as two K segments."""
+
+    def __init__(self, input_dim, output_dim, initializers, padding, bilinear=True):
+        super().__init__()
+        if not bilinear:
+            raise NotImplementedError("ConvTranspose2d up-path is dead code in the reference (bilinear=True always)")
+        self.bilinear = bilinear
+        self.conv_block = DownConvBlock(input_dim, output_dim, initializers, padding, pool=False)
+
+    def forward_nhwc(self, x, bridge):
+        up = upsample2x_op(x)
+        assert up.shape[2] == bridge.shape[2]  # widths (unet_blocks.py:55)
+        if up.shape[1] != bridge.shape[1]:
+            raise RuntimeError("Sizes of tensors must match except in dimension 1")
+        full, _ = run_conv_stack(self.conv_block.convs(), up, src1=bridge)
+        return full
+
+    def forward(self, x, bridge):
+        return as_nchw(self.forward_nhwc(as_nhwc(x), as_nhwc(bridge)))

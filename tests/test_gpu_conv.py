@@ -1,0 +1,144 @@
+"""GPU parity of the conv / pool / upsample / head kernels (called through the C ABI) against a plain
+PyTorch fp32 reference of the same op on the same bf16-rounded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _ref_conv(srcs, w, bias, relu, pool):
+    """srcs: list of NHWC bf16; w (cout, cin, 3, 3) fp32 (bf16-representable)."""
+    x = torch.cat([s.float() for s in srcs], dim=3).permute(0, 3, 1, 2)
+    y = F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    if relu:
+        y = F.relu(y)
+    full = y.permute(0, 2, 3, 1).contiguous()
+    pooled = F.avg_pool2d(y, 2).permute(0, 2, 3, 1).contiguous() if pool else None
+    return full, pooled
+
+
+CONV_CASES = [
+    # B, H, W, c0, c1, cout, pool, bn
+    (1, 16, 16, 64, 0, 64, False, 0),
+    (2, 24, 40, 64, 0, 64, True, 0),
+    (1, 8, 8, 128, 0, 128, True, 0),
+    (1, 5, 9, 256, 0, 512, False, 0),
+    (2, 16, 32, 128, 64, 64, False, 0),
+    (1, 16, 16, 512, 256, 256, False, 256),
+    (1, 32, 16, 256, 0, 256, True, 64),
+    (1, 64, 64, 64, 0, 128, False, 128),
+]
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout,pool,bn", CONV_CASES)
+@pytest.mark.parametrize("simt", [False, True])
+def test_conv3x3_matches_fp32_reference(B, H, W, c0, c1, cout, pool, bn, simt):
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + H * 10 + cout)
+    s0 = torch.randn(B, H, W, c0, generator=g).to(dev).to(torch.bfloat16)
+    s1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(torch.bfloat16) if c1 else None
+    ctot = c0 + c1
+    w = (torch.randn(cout, ctot, 3, 3, generator=g) * (2.0 / (9 * ctot)) ** 0.5).to(dev)
+    w = w.to(torch.bfloat16).float()  # bf16-representable so that only accumulation order differs
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    wp = ops.pack_conv3x3_weights(w)
+    full, pooled = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn, simt=simt)
+    torch.cuda.synchronize()
+    rfull, rpool = _ref_conv([s0] + ([s1] if c1 else []), w, bias, True, pool)
+    # outputs are bf16: half an ulp (2^-9 relative) + fp32 accumulation noise
+    err = (full.float() - rfull).abs()
+    tol = 2 ** -8 * rfull.abs() + 1e-3
+    assert (err <= tol).all(), f"full: max err {err.max().item()} at {err.argmax().item()}"
+    if pool:
+        err = (pooled.float() - rpool).abs()
+        tol = 2 ** -8 * rpool.abs() + 1e-3
+        assert (err <= tol).all(), f"pool: max err {err.max().item()}"
+
+
+def test_conv3x3_pool_only_output():
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(7)
+    s0 = torch.randn(1, 16, 16, 64, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.06).to(dev).to(torch.bfloat16).float()
+    bias = torch.zeros(64, device=dev)
+    wp = ops.pack_conv3x3_weights(w)
+    f1, p1 = ops.conv3x3(s0, None, wp, bias, want_full=True, want_pool=True)
+    f2, p2 = ops.conv3x3(s0, None, wp, bias, want_full=False, want_pool=True)
+    assert f2 is None and torch.equal(p1, p2)
+
+
+@pytest.mark.parametrize("cin", [1, 2])
+def test_first_conv(cin):
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, cin, 24, 40, generator=g).to(dev)
+    w = (torch.randn(64, cin, 3, 3, generator=g) * 0.4).to(dev)
+    b = (torch.randn(64, generator=g) * 0.1).to(dev)
+    out = ops.conv3x3_first(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if cin == 2 else None, w, b)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float().permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert (err <= 2 ** -8 * ref.abs() + 1e-5).all(), err.max().item()
+
+
+def test_avgpool_and_upsample():
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 10, 18, 128, generator=g).to(dev).to(torch.bfloat16)
+    xn = x.float().permute(0, 3, 1, 2)
+    p = ops.avgpool2(x)
+    rp = F.avg_pool2d(xn, 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1)
+    assert ((p.float() - rp).abs() <= 2 ** -8 * rp.abs() + 1e-6).all()
+    u = ops.upsample2x(x)
+    ru = F.interpolate(xn, mode="bilinear", scale_factor=2, align_corners=True).permute(0, 2, 3, 1)
+    err = (u.float() - ru).abs()
+    assert (err <= 2 ** -8 * ru.abs() + 1e-5).all(), err.max().item()
+
+
+def test_gauss_head_and_latents():
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    enc = torch.randn(3, 5, 9, 512, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(12, 512, 1, 1, generator=g) * 0.05).to(dev)
+    b = (torch.randn(12, generator=g) * 0.01).to(dev)
+    out = ops.gauss_head(enc, w, b, 6)
+    e = enc.float().permute(0, 3, 1, 2)
+    e = torch.mean(torch.mean(e, dim=2, keepdim=True), dim=3, keepdim=True)
+    ref = F.conv2d(e, w, b)[:, :, 0, 0]
+    assert torch.allclose(out, ref, atol=1e-5), (out - ref).abs().max().item()
+    eps = torch.randn(4, 3, 6, generator=g).to(dev)
+    z = ops.latent_samples(out, eps)
+    assert torch.allclose(z, out[None, :, :6] + torch.exp(out[None, :, 6:]) * eps, atol=1e-6)
+    q = out.clone()
+    q[:, :6] += 0.3
+    kl = ops.kl_diag_gauss(q, out)
+    d = torch.distributions
+    ref_kl = d.kl.kl_divergence(d.Independent(d.Normal(q[:, :6], torch.exp(q[:, 6:])), 1),
+                                d.Independent(d.Normal(out[:, :6], torch.exp(out[:, 6:])), 1))
+    assert torch.allclose(kl, ref_kl, rtol=1e-5, atol=1e-6)
+
+
+def test_multi_tensor_ema_bit_exact():
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 1, 3, 3), (64,), (512, 256, 3, 3), (12, 512, 1, 1), (7,), (70001,)]
+    teacher = [torch.randn(s, generator=g).to(dev) for s in shapes]
+    student = [torch.randn(s, generator=g).to(dev) for s in shapes]
+    m = 0.999
+    ref = [t * m + p * (1. - m) for t, p in zip(teacher, student)]  # mean_teacher_trainer.py:55
+    table = ops.build_ema_table(teacher, student)
+    ops.multi_tensor_ema(table, m)
+    for t, r in zip(teacher, ref):
+        assert torch.equal(t, r)
