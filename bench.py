@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the PUNet Monte-Carlo inference hot path (BASELINE.json metric: px*samples/s at S=16).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tiles T] [--size HW] [--samples S]
+
+One "step" = one batch of T synthetic HxW tiles through  forward(prior + U-Net) + S-sample fused
+Fcomb/sigmoid/mean/consensus-mask  (the path of mean_teacher_trainer.py:72-88 / punet_predictions.py:29-33).
+Under torchrun every rank processes its own tiles (weak scaling, no data-path collective); the time is the
+max over ranks of the CUDA-event time of the K timed steps.
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port of the
+reference PyTorch code: the reference tree itself does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PX_FORWARD = 2_509_056  # prior 701 568 + U-Net 1 807 488, incl. the cin=1 first layers
+FIRST_LAYER_FLOP_PER_PX = 2 * 2 * 9 * 64  # the two cin=1 first layers run on CUDA cores (HBM-bound)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=4, help="tiles per GPU per step")
+    ap.add_argument("--size", type=int, default=1024, help="tile height = width")
+    ap.add_argument("--samples", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        clocks, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                clocks.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def cpu_reference_run(size, samples, tiles, steps, warmup):
+    """The reference path on host cores (oracle port), fp32, all threads.  Returns (px*samples/s, s/step, cores)."""
+    import torch
+    from oracle import punet_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = po.make_state_dict(0, last_layer_gain=8.0)
+    x, _, eps, _ = po.synthetic_inputs(tiles, size, size, s=samples)
+
+    def step():
+        with torch.no_grad():
+            y, z, _ = po.sample_from_teacher(sd, x, eps, do_consensus_masking=True)
+        return y, z
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return tiles * size * size * samples / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: one 512x512 tile per step keeps `--steps 10 --warmup 3` within a few minutes
+    size, tiles = min(args.size, 512), 1
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    val, dt, cores = cpu_reference_run(size, args.samples, tiles, steps, warmup)
+    sample = f"{tiles} tile {size}x{size}, S={args.samples}, {steps} timed steps after {warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": "punet_mc_px_samples_per_s", "value": val, "unit": "px*samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PUNet MC inference S={args.samples} + consensus mask, {args.size}x{args.size} tiles",
+                   "timed_sample": sample},
+        "cpu_baseline": {"value": val, "unit": "px*samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "px*samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import punet_oracle as po
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, _lib, consensus, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    T, HW, S = args.tiles, args.size, args.samples
+    sd = po.make_state_dict(0, last_layer_gain=8.0)
+    model = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0).to(dev).eval()
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1 + rank)
+    host_x = torch.randn(T, 1, HW, HW, generator=g).pin_memory()
+    eps = torch.randn(S, T, 6, generator=torch.Generator().manual_seed(3)).to(dev)
+    x_dev = host_x.to(dev)
+    out_mean = torch.empty(T, 1, HW, HW, dtype=torch.float32).pin_memory()
+    out_mask = torch.empty(T, 1, HW, HW, dtype=torch.int64).pin_memory()
+
+    def step_resident():
+        return consensus.sample_from_teacher(model, x_dev, S, do_consensus_masking=True, eps=eps)
+
+    def step_e2e():
+        return consensus.predict_host(model, host_x, S, True, out_mean, out_mask, eps=eps)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ops.PROFILE = [] if profile else None
+        lib.pda_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.pda_launch_count()
+        prof, ops.PROFILE = ops.PROFILE, None
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, prof, clocks
+
+    for _ in range(args.warmup):
+        step_resident()
+    ms, launches, prof, clocks = timed(step_resident, args.steps, profile=True)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    px_samples = float(T) * HW * HW * S * world
+    value = px_samples * args.steps / (ms * 1e-3)
+    e2e_value = px_samples * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (tcgen05 conv3x3), timed live per launch on the launching stream
+    hbm_peak, tf_peak, peak_src = load_peaks()
+    conv_ms = sum(a.elapsed_time(b) for k, a, b, _ in prof if k == "conv3x3_tc")
+    conv_flop = sum(w for k, _, _, w in prof if k == "conv3x3_tc")
+    n_conv = sum(1 for k, *_ in prof if k == "conv3x3_tc")
+    fc_ms = sum(a.elapsed_time(b) for k, a, b, _ in prof if k == "fcomb_mc")
+    fc_px = sum(w for k, _, _, w in prof if k == "fcomb_mc")
+    achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    fc_gbs = fc_px * 140.0 / (fc_ms * 1e-3) / 1e9 if fc_ms > 0 else 0.0
+    fc_tf = fc_px * 2.0 * (4096 + S * 4160) / (fc_ms * 1e-3) / 1e12 if fc_ms > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        csize = min(HW, 512)
+        cval, cdt, cores = cpu_reference_run(csize, S, 1, 1, 1)
+        cpu = {"value": cval, "unit": "px*samples/s", "cores": cores, "kind": "port",
+               "sample": f"1 tile {csize}x{csize}, S={S}, 1 timed step after 1 warm-up ({cdt:.1f} s)"}
+
+    line = {
+        "metric": "punet_mc_px_samples_per_s", "value": value, "unit": "px*samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"PUNet (64-128-256-512, latent 6) MC inference: forward + S={S} fused "
+                               f"Fcomb/sigmoid/mean/consensus-mask on {T} tiles/GPU of 1x{HW}x{HW} "
+                               f"(BASELINE config 5 at S={S})",
+                   "tiles_per_gpu": T, "tile": HW, "samples": S, "parallelism": f"tile-sharded x{world}",
+                   "l2": "activations >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+        "e2e": {"value": e2e_value, "unit": "px*samples/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": host_x.numel() * 4,
+                "d2h_bytes_per_step": out_mean.numel() * 4 + out_mask.numel() * 8},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all layers)",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "launches": n_conv, "kernel_ms_per_step": conv_ms / args.steps,
+                     "share_of_step": conv_ms / ms},
+        "roofline_fcomb": {"bound": "hbm (north star) / fp32 FMA (actual)", "achieved": fc_gbs, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": fc_gbs / hbm_peak, "algorithmic_bytes_per_px": 140,
+                           "achieved_tflops": fc_tf, "kernel_ms_per_step": fc_ms / args.steps,
+                           "share_of_step": fc_ms / ms},
+        "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,10 @@ extern "C" {
 int pda_abi_version(void);
 const char* pda_error_string(int code);
 
+/* Number of kernels launched through this library since load / the last reset (bench.py "gpu_launches"). */
+long long pda_launch_count(void);
+void pda_reset_launch_count(void);
+
 /* Weights of nn.Conv2d(cin, cout, 3): OIHW fp32 -> [cout][tap = ky*3+kx][cin] bf16 (K-major GEMM B operand).
  * With rot180 != 0 the taps are reversed and cin/cout swapped ([cin][8-tap][cout]): the dgrad operand. */
 int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, void* stream);

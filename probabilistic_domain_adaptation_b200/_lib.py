@@ -17,6 +17,8 @@ _F = _c.c_float
 SIGNATURES = {
     "pda_abi_version": [],
     "pda_error_string": [_I],
+    "pda_launch_count": [],
+    "pda_reset_launch_count": [],
     "pda_pack_conv3x3_weights": [_P, _P, _I, _I, _I, _P],
     "pda_conv3x3_first": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -30,7 +32,7 @@ SIGNATURES = {
     "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
 }
-_RESTYPES = {"pda_error_string": _c.c_char_p}
+_RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None}
 
 _lib = None
 

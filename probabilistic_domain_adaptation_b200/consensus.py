@@ -1,0 +1,92 @@
+"""Consensus weighting / masking and mean-teacher entry points on the fused kernels.
+
+Drop-ins for the helper bodies that the reference duplicates in its trainers and prediction functions:
+  sample_from_teacher / sample_from_weak_model   mean_teacher_trainer.py:72-88, adamt_trainer.py:60-76,
+                                                 fixmatch_trainer.py:37-54, adamatch_trainer.py:33-49
+  sample_from_model                              mean_teacher_trainer.py:90-93
+  _momentum_update                               mean_teacher_trainer.py:52-55, adamt_trainer.py:40-43
+  _custom_punet_prediction                       punet_predictions.py:29-33
+  pseudo-label + consensus mask                  punet_predictions.py:104-124
+(paths relative to /root/reference/prob_utils).
+"""
+import torch
+
+from . import ops
+from .autograd_ops import invalidate_packed
+
+
+@torch.no_grad()
+def sample_from_teacher(net, inputs, n_samples=16, upper_thres=0.9, lower_thres=0.1, do_consensus_masking=False,
+                        eps=None):
+    """net.forward(inputs, None, training=False); n_samples x sigmoid(net.sample()); mean and consensus.
+    Returns (samples, consensus): (B,1,H,W) fp32 pseudo-label and fp32 k/n weight, or int64 {0,1} mask."""
+    net.forward(inputs, None, training=False)
+    return net.mc_consensus(n_samples, eps=eps, upper_thres=upper_thres, lower_thres=lower_thres,
+                            do_consensus_masking=do_consensus_masking)
+
+
+sample_from_weak_model = sample_from_teacher
+
+
+@torch.no_grad()
+def sample_from_model(net, n_samples=16, eps=None):
+    """Mean of n_samples sigmoid samples of an already-forwarded net (logging / validation helper)."""
+    mean, _ = net.mc_consensus(n_samples, eps=eps, want_consensus=False)
+    return mean
+
+
+@torch.no_grad()
+def punet_mc_prediction(model, raw, prior_samples=8, eps=None):
+    """The per-tile closure of punet_prediction: forward, prior_samples x sigmoid(sample(testing=True)), mean."""
+    model.forward(raw, None, training=False)
+    mean, _ = model.mc_consensus(prior_samples, eps=eps, testing=True, want_consensus=False)
+    return mean
+
+
+@torch.no_grad()
+def punet_pseudo_labels(model, patch, prior_samples=8, upper_threshold=0.9, lower_threshold=0.1, eps=None):
+    """Whole-image pseudo-label + consensus MASK (punet_predictions.py:104-124) -> (mean fp32, mask uint8)."""
+    model.forward(patch, None, training=False)
+    mean, mask = model.mc_consensus(prior_samples, eps=eps, testing=True, upper_thres=upper_threshold,
+                                    lower_thres=lower_threshold, do_consensus_masking=True)
+    return mean, mask.to(torch.uint8)
+
+
+class MomentumUpdater:
+    """teacher = teacher * m + student * (1 - m) over all parameters in ONE kernel launch.
+    Keeps a device-side pointer table; rebuilt if any parameter storage moved."""
+
+    def __init__(self, model, teacher):
+        self.model, self.teacher = model, teacher
+        self._table, self._key = None, None
+
+    def _refresh(self):
+        tp = [p.data for p in self.teacher.parameters()]
+        sp = [p.data for p in self.model.parameters()]
+        key = tuple(t.data_ptr() for t in tp) + tuple(s.data_ptr() for s in sp)
+        if key != self._key:
+            self._table = ops.build_ema_table(tp, sp)
+            self._key = key
+
+    @torch.no_grad()
+    def step(self, momentum):
+        self._refresh()
+        ops.multi_tensor_ema(self._table, momentum)
+        invalidate_packed(self.teacher)  # parameter memory changed behind autograd's version counters
+
+
+def adamt_momentum(iteration, momentum=0.999):
+    """adamt_trainer.py:41 warm-up schedule."""
+    return min(1 - 1 / (iteration + 1), momentum)
+
+
+@torch.no_grad()
+def predict_host(model, host_images, n_samples, do_consensus_masking, out_mean, out_cons, eps=None):
+    """End-to-end call with HOST buffers (pinned): H2D of the image batch, forward + fused MC consensus,
+    D2H of the mean probability and the consensus.  Everything is enqueued on the current stream."""
+    dev = next(model.parameters()).device
+    x = host_images.to(dev, non_blocking=True)
+    mean, cons = sample_from_teacher(model, x, n_samples, do_consensus_masking=do_consensus_masking, eps=eps)
+    out_mean.copy_(mean, non_blocking=True)
+    out_cons.copy_(cons, non_blocking=True)
+    return out_mean, out_cons

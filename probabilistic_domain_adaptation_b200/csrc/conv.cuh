@@ -7,6 +7,10 @@
 
 #include "../../include/pda_b200.h"
 
+#include <atomic>
+extern std::atomic<long long> g_pda_launches;  // kernels launched through the C ABI (bench.py gpu_launches)
+#define PDA_COUNT(n) g_pda_launches.fetch_add((n), std::memory_order_relaxed)
+
 namespace pda {
 
 struct ConvArgs {

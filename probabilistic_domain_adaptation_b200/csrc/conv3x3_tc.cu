@@ -252,6 +252,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     configured = true;
   }
   dim3 grid(args.tiles_x * args.tiles_y * args.B, args.cout / BN);
+  PDA_COUNT(1);
   conv3x3_tc_kernel<BN, STAGES><<<grid, 192, L::DYN_BYTES, stream>>>(a0, a1, b, args);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

@@ -135,6 +135,7 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
     configured = smem;
   }
   dim3 grid((P + 127) / 128, B);
+  PDA_COUNT(1);
   fcomb_mc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2,
                                                              b2, w3, b3, P, S, latent, B, upper, lower, mean_prob,
                                                              cons_weight, cons_mask, logits, probs);

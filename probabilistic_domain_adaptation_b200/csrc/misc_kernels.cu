@@ -4,6 +4,8 @@
 #include "conv.cuh"
 #include "ptx.cuh"
 
+std::atomic<long long> g_pda_launches{0};
+
 namespace pda {
 
 // ------------------------------------------------------------------------------------------------
@@ -329,6 +331,7 @@ extern "C" {
 int pda_pack_conv3x3_weights(const float* w, void* o, int cout, int cin, int rot180, void* stream) {
   if (!w || !o) return PDA_ERR_ARG;
   if (cout <= 0 || cin <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
   pack_w_kernel<<<grid_for(9LL * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
       w, static_cast<__nv_bfloat16*>(o), cout, cin, rot180);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
@@ -342,6 +345,7 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
   const size_t smem = (size_t)(cin * 9 * cout + cout) * sizeof(float);
   if (smem > 48 * 1024) return PDA_ERR_SHAPE;
   const long long total = (long long)B * H * W * (cout >> 3);
+  PDA_COUNT(1);
   conv_first_kernel<<<grid_for(total, 256, 148 * 8), 256, smem, (cudaStream_t)stream>>>(
       x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
@@ -366,11 +370,13 @@ int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, co
     if ((H & 1) || (W & 1)) return PDA_ERR_SHAPE;
     if (cudaMallocAsync(&tmp, total * sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
   }
+  PDA_COUNT(1);
   conv3x3_simt_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(src0), c0, static_cast<const __nv_bfloat16*>(src1), c1,
       static_cast<const __nv_bfloat16*>(w_packed), bias, static_cast<__nv_bfloat16*>(out), tmp, B, H, W, cout, relu);
   if (out_pool) {
-    avgpool2_f32_to_bf16_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(tmp, static_cast<__nv_bfloat16*>(out_pool),
+    PDA_COUNT(1);
+  avgpool2_f32_to_bf16_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(tmp, static_cast<__nv_bfloat16*>(out_pool),
                                                                           B, H, W, cout);
     cudaFreeAsync(tmp, st);
   }
@@ -381,6 +387,7 @@ int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, voi
   if (!in || !out) return PDA_ERR_ARG;
   if ((H & 1) || (W & 1) || (C & 7) || B <= 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  PDA_COUNT(1);
   avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
@@ -390,6 +397,7 @@ int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w,
   if (!in || !out) return PDA_ERR_ARG;
   if ((C & 7) || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (2 * h) * (2 * w) * (C / 8);
+  PDA_COUNT(1);
   upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, C / 8);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
@@ -403,6 +411,7 @@ int pda_gauss_head(const void* enc, const float* w_head, const float* b_head, fl
   if (B <= 0 || P <= 0 || C <= 0 || (C & 1) || latent <= 0 || C * sizeof(float) > 48 * 1024) return PDA_ERR_SHAPE;
   const int nchunk = pda_gauss_head_scratch_rows(P);
   cudaStream_t st = (cudaStream_t)stream;
+  PDA_COUNT(2);
   mean_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(static_cast<const __nv_bfloat162*>(enc), scratch, P, C / 2,
                                                        nchunk);
   gauss_head_kernel<<<B, 256, C * sizeof(float), st>>>(scratch, w_head, b_head, mu_logsigma, P, C, nchunk,
@@ -414,6 +423,7 @@ int pda_latent_samples(const float* mls, const float* eps, float* z, int S, int 
   if (!mls || !eps || !z) return PDA_ERR_ARG;
   const int n = S * B * latent;
   if (n <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
   latent_samples_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mls, eps, z, S, B, latent);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
@@ -421,6 +431,7 @@ int pda_latent_samples(const float* mls, const float* eps, float* z, int S, int 
 int pda_kl_diag_gauss(const float* q, const float* p, float* kl, int B, int latent, void* stream) {
   if (!q || !p || !kl) return PDA_ERR_ARG;
   if (B <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
   kl_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q, p, kl, B, latent);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
@@ -429,11 +440,15 @@ int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, vo
   if (!table) return PDA_ERR_ARG;
   if (n_chunks <= 0) return PDA_ERR_SHAPE;
   // the reference multiplies by the python doubles m and (1. - m), each rounded to fp32 by ATen
+  PDA_COUNT(1);
   ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, (float)momentum, (float)(1.0 - momentum));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
 int pda_abi_version(void) { return PDA_ABI_VERSION; }
+
+long long pda_launch_count(void) { return g_pda_launches.load(); }
+void pda_reset_launch_count(void) { g_pda_launches.store(0); }
 
 const char* pda_error_string(int code) {
   switch (code) {

@@ -8,8 +8,31 @@ import torch
 from . import _lib
 
 
+# When set to a list, every tensor-core conv / fused-Fcomb launch appends (kind, start_event, end_event, work)
+# so that bench.py can time the dominant kernel live, on the launching stream, inside the timed region.
+PROFILE = None
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+class _Timed:
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.e0, self.e1, self.work))
+        return False
 
 
 def _ptr(t):
@@ -63,8 +86,9 @@ def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=Fal
         rc = lib.pda_conv3x3_bf16_simt(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
                                        _ptr(full), _ptr(pool), B, H, W, cout, int(relu), _stream())
     else:
-        rc = lib.pda_conv3x3_bf16(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
-                                  _ptr(full), _ptr(pool), B, H, W, cout, int(relu), int(bn_tile), _stream())
+        with _Timed("conv3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
+            rc = lib.pda_conv3x3_bf16(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
+                                      _ptr(full), _ptr(pool), B, H, W, cout, int(relu), int(bn_tile), _stream())
     _lib.check(rc, "conv3x3")
     return full, pool
 
@@ -139,10 +163,11 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
     logits = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_logits else None
     probs = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_probs else None
     z = z.contiguous().float()
-    rc = lib.pda_fcomb_mc_consensus(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                    b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), B, P, S, L, float(upper),
-                                    float(lower), _ptr(mean), _ptr(weight), _ptr(mask), _ptr(logits), _ptr(probs),
-                                    _stream())
+    with _Timed("fcomb_mc", float(B * P)):
+        rc = lib.pda_fcomb_mc_consensus(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                                        w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), B, P, S, L,
+                                        float(upper), float(lower), _ptr(mean), _ptr(weight), _ptr(mask),
+                                        _ptr(logits), _ptr(probs), _stream())
     _lib.check(rc, "fcomb_mc_consensus")
     return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs}
 
