@@ -93,6 +93,13 @@ int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, co
                            float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
                            float* logits, float* probs, void* stream);
 
+/* Same contract in exact-order fp32 on CUDA cores (no bf16 rounding of weights / hidden activations): the
+ * numerics baseline of the tensor-core kernel above.  ~20x slower; selected explicitly by the caller only. */
+int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
+                                const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
+                                float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
+                                float* logits, float* probs, void* stream);
+
 /* Mean-teacher EMA over many tensors in one launch: t = t*m + p*(1-m)  (mean_teacher_trainer.py:52-55,
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
 int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream);

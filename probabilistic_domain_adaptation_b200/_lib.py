@@ -30,6 +30,7 @@ SIGNATURES = {
     "pda_latent_samples": [_P, _P, _P, _I, _I, _I, _P],
     "pda_kl_diag_gauss": [_P, _P, _P, _I, _I, _P],
     "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
+    "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
 }
 _RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None}

@@ -25,6 +25,7 @@ struct ConvArgs {
   __nv_bfloat16* out_pool;  // NHWC [B][H/2][W/2][cout] (2x2 average of the post-ReLU fp32 values) or nullptr
 };
 
+void* get_encode_tiled();  // cuTensorMapEncodeTiled driver entry point (or nullptr)
 int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h, int box_c);
 int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long long outer, int box_inner,
                         int box_outer);

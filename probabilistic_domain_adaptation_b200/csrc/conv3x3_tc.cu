@@ -212,6 +212,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+void* get_encode_tiled() { return reinterpret_cast<void*>(get_encode_fn()); }
+
 int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h,
                         int box_c) {
   EncodeTiledFn enc = get_encode_fn();

@@ -3,6 +3,7 @@
 // Reference: S x Fcomb.forward (/root/reference/prob_utils/my_models/probabilistic_unet.py:200-214) followed by the
 // consensus arithmetic of prob_utils/my_trainer/mean_teacher_trainer.py:74-86.
 //
+// fp32 CUDA-core version: the numerics baseline of csrc/fcomb_tc.cu (selected explicitly, never implicitly).
 // concat(F, z_s) . W1 = F . W1[:, :64]  +  z_s . W1[:, 64:]: the feature projection is computed ONCE per pixel and
 // each latent sample only contributes a per-(sample, image) bias vector; the tiled-z tensor and the 70-channel
 // concat are never materialised.  fp32 CUDA-core version (one pixel per thread): exact-order fp32 math, used as
@@ -119,7 +120,7 @@ fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
 
 using namespace pda;
 
-extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1,
+extern "C" int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w1, const float* b1,
                                       const float* w2, const float* b2, const float* w3, const float* b3, int B, int P,
                                       int S, int latent, float upper, float lower, float* mean_prob,
                                       float* cons_weight, int64_t* cons_mask, float* logits, float* probs,

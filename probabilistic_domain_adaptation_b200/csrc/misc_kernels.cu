@@ -31,35 +31,39 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math.  8 output channels per thread.
+// first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math.  Each thread owns 8 output channels
+// (weights live in registers for the whole kernel) and walks over pixels; the 8 threads of a pixel
+// write one contiguous 128-byte row (cout = 64).
 // ------------------------------------------------------------------------------------------------
+template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ w,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int cout,
                   int relu) {
-  extern __shared__ float ws[];  // [cin][9][cout] + bias[cout]
-  const int cin = x1 ? 2 : 1;
-  for (int i = threadIdx.x; i < cout * cin * 9; i += blockDim.x) {
-    const int co = i / (cin * 9), r = i % (cin * 9);  // OIHW: (co, ci, tap)
-    ws[r * cout + co] = w[i];
-  }
-  float* bs = ws + cin * 9 * cout;
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) bs[i] = bias[i];
-  __syncthreads();
   const int groups = cout >> 3;
-  const long long total = (long long)B * H * W * groups;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int g = t % groups;
-    const long long pix = t / groups;
+  const int g = threadIdx.x % groups;              // output-channel group of this thread (fixed)
+  const int lanes_px = blockDim.x / groups;        // pixels processed by a block per iteration
+  const int lpx = threadIdx.x / groups;
+  float wr[CIN][9][8], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = bias[g * 8 + j];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wr[ci][t][j] = w[((g * 8 + j) * CIN + ci) * 9 + t];  // OIHW
+  }
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * lanes_px + lpx; pix < npix; pix += (long long)gridDim.x * lanes_px) {
     const int x = pix % W;
     const int y = (pix / W) % H;
-    const int b = pix / ((long long)W * H);
+    const long long img_off = (pix / ((long long)W * H)) * H * W;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[g * 8 + j];
-    for (int ci = 0; ci < cin; ++ci) {
-      const float* xp = (ci == 0 ? x0 : x1) + (long long)b * H * W;
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* xp = (ci == 0 ? x0 : x1) + img_off;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = y + ky - 1;
@@ -67,9 +71,8 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
         for (int kx = 0; kx < 3; ++kx) {
           const int xx = x + kx - 1;
           const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (long long)yy * W + xx) : 0.f;
-          const float* wr = ws + ((ci * 9 + ky * 3 + kx) * cout + g * 8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[ci][ky * 3 + kx][j], acc[j]);
         }
       }
     }
@@ -341,13 +344,16 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
                       int W, int cout, int relu, void* stream) {
   if (!x0 || !w || !bias || !out) return PDA_ERR_ARG;
   if (cout <= 0 || (cout & 7) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
-  const int cin = x1 ? 2 : 1;
-  const size_t smem = (size_t)(cin * 9 * cout + cout) * sizeof(float);
-  if (smem > 48 * 1024) return PDA_ERR_SHAPE;
-  const long long total = (long long)B * H * W * (cout >> 3);
+  const int groups = cout >> 3;
+  if (256 % groups) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * H * W * groups;
   PDA_COUNT(1);
-  conv_first_kernel<<<grid_for(total, 256, 148 * 8), 256, smem, (cudaStream_t)stream>>>(
-      x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
+  if (x1)
+    conv_first_kernel<2><<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
+  else
+    conv_first_kernel<1><<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 

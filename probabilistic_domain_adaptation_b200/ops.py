@@ -148,7 +148,7 @@ def kl_diag_gauss(mls_q, mls_p):
 
 
 def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, want_mean=True, want_weight=True,
-                       want_mask=False, want_logits=False, want_probs=False):
+                       want_mask=False, want_logits=False, want_probs=False, precision="bf16"):
     """feat (B,H,W,64) bf16; z (S,B,L) fp32.  Returns dict of (B,1,H,W) / (S,B,1,H,W) tensors."""
     _need_cuda(feat, z, w1)
     lib = _lib.load()
@@ -163,11 +163,11 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
     logits = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_logits else None
     probs = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_probs else None
     z = z.contiguous().float()
+    fn = lib.pda_fcomb_mc_consensus if precision == "bf16" else lib.pda_fcomb_mc_consensus_fp32
     with _Timed("fcomb_mc", float(B * P)):
-        rc = lib.pda_fcomb_mc_consensus(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(),
-                                        w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), B, P, S, L,
-                                        float(upper), float(lower), _ptr(mean), _ptr(weight), _ptr(mask),
-                                        _ptr(logits), _ptr(probs), _stream())
+        rc = fn(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                w3.data_ptr(), b3.data_ptr(), B, P, S, L, float(upper), float(lower), _ptr(mean), _ptr(weight),
+                _ptr(mask), _ptr(logits), _ptr(probs), _stream())
     _lib.check(rc, "fcomb_mc_consensus")
     return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs}
 

@@ -24,31 +24,55 @@ def _model(gain=1.0, **kw):
     return m.eval()
 
 
-def test_fcomb_kernel_fp32_parity_and_bit_exact_consensus():
-    """Fcomb + consensus on oracle features: fp32 kernel vs oracle within 1e-4; mask/weight bit-exact
-    when recomputed with the reference's torch ops on the kernel's own probabilities."""
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9)])
+def test_fcomb_kernel_parity_and_bit_exact_consensus(precision, shape):
+    """Fcomb + consensus on given features vs the oracle: the fp32 kernel within 1e-4, the tensor-core kernel
+    (bf16 weights / hidden activations, fp32 accumulate) within 5e-3 of the unit-gain logit scale; mask and
+    weight bit-exact when recomputed with the reference's torch ops on the kernel's own probabilities."""
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
-    sd = po.make_state_dict(0, last_layer_gain=24.0)
+    gain = 24.0
+    sd = po.make_state_dict(0, last_layer_gain=gain)
     g = torch.Generator().manual_seed(21)
-    feat = torch.relu(torch.randn(2, 64, 24, 40, generator=g)).to(torch.bfloat16)
-    z = torch.randn(16, 2, 6, generator=g)
+    b, h, w_ = shape
+    feat = torch.relu(torch.randn(b, 64, h, w_, generator=g)).to(torch.bfloat16)
+    z = torch.randn(16, b, 6, generator=g)
     ref = torch.stack([po.fcomb_logits(sd, feat.float(), z[s]) for s in range(16)], 0)
     k = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
     w = [sd[f"{n}.{p}"].to(dev).contiguous() for n in k for p in ("weight", "bias")]
+    tol = 1e-4 * max(1.0, ref.abs().max().item()) if precision == "fp32" else 5e-3 * gain
     for masking in (False, True):
         out = ops.fcomb_mc_consensus(feat.permute(0, 2, 3, 1).contiguous().to(dev), z.to(dev), *w,
-                                     want_mask=masking, want_weight=not masking, want_logits=True, want_probs=True)
-        assert (out["logits"].cpu() - ref).abs().max() < 1e-4 * max(1.0, ref.abs().max().item())
+                                     want_mask=masking, want_weight=not masking, want_logits=True, want_probs=True,
+                                     precision=precision)
+        err = (out["logits"].cpu() - ref).abs().max().item()
+        print(precision, shape, "max |logit err| / gain =", err / gain)
+        assert err < tol, (err, tol)
         y, c = po.consensus_from_probs(out["probs"].cpu(), do_consensus_masking=masking)
         mine = out["mask"] if masking else out["weight"]
         assert mine.dtype == c.dtype
         assert torch.equal(mine.cpu(), c), "consensus not bit-exact on identical probabilities"
         assert torch.allclose(out["mean"].cpu(), y, atol=1e-6)
         assert torch.allclose(out["probs"].cpu(), torch.sigmoid(out["logits"].cpu()), atol=1e-6)
-        if masking:
+        if masking and b * h * w_ > 500:
             frac = mine.float().mean().item()
             assert 0.0 < frac < 1.0, frac
+
+
+@pytest.mark.parametrize("S", [1, 3, 8, 64])
+def test_fcomb_sample_counts(S):
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    sd = po.make_state_dict(0, last_layer_gain=4.0)
+    g = torch.Generator().manual_seed(5 + S)
+    feat = torch.relu(torch.randn(2, 64, 16, 24, generator=g)).to(torch.bfloat16)
+    z = torch.randn(S, 2, 6, generator=g)
+    ref = torch.stack([po.fcomb_logits(sd, feat.float(), z[s]) for s in range(S)], 0)
+    k = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
+    w = [sd[f"{n}.{p}"].to(dev).contiguous() for n in k for p in ("weight", "bias")]
+    out = ops.fcomb_mc_consensus(feat.permute(0, 2, 3, 1).contiguous().to(dev), z.to(dev), *w, want_logits=True)
+    assert (out["logits"].cpu() - ref).abs().max().item() < 5e-3 * 4.0
 
 
 @pytest.mark.parametrize("name", MC_CASES)
@@ -120,7 +144,7 @@ def test_sample_api_and_rng_stream():
     assert singles[0].shape == (2, 1, 32, 48)
     assert torch.allclose(m.z_prior_sample, zs, atol=1e-6)
     for s in range(3):
-        assert torch.allclose(singles[s], logits[s], atol=1e-5)
+        assert torch.allclose(singles[s], logits[s], atol=1e-4)
         assert torch.allclose(singles_t[s], logits[s], atol=1e-4)
     d = m.prior_latent_space
     assert d.base_dist.loc.shape == (2, 6) and d.rsample().shape == (2, 6) and d.log_prob(zs).shape == (2,)
