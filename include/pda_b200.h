@@ -104,6 +104,65 @@ int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
 int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training (backward) entry points.  They replace what torch.autograd runs behind loss.backward() in the step
+ * bodies punet_trainer.py:24-36 / mean_teacher_trainer.py:111-119 (cuDNN dgrad/wgrad, ATen elementwise backward).
+ * dgrad of conv3x3 is pda_conv3x3_bf16 itself, called with the rot180-packed weights and relu = 0.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Weight (+bias) gradient of conv3x3: dW[co][ci][ky][kx] = sum_p dZ[p][co] * X[p + tap][ci] on tcgen05 tensor cores
+ * (K = pixels; both operands read as MN-major straight from NHWC).  X = concat(src0, src1) as in the forward.
+ * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  scratch: fp32 [cout*9*(c0+c1)].  dw_oihw fp32 OIHW,
+ * dbias fp32 [cout] (may be NULL).  accumulate != 0 adds to dw/dbias instead of overwriting. */
+int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
+                           float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate, void* stream);
+
+/* dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): ReLU backward fused with the backward of the 2x2 average pool that
+ * consumes Y (unet_blocks.py:17,20).  NHWC bf16; dfull or dpool may be NULL; y == NULL skips the ReLU mask
+ * (plain AvgPool2d backward). */
+int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, int B, int H, int W, int C,
+                           void* stream);
+
+/* Backward of the bilinear x2 upsample (unet_blocks.py:51): dout (2h,2w) -> din (h,w), NHWC bf16. */
+int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream);
+
+/* First layer (cin 1 or 2) weight/bias gradient; out = forward output (for the ReLU mask), dout its gradient. */
+int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,
+                          int B, int H, int W, int cout, void* stream);
+
+/* Gaussian head: spatial mean [B][C] from the forward's stage-1 scratch, and the backward to the encoder output. */
+int pda_gauss_head_mean(const float* scratch, float* mean, int B, int P, int C, void* stream);
+int pda_gauss_head_bwd(const float* dmls, const float* w_head, const float* mean, const void* enc, float* dw,
+                       float* db, float* dmean_scratch, void* denc, int B, int P, int C, int latent, void* stream);
+
+/* d KL(q||p) / d (mu|log_sigma) of both distributions, given dkl [B]. */
+int pda_kl_diag_gauss_bwd(const float* q, const float* p, const float* dkl, float* dq, float* dp, int B, int latent,
+                          void* stream);
+
+/* Reconstruction loss of ProbabilisticUnet.elbo (probabilistic_unet.py:347-369): BCE-with-logits (dice = 0) or
+ * Dice-with-logits (dice = 1) of (logits * consm, segm * consm); consm fp32 or int64, both NULL = no mask.
+ * out2 = (sum, mean); stats3 is kept for the backward.  partial: double [3 * pda_recon_loss_blocks(n)]. */
+int pda_recon_loss_blocks(long long n);
+int pda_recon_loss_fwd(const float* logits, const float* segm, const float* consm_f32, const int64_t* consm_i64,
+                       long long n, int dice, double* partial, float* out2, float* stats3, void* stream);
+int pda_recon_loss_bwd(const float* logits, const float* segm, const float* consm_f32, const int64_t* consm_i64,
+                       long long n, int dice, const float* stats3, const float* gout2, float* dlogits, void* stream);
+
+/* l2_regularisation (utils.py:32-40): out = sum_t ||W_t||_2 over many tensors in two launches.
+ * table int64 [n_chunks][4] = (ptr, numel<=65536, tensor_index, 0);
+ * backward table = (w_ptr, byte offset of this chunk's gradient inside grad_base, numel, tensor_index): the gradients
+ * gout / ||W_t|| * W_t of all tensors are written into one flat fp32 buffer. */
+int pda_multi_tensor_l2norm_fwd(const int64_t* table, int n_chunks, int n_tensors, double* partial, float* norms,
+                                float* out, void* stream);
+int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const float* norms, const float* gout,
+                                void* grad_base, void* stream);
+
+/* Fcomb backward for one latent sample z [B][L]: dlogit [B][P] -> dfeat [B][P][64] bf16, parameter grads, dz [B][L].
+ * scratch: fp32 [64*64 + B*64]. */
+int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
+                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,19 @@ SIGNATURES = {
     "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
+    "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pda_upsample2x_bilinear_bwd_bf16": [_P, _P, _I, _I, _I, _I, _P],
+    "pda_conv3x3_first_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pda_gauss_head_mean": [_P, _P, _I, _I, _I, _P],
+    "pda_gauss_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pda_kl_diag_gauss_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "pda_recon_loss_blocks": [_c.c_longlong],
+    "pda_recon_loss_fwd": [_P, _P, _P, _P, _c.c_longlong, _I, _P, _P, _P, _P],
+    "pda_recon_loss_bwd": [_P, _P, _P, _P, _c.c_longlong, _I, _P, _P, _P, _P],
+    "pda_multi_tensor_l2norm_fwd": [_P, _I, _I, _P, _P, _P, _P],
+    "pda_multi_tensor_l2norm_bwd": [_P, _I, _P, _P, _P, _P],
+    "pda_fcomb_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None}
 

@@ -1,0 +1,838 @@
+// Backward / loss kernels of the PUNet training step that are not tensor-core GEMMs:
+// ReLU+pool backward, bilinear-upsample backward, first-layer weight gradient, Gaussian-head backward, KL backward,
+// reconstruction loss (Dice / BCE with consensus mask) forward+backward, multi-tensor L2 norm forward+backward,
+// Fcomb backward.  References are cited per kernel (paths relative to /root/reference/prob_utils).
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace pda {
+
+__device__ __forceinline__ void unpack8f(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+static inline int grid_cap(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ------------------------------------------------------------------------------------------------
+// dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): backward of ReLU (unet_blocks.py:20) and of the
+// AvgPool2d that consumes the block output (unet_blocks.py:17).  NHWC bf16; dFull / dPool may be NULL.
+// ------------------------------------------------------------------------------------------------
+__global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ dpool,
+                                     const uint4* __restrict__ y, uint4* __restrict__ dz, int B, int H, int W, int C8) {
+  const long long total = (long long)B * H * W * C8;
+  const int Hp = H >> 1, Wp = W >> 1;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    float g[8], a[8], yv[8];
+    if (dfull) {
+      unpack8f(__ldg(dfull + t), g);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    }
+    if (dpool) {
+      const int c = t % C8;
+      const long long pix = t / C8;
+      const int x = pix % W;
+      const int yy = (pix / W) % H;
+      const int b = pix / ((long long)W * H);
+      unpack8f(__ldg(dpool + (((long long)b * Hp + (yy >> 1)) * Wp + (x >> 1)) * C8 + c), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(0.25f, a[i], g[i]);
+    }
+    if (y) {  // y == nullptr: plain average-pool backward, no ReLU mask
+      unpack8f(__ldg(y + t), yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
+    }
+    dz[t] = pack8f(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of F.interpolate(bilinear, x2, align_corners=True) (unet_blocks.py:51), gather form:
+// every input pixel sums the output-gradient pixels whose footprint contains it (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int B, int h, int w,
+                                      int C8) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)B * h * w * C8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    const long long pix = t / C8;
+    const int x = pix % w;
+    const int y = (pix / w) % h;
+    const int b = pix / ((long long)w * h);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // candidate output rows / columns: source coordinate rh*Y lies in (y-1, y+1)
+    const int Y0 = max(0, 2 * y - 2), Y1 = min(Ho - 1, 2 * y + 3);
+    const int X0 = max(0, 2 * x - 2), X1 = min(Wo - 1, 2 * x + 3);
+    for (int Y = Y0; Y <= Y1; ++Y) {
+      const float sy = rh * Y;
+      const int y1 = (int)sy;
+      const int yp = (y1 < h - 1) ? 1 : 0;
+      const float ly1 = sy - y1, ly0 = 1.f - ly1;
+      float wy = 0.f;
+      if (y1 == y) wy += ly0;
+      if (y1 + yp == y) wy += ly1;
+      if (wy == 0.f) continue;
+      for (int X = X0; X <= X1; ++X) {
+        const float sx = rw * X;
+        const int x1 = (int)sx;
+        const int xp = (x1 < w - 1) ? 1 : 0;
+        const float lx1 = sx - x1, lx0 = 1.f - lx1;
+        float wx = 0.f;
+        if (x1 == x) wx += lx0;
+        if (x1 + xp == x) wx += lx1;
+        if (wx == 0.f) continue;
+        float g[8];
+        unpack8f(__ldg(dout + (((long long)b * Ho + Y) * Wo + X) * C8 + c), g);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, g[i], acc[i]);
+      }
+    }
+    din[t] = pack8f(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer (cin 1 or 2) weight / bias gradient: dW[co][ci][tap] = sum_p dZ[p][co] * x_ci[p + tap],
+// dZ = dOut * (out > 0).  Mirrors conv_first_kernel: thread owns 8 output channels, accumulates in registers.
+// ------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const __nv_bfloat16* __restrict__ out,
+                      const __nv_bfloat16* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db, int B,
+                      int H, int W, int cout) {
+  extern __shared__ float red[];  // [cout * CIN * 9 + cout]
+  const int groups = cout >> 3;
+  const int g = threadIdx.x % groups;
+  const int lanes_px = blockDim.x / groups;
+  const int lpx = threadIdx.x / groups;
+  const int nred = cout * CIN * 9 + cout;
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[CIN][9][8], accb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    accb[j] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[ci][t][j] = 0.f;
+  }
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * lanes_px + lpx; pix < npix; pix += (long long)gridDim.x * lanes_px) {
+    const int x = pix % W;
+    const int y = (pix / W) % H;
+    const long long img_off = (pix / ((long long)W * H)) * H * W;
+    float dz[8], yv[8];
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(dout + pix * cout + g * 8)), dz);
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(out + pix * cout + g * 8)), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dz[j] = yv[j] > 0.f ? dz[j] : 0.f;
+      accb[j] += dz[j];
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* xp = (ci == 0 ? x0 : x1) + img_off;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + kx - 1;
+          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (long long)yy * W + xx) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[ci][ky * 3 + kx][j] = fmaf(v, dz[j], acc[ci][ky * 3 + kx][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int co = g * 8 + j;
+    atomicAdd(&red[cout * CIN * 9 + co], accb[j]);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&red[(co * CIN + ci) * 9 + t], acc[ci][t][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) atomicAdd(dw + i, red[i]);
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(db + i, red[cout * CIN * 9 + i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian head backward (probabilistic_unet.py:126-130): d(mu|log_sigma)[B][2L] ->
+//   dW[o][c] = sum_b d[b][o] * mean[b][c],  db[o] = sum_b d[b][o],  dmean[b][c] = sum_o d[b][o] * W[o][c]
+//   dEnc[b][p][c] = dmean[b][c] / P * (enc > 0)   (ReLU of the last encoder conv folded in)
+// ------------------------------------------------------------------------------------------------
+__global__ void gauss_head_bwd_small_kernel(const float* __restrict__ dmls, const float* __restrict__ w,
+                                            const float* __restrict__ mean, float* __restrict__ dw,
+                                            float* __restrict__ db, float* __restrict__ dmean, int B, int C, int nout,
+                                            float inv_p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nout * C) {
+    const int o = i / C, c = i % C;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dmls[b * nout + o], mean[(long long)b * C + c], s);
+    dw[i] = s;
+  }
+  if (i < nout) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dmls[b * nout + i];
+    db[i] = s;
+  }
+  if (i < B * C) {
+    const int b = i / C, c = i % C;
+    float s = 0.f;
+    for (int o = 0; o < nout; ++o) s = fmaf(dmls[b * nout + o], w[(long long)o * C + c], s);
+    dmean[i] = s * inv_p;
+  }
+}
+
+__global__ void gauss_head_bwd_enc_kernel(const float* __restrict__ dmean, const uint4* __restrict__ enc,
+                                          uint4* __restrict__ denc, int B, int P, int C8) {
+  const long long total = (long long)B * P * C8;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = t % C8;
+    const int b = t / ((long long)P * C8);
+    float e[8], g[8];
+    unpack8f(__ldg(enc + t), e);
+    const float* dm = dmean + (long long)b * C8 * 8 + c * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = e[i] > 0.f ? dm[i] : 0.f;
+    denc[t] = pack8f(g);
+  }
+}
+
+// mean over pixels [B][C] from the stage-1 partial sums of the forward (kept for backward)
+__global__ void mean_from_partials_kernel(const float* __restrict__ partial, float* __restrict__ mean, int C, int nchunk,
+                                          float inv_p, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / C, c = i % C;
+  float s = 0.f;
+  for (int k = 0; k < nchunk; ++k) s += partial[((long long)b * nchunk + k) * C + c];
+  mean[i] = s * inv_p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KL(q||p) backward for diagonal Gaussians parametrised by (mu | log_sigma) (probabilistic_unet.py:332)
+// ------------------------------------------------------------------------------------------------
+__global__ void kl_bwd_kernel(const float* __restrict__ q, const float* __restrict__ p, const float* __restrict__ dkl,
+                              float* __restrict__ dq, float* __restrict__ dp, int B, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  const int b = i / L, d = i % L;
+  const float g = dkl[b];
+  const float mq = q[b * 2 * L + d], lq = q[b * 2 * L + L + d];
+  const float mp = p[b * 2 * L + d], lp = p[b * 2 * L + L + d];
+  const float sp = expf(lp);
+  const float r = expf(lq) / sp, vr = r * r;
+  const float dm = (mq - mp) / sp;
+  // kl = 0.5 * (vr + dm^2 - 1 - log vr);  vr = exp(2 lq - 2 lp)
+  dq[b * 2 * L + d] = g * dm / sp;
+  dq[b * 2 * L + L + d] = g * (vr - 1.f);
+  dp[b * 2 * L + d] = -g * dm / sp;
+  dp[b * 2 * L + L + d] = g * (1.f - vr - dm * dm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reconstruction loss (probabilistic_unet.py:347-369).  x = logit * c, t = segm * c (c = consensus, optional).
+//   BCE : l = (1 - t) x - log_sigmoid(x)  (ATen binary_cross_entropy_with_logits), outputs sum and mean
+//   Dice: 1 - 2 sum(p t) / max(sum p^2 + sum t^2, 1e-7), p = sigmoid(x)   (torch_em DiceLossWithLogits)
+// stats[0..2] = (S0, S1, S2): BCE -> (sum l, -, -);  Dice -> (sum p t, sum p^2, sum t^2)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float consm_at(const float* cf, const long long* ci, long long i) {
+  return cf ? cf[i] : (ci ? (float)ci[i] : 1.f);
+}
+
+__global__ void __launch_bounds__(256)
+recon_loss_partial_kernel(const float* __restrict__ logits, const float* __restrict__ segm, const float* __restrict__ cf,
+                          const long long* __restrict__ ci, long long n, int dice, double* __restrict__ partial) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = consm_at(cf, ci, i);
+    const float x = logits[i] * c, t = segm[i] * c;
+    if (dice) {
+      const float p = 1.0f / (1.0f + expf(-x));
+      s0 += (double)(p * t);
+      s1 += (double)(p * p);
+      s2 += (double)(t * t);
+    } else {
+      const float ls = fminf(x, 0.f) - log1pf(expf(-fabsf(x)));
+      s0 += (double)((1.f - t) * x - ls);
+    }
+  }
+  __shared__ double sh[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane == 0) {
+    sh[0][warp] = s0;
+    sh[1][warp] = s1;
+    sh[2][warp] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += sh[threadIdx.x][k];
+    partial[blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void recon_loss_final_kernel(const double* __restrict__ partial, int nblocks, long long n, int dice,
+                                        float* __restrict__ out, float* __restrict__ stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nblocks; ++k) {
+    s0 += partial[3 * k];
+    s1 += partial[3 * k + 1];
+    s2 += partial[3 * k + 2];
+  }
+  stats[0] = (float)s0;
+  stats[1] = (float)s1;
+  stats[2] = (float)s2;
+  if (dice) {
+    const float den = fmaxf((float)(s1 + s2), 1e-7f);
+    const float loss = 1.f - 2.f * ((float)s0 / den);
+    out[0] = loss;  // sum of a scalar
+    out[1] = loss;  // mean of a scalar
+  } else {
+    out[0] = (float)s0;
+    out[1] = (float)(s0 / (double)n);
+  }
+}
+
+__global__ void recon_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ segm,
+                                      const float* __restrict__ cf, const long long* __restrict__ ci, long long n,
+                                      int dice, const float* __restrict__ stats, const float* __restrict__ gout,
+                                      float* __restrict__ dlogits) {
+  // gout[0] = dL/d(sum), gout[1] = dL/d(mean)
+  const float gs = gout[0], gm = gout[1];
+  float k_num = 0.f, k_den = 0.f;
+  if (dice) {
+    const float num = stats[0], den_raw = stats[1] + stats[2];
+    const float den = fmaxf(den_raw, 1e-7f);
+    // loss = 1 - 2 num / den ; dloss/dp_i = -2 (t_i / den - num * 2 p_i / den^2) (second term only if not clamped)
+    k_num = -2.f / den;
+    k_den = (den_raw > 1e-7f) ? 4.f * num / (den * den) : 0.f;
+  }
+  const float g_bce = gs + gm / (float)n;
+  const float g_dice = gs + gm;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = consm_at(cf, ci, i);
+    const float x = logits[i] * c, t = segm[i] * c;
+    const float p = 1.0f / (1.0f + expf(-x));
+    float d;
+    if (dice)
+      d = g_dice * (k_num * t + k_den * p) * p * (1.f - p);
+    else
+      d = g_bce * (p - t);
+    dlogits[i] = d * c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-tensor L2 norm (utils.py:32-40): out = sum over tensors of ||W_t||_2
+// table rows: (ptr, numel, tensor_index, unused), chunks of <= 65536 elements
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_partial_kernel(const long long* __restrict__ table, double* __restrict__ partial) {
+  const long long* e = table + 4LL * blockIdx.x;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  const int n = (int)e[1];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = w[i];
+    s += (double)v * (double)v;
+  }
+  __shared__ double sh[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sh[k];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void l2_final_kernel(const long long* __restrict__ table, const double* __restrict__ partial, int n_chunks,
+                                int n_tensors, float* __restrict__ norms, float* __restrict__ out) {
+  __shared__ float total;
+  if (threadIdx.x == 0) total = 0.f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tensors; t += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < n_chunks; ++k)
+      if ((int)table[4LL * k + 2] == t) s += partial[k];
+    norms[t] = (float)sqrt(s);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;  // same left-to-right fp32 sum as the reference's python loop
+    for (int t = 0; t < n_tensors; ++t) acc += norms[t];
+    out[0] = acc;
+  }
+}
+
+// grad table rows: (w_ptr, byte offset of the gradient inside grad_base, numel, tensor_index)
+__global__ void __launch_bounds__(256)
+l2_bwd_kernel(const long long* __restrict__ table, const float* __restrict__ norms, const float* __restrict__ gout,
+              char* __restrict__ grad_base) {
+  const long long* e = table + 4LL * blockIdx.x;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  float* g = reinterpret_cast<float*>(grad_base + e[1]);
+  const int n = (int)e[2];
+  const float nrm = norms[(int)e[3]];
+  const float k = nrm > 0.f ? gout[0] / nrm : 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = k * w[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fcomb backward for ONE latent sample (the training form, probabilistic_unet.py:200-214 under autograd).
+// fp32 CUDA cores.  Persistent CTAs of 128 threads; one pixel per thread per 128-pixel tile of one image.
+//   recompute: a1 = relu(W1f F + bz), h2 = W2 a1 + b2, a2 = relu(h2)
+//   backward : da2 = g w3 (h2>0); da1 = W2^T da2 (a1>0); dF = W1f^T da1
+//   weight grads accumulate in registers across the CTA's tiles (each thread owns a 4x8 block of dW2 and of
+//   dW1f), column sums through shared-memory tiles; one atomicAdd pass per CTA at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int FB = 64;
+constexpr int FB_LD = 68;  // padded row length of the shared tiles (floats): 16-byte aligned rows, conflict-free
+
+__global__ void __launch_bounds__(128, 1)
+fcomb_bwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                 const float* __restrict__ w3, const float* __restrict__ dlogit, int P, int L, int B, int tiles_per_img,
+                 int num_tiles, __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw1f, float* __restrict__ dw2,
+                 float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3, float* __restrict__ dbz) {
+  extern __shared__ __align__(16) float sm[];
+  float* w1s = sm;                       // [64][64]
+  float* w2s = w1s + FB * FB;            // [64][64]
+  float* tF = w2s + FB * FB;             // [128][FB_LD]
+  float* tA1 = tF + 128 * FB_LD;
+  float* tD2 = tA1 + 128 * FB_LD;
+  float* tD1 = tD2 + 128 * FB_LD;
+  float* vec = tD1 + 128 * FB_LD;        // bz[64] b2[64] w3[64] dw3acc[64] db3acc[1]
+  float* bzs = vec, *b2s = vec + 64, *w3s = vec + 128, *dw3acc = vec + 192, *db3acc = vec + 256;
+  const int tid = threadIdx.x;
+  const int kin = FB + L;
+  for (int i = tid; i < FB * FB; i += 128) {
+    w1s[i] = w1[(i / FB) * kin + (i % FB)];
+    w2s[i] = w2[i];
+  }
+  if (tid < 64) {
+    b2s[tid] = b2[tid];
+    w3s[tid] = w3[tid];
+    dw3acc[tid] = 0.f;
+  }
+  if (tid == 0) db3acc[0] = 0.f;
+  // this thread's 4x8 block of each 64x64 weight gradient
+  const int jb = (tid >> 3) * 4, ib = (tid & 7) * 8;
+  float accW2[4][8], accW1[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) accW2[a][c] = accW1[a][c] = 0.f;
+  float accb2 = 0.f;  // column tid (tid < 64) of db2
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img;
+    const int p0 = (tile - b * tiles_per_img) * 128;
+    if (tid < 64) {
+      float acc = b1[tid];
+      for (int d = 0; d < L; ++d) acc = fmaf(w1[tid * kin + FB + d], z[b * L + d], acc);
+      bzs[tid] = acc;
+    }
+    __syncthreads();
+    const int pix = p0 + tid;
+    const bool valid = pix < P;
+    const size_t gp = (size_t)b * P + pix;
+    float a1[FB];
+    {
+      float f[FB];
+      if (valid) {
+        const uint4* src = reinterpret_cast<const uint4*>(feat + gp * FB);
+#pragma unroll
+        for (int k = 0; k < FB / 8; ++k) {
+          float t8[8];
+          unpack8f(__ldg(src + k), t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[8 * k + i] = t8[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < FB; ++i) f[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < FB; i += 4)
+        *reinterpret_cast<float4*>(tF + tid * FB_LD + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+#pragma unroll 2
+      for (int j = 0; j < FB; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(w1s + j * FB);
+        float s0 = bzs[j], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < FB / 4; ++i) {
+          const float4 w = wr[i];
+          s0 = fmaf(w.x, f[4 * i], s0);
+          s1 = fmaf(w.y, f[4 * i + 1], s1);
+          s2 = fmaf(w.z, f[4 * i + 2], s2);
+          s3 = fmaf(w.w, f[4 * i + 3], s3);
+        }
+        tA1[tid * FB_LD + j] = fmaxf((s0 + s1) + (s2 + s3), 0.f);  // dynamic index: through shared memory
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < FB; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(tA1 + tid * FB_LD + i);
+      a1[i] = v.x;
+      a1[i + 1] = v.y;
+      a1[i + 2] = v.z;
+      a1[i + 3] = v.w;
+    }
+    const float g = valid ? dlogit[gp] : 0.f;
+    float da1[FB];
+#pragma unroll
+    for (int i = 0; i < FB; ++i) da1[i] = 0.f;
+    float dw3_part = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < FB; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(w2s + j * FB);
+      float s0 = b2s[j], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < FB / 4; ++i) {
+        const float4 w = wr[i];
+        s0 = fmaf(w.x, a1[4 * i], s0);
+        s1 = fmaf(w.y, a1[4 * i + 1], s1);
+        s2 = fmaf(w.z, a1[4 * i + 2], s2);
+        s3 = fmaf(w.w, a1[4 * i + 3], s3);
+      }
+      const float h2 = (s0 + s1) + (s2 + s3);
+      const float d2 = h2 > 0.f ? g * w3s[j] : 0.f;
+      tD2[tid * FB_LD + j] = d2;
+      // dW3[j] = sum_p g * relu(h2): warp reduce, one shared atomic per warp
+      dw3_part = g * fmaxf(h2, 0.f);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) dw3_part += __shfl_xor_sync(0xffffffffu, dw3_part, d);
+      if ((tid & 31) == 0) atomicAdd(&dw3acc[j], dw3_part);
+#pragma unroll
+      for (int i = 0; i < FB / 4; ++i) {
+        const float4 w = wr[i];
+        da1[4 * i] = fmaf(w.x, d2, da1[4 * i]);
+        da1[4 * i + 1] = fmaf(w.y, d2, da1[4 * i + 1]);
+        da1[4 * i + 2] = fmaf(w.z, d2, da1[4 * i + 2]);
+        da1[4 * i + 3] = fmaf(w.w, d2, da1[4 * i + 3]);
+      }
+    }
+    {
+      float gsum = g;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, d);
+      if ((tid & 31) == 0) atomicAdd(db3acc, gsum);
+    }
+#pragma unroll
+    for (int i = 0; i < FB; ++i) da1[i] = a1[i] > 0.f ? da1[i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < FB; i += 4)
+      *reinterpret_cast<float4*>(tD1 + tid * FB_LD + i) = make_float4(da1[i], da1[i + 1], da1[i + 2], da1[i + 3]);
+    // dF = W1f^T da1 (a1 registers are dead now: reuse as the accumulator)
+#pragma unroll
+    for (int i = 0; i < FB; ++i) a1[i] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < FB; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(w1s + j * FB);
+      const float d = tD1[tid * FB_LD + j];
+#pragma unroll
+      for (int i = 0; i < FB / 4; ++i) {
+        const float4 w = wr[i];
+        a1[4 * i] = fmaf(w.x, d, a1[4 * i]);
+        a1[4 * i + 1] = fmaf(w.y, d, a1[4 * i + 1]);
+        a1[4 * i + 2] = fmaf(w.z, d, a1[4 * i + 2]);
+        a1[4 * i + 3] = fmaf(w.w, d, a1[4 * i + 3]);
+      }
+    }
+    if (valid) {
+      uint4* dst = reinterpret_cast<uint4*>(dfeat + gp * FB);
+#pragma unroll
+      for (int k = 0; k < FB / 8; ++k) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = a1[8 * k + i];
+        dst[k] = pack8f(t8);
+      }
+    }
+    __syncthreads();
+    // weight-gradient partial sums over the tile's 128 pixels
+#pragma unroll 2
+    for (int p = 0; p < 128; ++p) {
+      const float4 d2 = *reinterpret_cast<const float4*>(tD2 + p * FB_LD + jb);
+      const float4 d1 = *reinterpret_cast<const float4*>(tD1 + p * FB_LD + jb);
+      const float4 aa = *reinterpret_cast<const float4*>(tA1 + p * FB_LD + ib);
+      const float4 ab = *reinterpret_cast<const float4*>(tA1 + p * FB_LD + ib + 4);
+      const float4 fa = *reinterpret_cast<const float4*>(tF + p * FB_LD + ib);
+      const float4 fb = *reinterpret_cast<const float4*>(tF + p * FB_LD + ib + 4);
+      const float d2v[4] = {d2.x, d2.y, d2.z, d2.w}, d1v[4] = {d1.x, d1.y, d1.z, d1.w};
+      const float av[8] = {aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w};
+      const float fv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          accW2[a][c] = fmaf(d2v[a], av[c], accW2[a][c]);
+          accW1[a][c] = fmaf(d1v[a], fv[c], accW1[a][c]);
+        }
+    }
+    if (tid < 64) {
+      float s2 = 0.f, s1 = 0.f;
+      for (int p = 0; p < 128; ++p) {
+        s2 += tD2[p * FB_LD + tid];
+        s1 += tD1[p * FB_LD + tid];
+      }
+      accb2 += s2;
+      atomicAdd(dbz + b * FB + tid, s1);  // per-image column sum of da1
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      atomicAdd(dw2 + (jb + a) * FB + ib + c, accW2[a][c]);
+      atomicAdd(dw1f + (jb + a) * FB + ib + c, accW1[a][c]);
+    }
+  if (tid < 64) {
+    atomicAdd(db2 + tid, accb2);
+    atomicAdd(dw3 + tid, dw3acc[tid]);
+  }
+  if (tid == 0) atomicAdd(db3, db3acc[0]);
+}
+
+// dbz [B][64] -> db1[64], dW1z[64][L] (written into the full dW1 [64][64+L]), dz[B][L]; also copies dW1f into dW1
+__global__ void fcomb_bwd_finish_kernel(const float* __restrict__ dbz, const float* __restrict__ dw1f,
+                                        const float* __restrict__ w1, const float* __restrict__ z,
+                                        float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dz, int B,
+                                        int L) {
+  const int kin = FB + L;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FB * FB; i += blockDim.x) dw1[(i / FB) * kin + (i % FB)] = dw1f[i];
+  for (int i = tid; i < FB; i += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dbz[b * FB + i];
+    db1[i] = s;
+  }
+  for (int i = tid; i < FB * L; i += blockDim.x) {
+    const int j = i / L, d = i % L;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dbz[b * FB + j], z[b * L + d], s);
+    dw1[j * kin + FB + d] = s;
+  }
+  for (int i = tid; i < B * L; i += blockDim.x) {
+    const int b = i / L, d = i % L;
+    float s = 0.f;
+    for (int j = 0; j < FB; ++j) s = fmaf(w1[j * kin + FB + d], dbz[b * FB + j], s);
+    dz[i] = s;
+  }
+}
+
+}  // namespace pda
+
+using namespace pda;
+#define ST(s) ((cudaStream_t)(s))
+#define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA)
+
+extern "C" {
+
+int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, int B, int H, int W, int C,
+                           void* stream) {
+  if (!dz || (!dfull && !dpool)) return PDA_ERR_ARG;
+  if ((C & 7) || B <= 0 || (dpool && ((H & 1) || (W & 1)))) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * H * W * (C / 8);
+  PDA_COUNT(1);
+  relu_pool_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
+      static_cast<const uint4*>(dfull), static_cast<const uint4*>(dpool), static_cast<const uint4*>(y),
+      static_cast<uint4*>(dz), B, H, W, C / 8);
+  return LAUNCH_OK();
+}
+
+int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream) {
+  if (!dout || !din) return PDA_ERR_ARG;
+  if ((C & 7) || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
+  const long long total = (long long)B * h * w * (C / 8);
+  PDA_COUNT(1);
+  upsample2x_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(dout),
+                                                                      static_cast<uint4*>(din), B, h, w, C / 8);
+  return LAUNCH_OK();
+}
+
+int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,
+                          int B, int H, int W, int cout, void* stream) {
+  if (!x0 || !out || !dout || !dw || !db) return PDA_ERR_ARG;
+  const int groups = cout >> 3;
+  if (cout <= 0 || (cout & 7) || 256 % groups) return PDA_ERR_SHAPE;
+  const int cin = x1 ? 2 : 1;
+  cudaStream_t st = ST(stream);
+  if (cudaMemsetAsync(dw, 0, sizeof(float) * cout * cin * 9, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(db, 0, sizeof(float) * cout, st) != cudaSuccess) return PDA_ERR_CUDA;
+  const size_t smem = sizeof(float) * (cout * cin * 9 + cout);
+  const long long total = (long long)B * H * W * groups;
+  const int grid = grid_cap(total, 256, 148 * 2);
+  PDA_COUNT(1);
+  if (x1)
+    conv_first_bwd_kernel<2><<<grid, 256, smem, st>>>(x0, x1, static_cast<const __nv_bfloat16*>(out),
+                                                      static_cast<const __nv_bfloat16*>(dout), dw, db, B, H, W, cout);
+  else
+    conv_first_bwd_kernel<1><<<grid, 256, smem, st>>>(x0, x1, static_cast<const __nv_bfloat16*>(out),
+                                                      static_cast<const __nv_bfloat16*>(dout), dw, db, B, H, W, cout);
+  return LAUNCH_OK();
+}
+
+int pda_gauss_head_mean(const float* scratch, float* mean, int B, int P, int C, void* stream) {
+  if (!scratch || !mean) return PDA_ERR_ARG;
+  const int nchunk = pda_gauss_head_scratch_rows(P);
+  const int total = B * C;
+  PDA_COUNT(1);
+  mean_from_partials_kernel<<<(total + 255) / 256, 256, 0, ST(stream)>>>(scratch, mean, C, nchunk, 1.f / (float)P,
+                                                                         total);
+  return LAUNCH_OK();
+}
+
+int pda_gauss_head_bwd(const float* dmls, const float* w_head, const float* mean, const void* enc, float* dw,
+                       float* db, float* dmean_scratch, void* denc, int B, int P, int C, int latent, void* stream) {
+  if (!dmls || !w_head || !mean || !enc || !dw || !db || !dmean_scratch || !denc) return PDA_ERR_ARG;
+  if ((C & 7) || B <= 0 || P <= 0) return PDA_ERR_SHAPE;
+  const int nout = 2 * latent;
+  int n = nout * C;
+  if (B * C > n) n = B * C;
+  PDA_COUNT(2);
+  gauss_head_bwd_small_kernel<<<(n + 255) / 256, 256, 0, ST(stream)>>>(dmls, w_head, mean, dw, db, dmean_scratch, B, C,
+                                                                       nout, 1.f / (float)P);
+  const long long total = (long long)B * P * (C / 8);
+  gauss_head_bwd_enc_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
+      dmean_scratch, static_cast<const uint4*>(enc), static_cast<uint4*>(denc), B, P, C / 8);
+  return LAUNCH_OK();
+}
+
+int pda_kl_diag_gauss_bwd(const float* q, const float* p, const float* dkl, float* dq, float* dp, int B, int latent,
+                          void* stream) {
+  if (!q || !p || !dkl || !dq || !dp) return PDA_ERR_ARG;
+  const int n = B * latent;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
+  kl_bwd_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(q, p, dkl, dq, dp, B, latent);
+  return LAUNCH_OK();
+}
+
+int pda_recon_loss_blocks(long long n) { return grid_cap(n, 256, 148 * 4); }
+
+int pda_recon_loss_fwd(const float* logits, const float* segm, const float* consm_f32, const int64_t* consm_i64,
+                       long long n, int dice, double* partial, float* out2, float* stats3, void* stream) {
+  if (!logits || !segm || !partial || !out2 || !stats3) return PDA_ERR_ARG;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  const int blocks = pda_recon_loss_blocks(n);
+  PDA_COUNT(2);
+  recon_loss_partial_kernel<<<blocks, 256, 0, ST(stream)>>>(logits, segm, consm_f32,
+                                                            reinterpret_cast<const long long*>(consm_i64), n, dice,
+                                                            partial);
+  recon_loss_final_kernel<<<1, 32, 0, ST(stream)>>>(partial, blocks, n, dice, out2, stats3);
+  return LAUNCH_OK();
+}
+
+int pda_recon_loss_bwd(const float* logits, const float* segm, const float* consm_f32, const int64_t* consm_i64,
+                       long long n, int dice, const float* stats3, const float* gout2, float* dlogits, void* stream) {
+  if (!logits || !segm || !stats3 || !gout2 || !dlogits) return PDA_ERR_ARG;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
+  recon_loss_bwd_kernel<<<grid_cap(n, 256), 256, 0, ST(stream)>>>(
+      logits, segm, consm_f32, reinterpret_cast<const long long*>(consm_i64), n, dice, stats3, gout2, dlogits);
+  return LAUNCH_OK();
+}
+
+int pda_multi_tensor_l2norm_fwd(const int64_t* table, int n_chunks, int n_tensors, double* partial, float* norms,
+                                float* out, void* stream) {
+  if (!table || !partial || !norms || !out) return PDA_ERR_ARG;
+  if (n_chunks <= 0 || n_tensors <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(2);
+  l2_partial_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), partial);
+  l2_final_kernel<<<1, 128, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), partial, n_chunks, n_tensors,
+                                             norms, out);
+  return LAUNCH_OK();
+}
+
+int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const float* norms, const float* gout,
+                                void* grad_base, void* stream) {
+  if (!grad_table || !norms || !gout || !grad_base) return PDA_ERR_ARG;
+  if (n_chunks <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
+  l2_bwd_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(grad_table), norms, gout,
+                                                  static_cast<char*>(grad_base));
+  return LAUNCH_OK();
+}
+
+int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
+                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream) {
+  // scratch: fp32, at least 64*64 + B*64 elements (dW1f accumulator, per-image column sums)
+  if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !dlogit || !dfeat || !dw1 || !db1 || !dw2 || !db2 || !dw3 ||
+      !db3 || !dz || !scratch)
+    return PDA_ERR_ARG;
+  if (B <= 0 || P <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  cudaStream_t st = ST(stream);
+  float* dw1f = scratch;
+  float* dbz = scratch + FB * FB;
+  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (FB * FB + (size_t)B * FB), st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(dw2, 0, sizeof(float) * FB * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(db2, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(dw3, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(db3, 0, sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
+  const int smem = sizeof(float) * (2 * FB * FB + 4 * 128 * FB_LD + 320);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(fcomb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PDA_ERR_CUDA;
+    configured = true;
+  }
+  const int tiles_per_img = (P + 127) / 128;
+  const long long num_tiles = (long long)tiles_per_img * B;
+  if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
+  const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
+  PDA_COUNT(2);
+  fcomb_bwd_kernel<<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2, b2, w3, dlogit, P,
+                                            latent, B, tiles_per_img, (int)num_tiles,
+                                            static_cast<__nv_bfloat16*>(dfeat), dw1f, dw2, db2, dw3, db3, dbz);
+  fcomb_bwd_finish_kernel<<<1, 256, 0, st>>>(dbz, dw1f, w1, z, dw1, db1, dz, B, latent);
+  return LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -193,3 +193,202 @@ def multi_tensor_ema(table, momentum):
     lib = _lib.load()
     _lib.check(lib.pda_multi_tensor_ema(table.data_ptr(), table.shape[0], float(momentum), _stream()),
                "multi_tensor_ema")
+
+
+# ------------------------------------------------------------------------------------------------
+# training (backward) wrappers
+# ------------------------------------------------------------------------------------------------
+def conv3x3_wgrad(src0, src1, dz, want_bias=True):
+    """dW (cout, c0+c1, 3, 3) fp32 and db (cout,) of conv3x3 from its NHWC bf16 inputs and dZ."""
+    _need_cuda(src0, src1, dz)
+    lib = _lib.load()
+    B, H, W, c0 = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    cout = dz.shape[3]
+    assert dz.shape[:3] == src0.shape[:3] and dz.is_contiguous() and src0.is_contiguous()
+    dev = src0.device
+    scratch = torch.empty(cout * 9 * (c0 + c1), dtype=torch.float32, device=dev)
+    dw = torch.empty((cout, c0 + c1, 3, 3), dtype=torch.float32, device=dev)
+    db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
+    with _Timed("wgrad3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
+        rc = lib.pda_conv3x3_wgrad_bf16(src0.data_ptr(), c0, _ptr(src1), c1, dz.data_ptr(), scratch.data_ptr(),
+                                        dw.data_ptr(), _ptr(db), B, H, W, cout, 0, _stream())
+    _lib.check(rc, "conv3x3_wgrad")
+    return dw, db
+
+
+def relu_pool_bwd(dfull, dpool, y, shape=None):
+    """dZ = (dFull + 0.25 * up2(dPool)) * (y > 0); y None = no ReLU mask.  NHWC bf16."""
+    _need_cuda(dfull, dpool, y)
+    lib = _lib.load()
+    ref = y if y is not None else dfull
+    B, H, W, C = ref.shape if ref is not None else shape
+    dev = (ref if ref is not None else dpool).device
+    dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.pda_relu_pool_bwd_bf16(_ptr(dfull), _ptr(dpool), _ptr(y), dz.data_ptr(), B, H, W, C, _stream()),
+               "relu_pool_bwd")
+    return dz
+
+
+def upsample2x_bwd(dout):
+    _need_cuda(dout)
+    lib = _lib.load()
+    B, H2, W2, C = dout.shape
+    din = torch.empty((B, H2 // 2, W2 // 2, C), dtype=torch.bfloat16, device=dout.device)
+    _lib.check(lib.pda_upsample2x_bilinear_bwd_bf16(dout.data_ptr(), din.data_ptr(), B, H2 // 2, W2 // 2, C,
+                                                    _stream()), "upsample2x_bwd")
+    return din
+
+
+def conv3x3_first_bwd(x0, x1, out, dout):
+    _need_cuda(x0, x1, out, dout)
+    lib = _lib.load()
+    B, H, W, cout = out.shape
+    cin = 1 if x1 is None else 2
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=out.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=out.device)
+    _lib.check(lib.pda_conv3x3_first_bwd(x0.data_ptr(), _ptr(x1), out.data_ptr(), dout.data_ptr(), dw.data_ptr(),
+                                         db.data_ptr(), B, H, W, cout, _stream()), "conv3x3_first_bwd")
+    return dw, db
+
+
+def gauss_head_fwd_train(enc, w_head, b_head, latent):
+    """Like gauss_head but also returns the stage-1 partial sums needed by the backward."""
+    _need_cuda(enc, w_head, b_head)
+    lib = _lib.load()
+    B, h, w, C = enc.shape
+    P = h * w
+    rows = lib.pda_gauss_head_scratch_rows(P)
+    scratch = torch.empty((B, rows, C), dtype=torch.float32, device=enc.device)
+    out = torch.empty((B, 2 * latent), dtype=torch.float32, device=enc.device)
+    _lib.check(lib.pda_gauss_head(enc.data_ptr(), w_head.data_ptr(), b_head.data_ptr(), scratch.data_ptr(),
+                                  out.data_ptr(), B, P, C, latent, _stream()), "gauss_head")
+    return out, scratch
+
+
+def gauss_head_bwd(dmls, w_head, scratch, enc, latent):
+    _need_cuda(dmls, w_head, scratch, enc)
+    lib = _lib.load()
+    B, h, w, C = enc.shape
+    P = h * w
+    dev = enc.device
+    mean = torch.empty((B, C), dtype=torch.float32, device=dev)
+    _lib.check(lib.pda_gauss_head_mean(scratch.data_ptr(), mean.data_ptr(), B, P, C, _stream()), "gauss_head_mean")
+    dw = torch.empty((2 * latent, C, 1, 1), dtype=torch.float32, device=dev)
+    db = torch.empty((2 * latent,), dtype=torch.float32, device=dev)
+    dmean = torch.empty((B, C), dtype=torch.float32, device=dev)
+    denc = torch.empty_like(enc)
+    dmls = dmls.contiguous().float()
+    _lib.check(lib.pda_gauss_head_bwd(dmls.data_ptr(), w_head.data_ptr(), mean.data_ptr(), enc.data_ptr(),
+                                      dw.data_ptr(), db.data_ptr(), dmean.data_ptr(), denc.data_ptr(), B, P, C,
+                                      latent, _stream()), "gauss_head_bwd")
+    return denc, dw, db
+
+
+def kl_diag_gauss_bwd(mls_q, mls_p, dkl):
+    _need_cuda(mls_q, mls_p, dkl)
+    lib = _lib.load()
+    B, L2 = mls_q.shape
+    dq, dp = torch.empty_like(mls_q), torch.empty_like(mls_p)
+    dkl = dkl.contiguous().float()
+    _lib.check(lib.pda_kl_diag_gauss_bwd(mls_q.data_ptr(), mls_p.data_ptr(), dkl.data_ptr(), dq.data_ptr(),
+                                         dp.data_ptr(), B, L2 // 2, _stream()), "kl_diag_gauss_bwd")
+    return dq, dp
+
+
+def _consm_ptrs(consm):
+    if consm is None:
+        return 0, 0
+    if consm.dtype == torch.int64:
+        return 0, consm.data_ptr()
+    assert consm.dtype == torch.float32
+    return consm.data_ptr(), 0
+
+
+def recon_loss_fwd(logits, segm, consm, dice):
+    """-> out2 (sum, mean) fp32, stats3 fp32 (kept for backward)."""
+    _need_cuda(logits, segm, consm)
+    lib = _lib.load()
+    n = logits.numel()
+    assert segm.numel() == n and (consm is None or consm.numel() == n)
+    dev = logits.device
+    partial = torch.empty(3 * lib.pda_recon_loss_blocks(n), dtype=torch.float64, device=dev)
+    out2 = torch.empty(2, dtype=torch.float32, device=dev)
+    stats = torch.empty(3, dtype=torch.float32, device=dev)
+    cf, ci = _consm_ptrs(consm)
+    _lib.check(lib.pda_recon_loss_fwd(logits.data_ptr(), segm.data_ptr(), cf, ci, n, int(dice), partial.data_ptr(),
+                                      out2.data_ptr(), stats.data_ptr(), _stream()), "recon_loss_fwd")
+    return out2, stats
+
+
+def recon_loss_bwd(logits, segm, consm, dice, stats, gout2):
+    _need_cuda(logits, segm, consm, stats, gout2)
+    lib = _lib.load()
+    n = logits.numel()
+    dlogits = torch.empty_like(logits)
+    cf, ci = _consm_ptrs(consm)
+    _lib.check(lib.pda_recon_loss_bwd(logits.data_ptr(), segm.data_ptr(), cf, ci, n, int(dice), stats.data_ptr(),
+                                      gout2.data_ptr(), dlogits.data_ptr(), _stream()), "recon_loss_bwd")
+    return dlogits
+
+
+def build_l2_tables(params):
+    """Device tables for the multi-tensor L2 norm: forward rows (ptr, numel, tensor, 0); backward rows
+    (w_ptr, byte offset inside the flat gradient buffer, numel, tensor).  Returns (fwd, bwd, offsets, total)."""
+    fwd, bwd, offsets, total = [], [], [], 0
+    for t, p in enumerate(params):
+        assert p.dtype == torch.float32 and p.is_contiguous()
+        n = p.numel()
+        offsets.append(total)
+        for off in range(0, n, _EMA_CHUNK):
+            m = min(_EMA_CHUNK, n - off)
+            fwd.append((p.data_ptr() + 4 * off, m, t, 0))
+            bwd.append((p.data_ptr() + 4 * off, 4 * (total + off), m, t))
+        total += (n + 3) // 4 * 4  # keep every tensor 16-byte aligned inside the flat buffer
+    dev = params[0].device
+    return (torch.tensor(fwd, dtype=torch.int64).to(dev), torch.tensor(bwd, dtype=torch.int64).to(dev), offsets, total)
+
+
+def multi_tensor_l2norm_fwd(table, n_tensors):
+    lib = _lib.load()
+    dev = table.device
+    partial = torch.empty(table.shape[0], dtype=torch.float64, device=dev)
+    norms = torch.empty(n_tensors, dtype=torch.float32, device=dev)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.check(lib.pda_multi_tensor_l2norm_fwd(table.data_ptr(), table.shape[0], n_tensors, partial.data_ptr(),
+                                               norms.data_ptr(), out.data_ptr(), _stream()), "l2norm_fwd")
+    return out, norms
+
+
+def multi_tensor_l2norm_bwd(table, norms, gout, total):
+    lib = _lib.load()
+    flat = torch.empty(total, dtype=torch.float32, device=table.device)
+    gout = gout.contiguous().float()
+    _lib.check(lib.pda_multi_tensor_l2norm_bwd(table.data_ptr(), table.shape[0], norms.data_ptr(), gout.data_ptr(),
+                                               flat.data_ptr(), _stream()), "l2norm_bwd")
+    return flat
+
+
+def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit):
+    """Backward of Fcomb for one latent sample: feat (B,H,W,64) bf16, z (B,L), dlogit (B,1,H,W) fp32."""
+    _need_cuda(feat, z, w1, dlogit)
+    lib = _lib.load()
+    B, H, W, C = feat.shape
+    L = z.shape[1]
+    dev = feat.device
+    dfeat = torch.empty_like(feat)
+    dw1, db1 = torch.empty_like(w1), torch.empty_like(b1)
+    dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+    dw3 = torch.empty_like(w3)
+    db3 = torch.empty(1, dtype=torch.float32, device=dev)
+    dz = torch.empty((B, L), dtype=torch.float32, device=dev)
+    scratch = torch.empty(64 * 64 + B * 64, dtype=torch.float32, device=dev)
+    z = z.contiguous().float()
+    dlogit = dlogit.contiguous().float()
+    with _Timed("fcomb_bwd", float(B * H * W)):
+        rc = lib.pda_fcomb_bwd(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                               b2.data_ptr(), w3.data_ptr(), dlogit.data_ptr(), B, H * W, L, dfeat.data_ptr(),
+                               dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(),
+                               db3.data_ptr(), dz.data_ptr(), scratch.data_ptr(), _stream())
+    _lib.check(rc, "fcomb_bwd")
+    return dfeat, dw1, db1, dw2, db2, dw3, db3, dz

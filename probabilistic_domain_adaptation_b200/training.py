@@ -1,18 +1,237 @@
-"""Differentiable (training) variants of the ops: torch.autograd.Function wrappers over the backward kernels."""
+"""Differentiable (training) variants of the ops: torch.autograd.Function wrappers over the backward kernels.
+
+These replace what torch.autograd runs behind `loss.backward()` in the reference's step bodies
+(punet_trainer.py:24-36, mean_teacher_trainer.py:111-119, ...: cuDNN dgrad / wgrad and ATen elementwise
+backward).  Activations and their gradients are NHWC bf16; parameter gradients are fp32 in the parameter's
+own layout (OIHW), so torch optimizers / GradScaler work unchanged.  autograd itself (graph, accumulation
+into .grad) is the plumbing; every tensor-sized arithmetic step is a libpda_b200 kernel.
+"""
 import torch
 
 from . import ops
+from .autograd_ops import packed_weight
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """conv3x3(pad 1) over the channel concat (x, src1) + bias + ReLU, optional fused 2x2 average pool output.
+    backward: dZ = (dFull + pool^T dPool) * (Y > 0); dgrad = the same tcgen05 conv on dZ with the rotated
+    weights (one launch per concat segment, contiguous row slices of the packed operand); wgrad on tensor cores."""
+
+    @staticmethod
+    def forward(ctx, x, src1, weight, bias, conv, relu, want_pool):
+        full, pool = ops.conv3x3(x, src1, packed_weight(conv), bias.detach(), relu, True, want_pool)
+        ctx.conv, ctx.relu, ctx.want_pool = conv, relu, want_pool
+        ctx.save_for_backward(x, src1, full)
+        ctx.set_materialize_grads(False)
+        if want_pool:
+            return full, pool
+        return full, None
+
+    @staticmethod
+    def backward(ctx, g_full, g_pool):
+        x, src1, full = ctx.saved_tensors
+        if g_full is None and g_pool is None:
+            return (None,) * 7
+        g_full = None if g_full is None else g_full.contiguous()
+        g_pool = None if g_pool is None else g_pool.contiguous()
+        dz = ops.relu_pool_bwd(g_full, g_pool, full if ctx.relu else None, shape=full.shape)
+        c0 = x.shape[3]
+        dx = dsrc1 = dw = db = None
+        need_x, need_s1, need_w, need_b = ctx.needs_input_grad[:4]
+        if need_x or need_s1:
+            wrot = packed_weight(ctx.conv, rot180=True)  # (c0 + c1, 9 * cout)
+            if need_x:
+                dx, _ = ops.conv3x3(dz, None, wrot[:c0], None, relu=False)
+            if need_s1 and src1 is not None:
+                dsrc1, _ = ops.conv3x3(dz, None, wrot[c0:], None, relu=False)
+        if need_w or need_b:
+            dw, db = ops.conv3x3_wgrad(x, src1, dz)
+        return dx, dsrc1, dw, db, None, None, None
+
+
+def conv3x3_train(x, src1, conv, relu, want_full, want_pool):
+    # the full-resolution map is always kept in training: it is the ReLU mask of the backward
+    full, pool = Conv3x3Fn.apply(x, src1, conv.weight, conv.bias, conv, relu, want_pool)
+    return full, pool
+
+
+class ConvFirstFn(torch.autograd.Function):
+    """First layer (cin 1 or 2 fp32 planes).  The image / label planes never need a gradient."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, relu):
+        if not relu:
+            raise NotImplementedError("first-layer backward assumes the fused ReLU")
+        out = ops.conv3x3_first(x0, x1, weight.detach(), bias.detach(), relu)
+        ctx.save_for_backward(x0, x1, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, x1, out = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise NotImplementedError("gradient w.r.t. the input image is not part of the reference's training path")
+        dw, db = ops.conv3x3_first_bwd(x0, x1, out, g.contiguous())
+        return None, None, dw, db, None
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return ops.avgpool2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.relu_pool_bwd(None, g.contiguous(), None, shape=ctx.shape)
+
+
+class Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2x(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.upsample2x_bwd(g.contiguous())
+
+
+class GaussHeadFn(torch.autograd.Function):
+    """Spatial mean + 1x1 conv head of AxisAlignedConvGaussian (probabilistic_unet.py:126-130)."""
+
+    @staticmethod
+    def forward(ctx, enc, weight, bias, latent):
+        out, scratch = ops.gauss_head_fwd_train(enc, weight.detach(), bias.detach(), latent)
+        ctx.latent = latent
+        ctx.save_for_backward(enc, weight, scratch)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        enc, weight, scratch = ctx.saved_tensors
+        denc, dw, db = ops.gauss_head_bwd(g, weight.detach(), scratch, enc, ctx.latent)
+        return denc, dw, db, None
+
+
+class KlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mls_q, mls_p):
+        ctx.save_for_backward(mls_q, mls_p)
+        return ops.kl_diag_gauss(mls_q.contiguous(), mls_p.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        q, p = ctx.saved_tensors
+        dq, dp = ops.kl_diag_gauss_bwd(q.contiguous(), p.contiguous(), g)
+        return dq, dp
 
 
 def kl_op(mls_q, mls_p):
     if torch.is_grad_enabled() and (mls_q.requires_grad or mls_p.requires_grad):
-        raise NotImplementedError("KL backward kernel not built yet")
+        return KlFn.apply(mls_q, mls_p)
     return ops.kl_diag_gauss(mls_q, mls_p)
 
 
+class ReconLossFn(torch.autograd.Function):
+    """(sum, mean) of BCE-with-logits or Dice-with-logits of (logits * consm, segm * consm)
+    (probabilistic_unet.py:347-369), one reduction kernel forward, one elementwise kernel backward."""
+
+    @staticmethod
+    def forward(ctx, logits, segm, consm, dice):
+        out2, stats = ops.recon_loss_fwd(logits, segm, consm, dice)
+        ctx.dice = dice
+        ctx.consm = consm
+        ctx.save_for_backward(logits, segm, stats)
+        return out2
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, segm, stats = ctx.saved_tensors
+        d = ops.recon_loss_bwd(logits, segm, ctx.consm, ctx.dice, stats, g.contiguous().float())
+        return d, None, None, None
+
+
 def recon_loss_op(logits, segm, consm, dice):
-    raise NotImplementedError("reconstruction-loss kernels not built yet")
+    """-> (reconstruction_loss, mean_reconstruction_loss) scalars."""
+    logits = logits.contiguous().float()
+    segm = segm.detach().contiguous().float()
+    if consm is not None:
+        consm = consm.detach().contiguous()
+        if consm.dtype not in (torch.float32, torch.int64):
+            consm = consm.float()
+    if torch.is_grad_enabled() and logits.requires_grad:
+        out2 = ReconLossFn.apply(logits, segm, consm, dice)
+    else:
+        out2, _ = ops.recon_loss_fwd(logits, segm, consm, dice)
+    return out2[0], out2[1]
+
+
+class L2NormSumFn(torch.autograd.Function):
+    """sum_t ||W_t||_2 over a parameter list (utils.py:32-40): two launches forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, cache, *params):
+        key = tuple(p.data_ptr() for p in params)
+        if cache.get("key") != key:
+            cache["fwd"], cache["bwd"], cache["offsets"], cache["total"] = ops.build_l2_tables(
+                [p.detach() for p in params])
+            cache["key"] = key
+        out, norms = ops.multi_tensor_l2norm_fwd(cache["fwd"], len(params))
+        ctx.cache = cache
+        ctx.shapes = [p.shape for p in params]
+        ctx.save_for_backward(norms)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (norms,) = ctx.saved_tensors
+        c = ctx.cache
+        flat = ops.multi_tensor_l2norm_bwd(c["bwd"], norms, g, c["total"])
+        grads = [flat[o:o + s.numel()].view(s) for o, s in zip(c["offsets"], ctx.shapes)]
+        return (None, *grads)
+
+
+_L2_CACHES = {}
 
 
 def l2_norm_sum(params):
-    raise NotImplementedError("multi-tensor L2-norm kernel not built yet")
+    params = list(params)
+    cache = _L2_CACHES.setdefault(tuple(id(p) for p in params), {})
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return L2NormSumFn.apply(cache, *params)
+    with torch.no_grad():
+        return L2NormSumFn.forward(_NoCtx(), cache, *params)
+
+
+class _NoCtx:
+    def save_for_backward(self, *a):
+        pass
+
+
+class FcombTrainFn(torch.autograd.Function):
+    """Fcomb for ONE latent sample with a backward (reconstruct() / sample() under autograd).  Forward is the
+    fused tensor-core kernel (S = 1); backward recomputes the hidden layers in fp32."""
+
+    @staticmethod
+    def forward(ctx, feat, z, w1, b1, w2, b2, w3, b3):
+        out = ops.fcomb_mc_consensus(feat, z[None].detach(), w1.detach(), b1.detach(), w2.detach(), b2.detach(),
+                                     w3.detach(), b3.detach(), want_mean=False, want_weight=False, want_logits=True)
+        ctx.save_for_backward(feat, z, w1, b1, w2, b2, w3)
+        return out["logits"][0]
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, z, w1, b1, w2, b2, w3 = ctx.saved_tensors
+        dfeat, dw1, db1, dw2, db2, dw3, db3, dz = ops.fcomb_bwd(feat, z.detach(), w1.detach(), b1.detach(),
+                                                                w2.detach(), b2.detach(), w3.detach(), g)
+        return dfeat, dz, dw1, db1, dw2, db2, dw3, db3
+
+
+def fcomb_train(feat, z, w, **want):
+    """z (S,B,L).  Differentiable only for a single sample with logits as the sole output (the training form)."""
+    extras = [k for k in ("want_mean", "want_weight", "want_mask", "want_probs") if want.get(k)]
+    if z.shape[0] != 1 or extras or not want.get("want_logits"):
+        raise NotImplementedError("autograd through the fused Monte-Carlo kernel: only S=1 logits are differentiable "
+                                  "(the reference's consensus sampling runs under torch.no_grad())")
+    logits = FcombTrainFn.apply(feat, z[0], *w)
+    return {"mean": None, "weight": None, "mask": None, "logits": logits[None], "probs": None}

@@ -28,7 +28,7 @@ def _model(gain=1.0, **kw):
 @pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9)])
 def test_fcomb_kernel_parity_and_bit_exact_consensus(precision, shape):
     """Fcomb + consensus on given features vs the oracle: the fp32 kernel within 1e-4, the tensor-core kernel
-    (bf16 weights / hidden activations, fp32 accumulate) within 5e-3 of the unit-gain logit scale; mask and
+    (bf16 weights / hidden activations, fp32 accumulate) within the 1e-2 bf16 tolerance at unit-gain logit scale; mask and
     weight bit-exact when recomputed with the reference's torch ops on the kernel's own probabilities."""
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
@@ -41,7 +41,7 @@ def test_fcomb_kernel_parity_and_bit_exact_consensus(precision, shape):
     ref = torch.stack([po.fcomb_logits(sd, feat.float(), z[s]) for s in range(16)], 0)
     k = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
     w = [sd[f"{n}.{p}"].to(dev).contiguous() for n in k for p in ("weight", "bias")]
-    tol = 1e-4 * max(1.0, ref.abs().max().item()) if precision == "fp32" else 5e-3 * gain
+    tol = 1e-4 * max(1.0, ref.abs().max().item()) if precision == "fp32" else 1e-2 * gain
     for masking in (False, True):
         out = ops.fcomb_mc_consensus(feat.permute(0, 2, 3, 1).contiguous().to(dev), z.to(dev), *w,
                                      want_mask=masking, want_weight=not masking, want_logits=True, want_probs=True,

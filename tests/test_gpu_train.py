@@ -1,0 +1,342 @@
+"""GPU parity of the training path (forward + ELBO + backward kernels, called through the C ABI) against
+torch autograd on fp32/fp64 references of the same ops, the CPU oracle and the reference-derived golden
+fixtures.  Activation gradients are bf16 in the kernels, so gradient checks are relative (cosine / norm ratio)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import punet_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+
+
+def _close_grad(mine, ref, cos=0.999, ratio=0.02, what=""):
+    c = _cos(mine, ref)
+    r = (mine.double().norm() / (ref.double().norm() + 1e-300)).item()
+    assert c > cos and abs(r - 1) < ratio, f"{what}: cos {c}, norm ratio {r}"
+
+
+CONV_BWD_CASES = [
+    # B, H, W, c0, c1, cout, pool
+    (2, 16, 16, 64, 0, 64, False),
+    (1, 24, 40, 64, 0, 128, True),
+    (2, 8, 8, 256, 128, 128, False),
+    (1, 5, 9, 128, 0, 256, False),
+    (1, 32, 32, 128, 64, 64, True),
+    (3, 16, 8, 512, 0, 512, False),
+]
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout,pool", CONV_BWD_CASES)
+def test_conv3x3_backward(B, H, W, c0, c1, cout, pool):
+    from probabilistic_domain_adaptation_b200.training import Conv3x3Fn
+    dev = _dev()
+    g = torch.Generator().manual_seed(H * 100 + cout + c1)
+    ctot = c0 + c1
+    x0 = torch.randn(B, H, W, c0, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
+    x1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True) if c1 else None
+    conv = torch.nn.Conv2d(ctot, cout, 3, padding=1).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn(cout, ctot, 3, 3, generator=g) * (2.0 / (9 * ctot)) ** 0.5).to(dev)
+                          .to(torch.bfloat16).float())
+        conv.bias.copy_((torch.randn(cout, generator=g) * 0.1).to(dev))
+    gf = torch.randn(B, H, W, cout, generator=g).to(dev).to(torch.bfloat16)
+    gp = torch.randn(B, H // 2, W // 2, cout, generator=g).to(dev).to(torch.bfloat16) if pool else None
+
+    full, pooled = Conv3x3Fn.apply(x0, x1, conv.weight, conv.bias, conv, True, pool)
+    loss = (full.float() * gf.float()).sum()
+    if pool:
+        loss = loss + (pooled.float() * gp.float()).sum()
+    loss.backward()
+
+    # reference: fp64 autograd on the same bf16-rounded inputs
+    xr0 = x0.detach().double().requires_grad_(True)
+    xr1 = x1.detach().double().requires_grad_(True) if c1 else None
+    wr = conv.weight.detach().double().requires_grad_(True)
+    br = conv.bias.detach().double().requires_grad_(True)
+    xin = torch.cat([xr0] + ([xr1] if c1 else []), 3).permute(0, 3, 1, 2)
+    y = F.relu(F.conv2d(xin, wr, br, padding=1))
+    rl = (y.permute(0, 2, 3, 1) * gf.double()).sum()
+    if pool:
+        rl = rl + (F.avg_pool2d(y, 2).permute(0, 2, 3, 1) * gp.double()).sum()
+    rl.backward()
+    _close_grad(x0.grad, xr0.grad, what="dx0")
+    if c1:
+        _close_grad(x1.grad, xr1.grad, what="dx1")
+    _close_grad(conv.weight.grad, wr.grad, what="dW")
+    _close_grad(conv.bias.grad, br.grad, what="db")
+    # element-wise: dW is an fp32 accumulation of bf16 products
+    err = (conv.weight.grad.double() - wr.grad).abs().max().item()
+    assert err < 2e-2 * wr.grad.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("cin", [1, 2])
+def test_first_conv_backward(cin):
+    from probabilistic_domain_adaptation_b200.training import ConvFirstFn
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, cin, 24, 40, generator=g).to(dev)
+    w = (torch.randn(64, cin, 3, 3, generator=g) * 0.4).to(dev).requires_grad_(True)
+    b = (torch.randn(64, generator=g) * 0.1).to(dev).requires_grad_(True)
+    go = torch.randn(2, 24, 40, 64, generator=g).to(dev).to(torch.bfloat16)
+    out = ConvFirstFn.apply(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if cin == 2 else None, w, b, True)
+    (out.float() * go.float()).sum().backward()
+    wr, br = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    y = F.relu(F.conv2d(x.double(), wr, br, padding=1)).permute(0, 2, 3, 1)
+    (y * go.double()).sum().backward()
+    _close_grad(w.grad, wr.grad, cos=0.9999, ratio=5e-3, what="dW first")
+    _close_grad(b.grad, br.grad, cos=0.9999, ratio=5e-3, what="db first")
+
+
+def test_upsample_and_pool_backward():
+    from probabilistic_domain_adaptation_b200.training import Upsample2xFn, AvgPool2Fn
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 10, 64, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
+    go = torch.randn(2, 12, 20, 64, generator=g).to(dev).to(torch.bfloat16)
+    (Upsample2xFn.apply(x).float() * go.float()).sum().backward()
+    xr = x.detach().double().requires_grad_(True)
+    up = F.interpolate(xr.permute(0, 3, 1, 2), mode="bilinear", scale_factor=2, align_corners=True)
+    (up.permute(0, 2, 3, 1) * go.double()).sum().backward()
+    err = (x.grad.double() - xr.grad).abs()
+    assert (err <= 2 ** -7 * xr.grad.abs() + 1e-2).all(), err.max().item()
+    x2 = torch.randn(2, 8, 12, 64, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
+    gp = torch.randn(2, 4, 6, 64, generator=g).to(dev).to(torch.bfloat16)
+    (AvgPool2Fn.apply(x2).float() * gp.float()).sum().backward()
+    ref = 0.25 * gp.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert torch.allclose(x2.grad.float(), ref, rtol=2 ** -7, atol=1e-6)
+
+
+def test_gauss_head_and_kl_backward():
+    from probabilistic_domain_adaptation_b200.training import GaussHeadFn, kl_op
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    enc = torch.relu(torch.randn(3, 5, 9, 512, generator=g)).to(dev).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(12, 512, 1, 1, generator=g) * 0.05).to(dev).requires_grad_(True)
+    b = (torch.randn(12, generator=g) * 0.01).to(dev).requires_grad_(True)
+    p = (torch.randn(3, 12, generator=g) * 0.3).to(dev).requires_grad_(True)
+    q = GaussHeadFn.apply(enc, w, b, 6)
+    kl = kl_op(q, p)
+    coef = torch.tensor([1.0, -2.0, 0.5], device=dev)
+    (kl * coef).sum().backward()
+
+    er = enc.detach().double().requires_grad_(True)
+    wr, br = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    pr = p.detach().double().requires_grad_(True)
+    m = er.mean(dim=(1, 2))
+    qr = m @ wr[:, :, 0, 0].t() + br
+    d = torch.distributions
+    klr = d.kl.kl_divergence(d.Independent(d.Normal(qr[:, :6], torch.exp(qr[:, 6:])), 1),
+                             d.Independent(d.Normal(pr[:, :6], torch.exp(pr[:, 6:])), 1))
+    assert torch.allclose(kl.double(), klr, rtol=1e-4, atol=1e-5)
+    (klr * coef.double()).sum().backward()
+    assert torch.allclose(w.grad.double(), wr.grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(b.grad.double(), br.grad, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(p.grad.double(), pr.grad, rtol=1e-3, atol=1e-6)
+    # reference gradient of enc, masked like the fused kernel (ReLU of the producing conv folded in)
+    ref = er.grad * (enc.detach().double() > 0)
+    _close_grad(enc.grad, ref, cos=0.9999, ratio=1e-2, what="denc")
+
+
+@pytest.mark.parametrize("dice", [False, True])
+@pytest.mark.parametrize("consm_kind", [None, "weight", "mask"])
+def test_recon_loss_forward_backward(dice, consm_kind):
+    from probabilistic_domain_adaptation_b200.training import recon_loss_op
+    dev = _dev()
+    g = torch.Generator().manual_seed(17)
+    logits = (torch.randn(2, 1, 40, 56, generator=g) * 3).to(dev).requires_grad_(True)
+    segm = torch.rand(2, 1, 40, 56, generator=g).to(dev)
+    k = torch.randint(0, 17, (2, 1, 40, 56), generator=g)
+    consm = None if consm_kind is None else (k.float() / 16 if consm_kind == "weight" else torch.where(k >= 8, 1, 0))
+    consm = None if consm is None else consm.to(dev)
+    s, m = recon_loss_op(logits, segm, consm, dice)
+    (2.0 * s + 3.0 * m).backward()
+    lr = logits.detach().double().requires_grad_(True)
+    rs, rm = po.reconstruction_loss(lr, segm.double(), None if consm is None else consm.double(),
+                                    consensus_masking=consm is not None, rl_swap=dice)
+    (2.0 * rs + 3.0 * rm).backward()
+    assert torch.allclose(s.double(), rs, rtol=1e-5) and torch.allclose(m.double(), rm, rtol=1e-5)
+    assert torch.allclose(logits.grad.double(), lr.grad, rtol=1e-3, atol=1e-9 + 1e-5 * lr.grad.abs().max().item())
+
+
+def test_l2_regularisation_forward_backward():
+    from probabilistic_domain_adaptation_b200.my_models.utils import l2_regularisation
+    dev = _dev()
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Conv2d(64, 70, 3), torch.nn.Conv2d(7, 3, 1), torch.nn.Conv2d(300, 300, 3)).to(dev)
+    out = l2_regularisation(m)
+    (out * 1e-5).backward()
+    mine = [p.grad.clone() for p in m.parameters()]
+    for p in m.parameters():
+        p.grad = None
+    ref = None
+    for p in m.parameters():  # utils.py:32-40
+        ref = p.norm(2) if ref is None else ref + p.norm(2)
+    (ref * 1e-5).backward()
+    assert torch.allclose(out, ref, rtol=1e-6)
+    for a, p in zip(mine, m.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-12)
+    with torch.no_grad():
+        assert torch.allclose(l2_regularisation(m), ref, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9)])
+def test_fcomb_backward(shape):
+    from probabilistic_domain_adaptation_b200.training import FcombTrainFn
+    dev = _dev()
+    sd = po.make_state_dict(0, last_layer_gain=4.0)
+    g = torch.Generator().manual_seed(23)
+    b, h, w_ = shape
+    feat = torch.relu(torch.randn(b, h, w_, 64, generator=g)).to(dev).to(torch.bfloat16).requires_grad_(True)
+    z = torch.randn(b, 6, generator=g).to(dev).requires_grad_(True)
+    keys = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
+    w = [sd[f"{n}.{p}"].to(dev).contiguous().requires_grad_(True) for n in keys for p in ("weight", "bias")]
+    go = torch.randn(b, 1, h, w_, generator=g).to(dev)
+    logits = FcombTrainFn.apply(feat, z, *w)
+    (logits * go).sum().backward()
+    fr = feat.detach().double().requires_grad_(True)
+    zr = z.detach().double().requires_grad_(True)
+    sdr = {}
+    wr = []
+    for n in keys:
+        for p in ("weight", "bias"):
+            t = sd[f"{n}.{p}"].to(dev).double().requires_grad_(True)
+            sdr[f"{n}.{p}"] = t
+            wr.append(t)
+    ref = po.fcomb_logits(sdr, fr.permute(0, 3, 1, 2), zr)
+    assert (logits.double() - ref).abs().max().item() < 5e-3 * 4.0
+    (ref * go.double()).sum().backward()
+    _close_grad(feat.grad, fr.grad, cos=0.9995, ratio=1e-2, what="dfeat")
+    assert torch.allclose(z.grad.double(), zr.grad, rtol=2e-3, atol=1e-4 * zr.grad.abs().max().item())
+    for a, r, n in zip(w, wr, ["w1", "b1", "w2", "b2", "w3", "b3"]):
+        assert torch.allclose(a.grad.double(), r.grad, rtol=2e-3, atol=2e-4 * r.grad.abs().max().item()), n
+
+
+TRAIN_CASES = ["train_bce_64x64", "train_dice_64x64", "train_dice_weight_64x64", "train_dice_mask_48x80",
+               "train_bce_mask_64x64"]
+
+
+def _train_model(g):
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet
+    m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, consensus_masking=g["consm_kind"] is not None,
+                          rl_swap=g["rl_swap"]).to(_dev())
+    m.load_state_dict(po.make_state_dict(0, last_layer_gain=4.0))
+    return m.train()
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_training_step_matches_reference_golden(golden, name):
+    """forward(training=True) + elbo + l2 + backward vs the reference-derived fixtures."""
+    from probabilistic_domain_adaptation_b200 import l2_regularisation
+    g = golden(name)
+    dev = _dev()
+    m = _train_model(g)
+    x, segm = g["x"].to(dev), g["segm"].to(dev)
+    consm = None if g["consm"] is None else g["consm"].to(dev)
+    m.forward(x, segm, training=True)
+    torch.manual_seed(4)
+    # the reference draws posterior.rsample() eps from the CPU generator; feed the identical draw
+    eps = g["eps_post"].to(dev)
+    d = m.posterior_latent_space
+    z = d.base_dist.loc + d.base_dist.scale * eps
+    m.posterior_latent_space.rsample = lambda *a, **k: z  # same latent draw as the fixture
+    elbo = m.elbo(segm, consm)
+    reg = l2_regularisation(m.posterior) + l2_regularisation(m.prior) + l2_regularisation(m.fcomb.layers)
+    loss = -elbo + 1e-5 * reg
+    mls_q, mls_p = m.posterior_latent_space._pda_mls, m.prior_latent_space._pda_mls
+    assert torch.allclose(mls_q[:, :6].cpu(), g["mu_q"], atol=2e-2)
+    assert torch.allclose(mls_q[:, 6:].cpu(), g["log_sigma_q"], atol=2e-2)
+    assert torch.allclose(mls_p[:, :6].cpu(), g["mu_p"], atol=2e-2)
+    assert torch.allclose(mls_p[:, 6:].cpu(), g["log_sigma_p"], atol=2e-2)
+    rec_err = (m.reconstruction.detach().cpu() - g["reconstruction"]).abs().max().item() / 4.0
+    print(name, "max |logit err| / gain =", rec_err)
+    assert rec_err < 1e-2
+    assert torch.allclose(reg.detach().cpu(), g["reg"], rtol=1e-5)
+    assert abs(m.kl.item() - g["kl"].item()) < 0.05 * abs(g["kl"].item()) + 1e-3
+    assert abs(m.reconstruction_loss.item() - g["reconstruction_loss"].item()) < 5e-3 * abs(
+        g["reconstruction_loss"].item()) + 1e-4
+    assert abs(m.mean_reconstruction_loss.item() - g["mean_reconstruction_loss"].item()) < 5e-3 * abs(
+        g["mean_reconstruction_loss"].item()) + 1e-4
+    assert abs(loss.item() - g["loss"].item()) < 5e-3 * abs(g["loss"].item()) + 1e-3
+    if "grad_norms" in g:
+        loss.backward()
+        bad = []
+        for k, p in m.named_parameters():
+            assert p.grad is not None, k
+            gn, rn = p.grad.norm().item(), g["grad_norms"][k]
+            if abs(gn - rn) > 0.05 * rn + 1e-7:
+                bad.append((k, gn, rn))
+        assert not bad, bad
+
+
+def test_training_gradients_match_oracle_autograd():
+    """Every parameter gradient of one Dice-ELBO step (consensus weights applied) against fp32 autograd through
+    the CPU oracle on the same weights / inputs / latent draw: direction (cosine) and norm."""
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, l2_regularisation
+    dev = _dev()
+    sd = po.make_state_dict(0, last_layer_gain=4.0)
+    b, h, w = 2, 32, 48
+    x, _, _, eps_post = po.synthetic_inputs(b, h, w)
+    segm = torch.rand(b, 1, h, w, generator=torch.Generator().manual_seed(2))
+    consm = torch.randint(0, 17, (b, 1, h, w), generator=torch.Generator().manual_seed(5)).float() / 16
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = po.training_loss(ref_sd, x, segm, eps_post, consm, beta=1.0, consensus_masking=True, rl_swap=True)
+    out["loss"].backward()
+
+    m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, consensus_masking=True, rl_swap=True).to(dev)
+    m.load_state_dict(sd)
+    m.train()
+    m.forward(x.to(dev), segm.to(dev), training=True)
+    d = m.posterior_latent_space
+    z = d.base_dist.loc + d.base_dist.scale * eps_post.to(dev)
+    m.posterior_latent_space.rsample = lambda *a, **k: z
+    elbo = m.elbo(segm.to(dev), consm.to(dev))
+    reg = l2_regularisation(m.posterior) + l2_regularisation(m.prior) + l2_regularisation(m.fcomb.layers)
+    loss = -elbo + 1e-5 * reg
+    loss.backward()
+    assert abs(loss.item() - out["loss"].item()) < 5e-3 * abs(out["loss"].item())
+    worst = (1.0, None)
+    for k, p in m.named_parameters():
+        c = _cos(p.grad.cpu(), ref_sd[k].grad)
+        r = p.grad.norm().item() / (ref_sd[k].grad.norm().item() + 1e-30)
+        if c < worst[0]:
+            worst = (c, k)
+        assert c > 0.97 and abs(r - 1) < 0.06, (k, c, r)
+    print("worst gradient cosine", worst)
+
+
+def test_optimizer_step_reduces_loss():
+    """A few Adam steps of the source-training step body (punet_trainer.py:24-36) on one batch drive the loss down."""
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, l2_regularisation
+    dev = _dev()
+    torch.manual_seed(0)
+    m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, rl_swap=True).to(dev).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    x, y, _, _ = po.synthetic_inputs(2, 64, 64)
+    y = torch.zeros_like(y)
+    y[:, :, 16:48, 16:48] = 1
+    x = (x * 0.1 + y).to(dev)
+    y = y.to(dev)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        m.forward(x, y, training=True)
+        elbo = m.elbo(y)
+        reg = l2_regularisation(m.posterior) + l2_regularisation(m.prior) + l2_regularisation(m.fcomb.layers)
+        loss = -elbo + 1e-5 * reg
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("losses", [round(v, 4) for v in losses])
+    assert losses[-1] < losses[0]
