@@ -36,6 +36,10 @@ def parse():
     ap.add_argument("--size", type=int, default=1024, help="tile height = width")
     ap.add_argument("--samples", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="both", choices=["infer", "train", "both"],
+                    help="infer: MC inference leg only; train: mean-teacher step leg only")
+    ap.add_argument("--train-batch", type=int, default=4, help="images per GPU per mean-teacher step (MitoEM: 4)")
+    ap.add_argument("--train-size", type=int, default=512)
     return ap.parse_args()
 
 
@@ -137,11 +141,126 @@ def run_reference(args):
     }))
 
 
+
+def make_model(dev, **kw):
+    """Random-init PUNet of the scripts' architecture (reference init scheme, seed 0); the last Fcomb layer is scaled
+    so that the sampled probabilities spread over (0, 1) and the consensus mask takes both values."""
+    import torch
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet
+    torch.manual_seed(0)
+    m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, **kw).to(dev)
+    with torch.no_grad():
+        m.fcomb.last_layer.weight.mul_(8.0)
+    return m
+
+
+TRAIN_FLOP_PER_PX = 3 * 3_229_056 + 2_509_056  # student fwd+bwd (3x forward, SURVEY.md 8(d)) + teacher forward
+
+
+def run_train_leg(args, dev, world, rank, local, lib, barrier):
+    """Mean-teacher consensus step (BASELINE config 3, mean_teacher_trainer.py:101-131): teacher forward + S prior
+    samples + consensus mask, student forward(x2, y) + Dice-ELBO(y, z) + L2 + backward, gradient all-reduce,
+    Adam, EMA.  Returns the "train" object of the JSON line (rank 0) or None."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, consensus, ops, steps
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer
+
+    Bt, HW, S = args.train_batch, args.train_size, args.samples
+    model = make_model(dev, consensus_masking=True, rl_swap=True).train()
+    teacher = copy.deepcopy(model)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    opt = FusedAdam(model.parameters(), lr=1e-5)
+    reducer = GradAllReducer(model)
+    ema = consensus.MomentumUpdater(model, teacher)
+    backprop = steps.default_backprop(opt, reducer)
+    g = torch.Generator().manual_seed(11 + rank)
+    x = torch.randn(Bt, 1, HW, HW, generator=g)
+    host_x1 = (x + 0.1 * torch.randn(Bt, 1, HW, HW, generator=g)).pin_memory()
+    host_x2 = (x + 0.25 * torch.randn(Bt, 1, HW, HW, generator=g)).pin_memory()
+    x1, x2 = host_x1.to(dev), host_x2.to(dev)
+    eps = torch.randn(S, Bt, 6, generator=torch.Generator().manual_seed(3)).to(dev)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        return steps.mean_teacher_step(model, teacher, opt, ema, x1, x2, n_samples=S, do_consensus_masking=True,
+                                       backprop=backprop, eps=eps)[0]
+
+    def step_e2e():
+        a = host_x1.to(dev, non_blocking=True)
+        b = host_x2.to(dev, non_blocking=True)
+        loss = steps.mean_teacher_step(model, teacher, opt, ema, a, b, n_samples=S, do_consensus_masking=True,
+                                       backprop=backprop, eps=eps)[0]
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def timed(fn, steps_, profile=False):
+        barrier()
+        ops.PROFILE = [] if profile else None
+        lib.pda_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps_):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.pda_launch_count()
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, prof
+
+    for _ in range(args.warmup):
+        loss = step_resident()
+    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    final_loss = float(loss.item())
+    reducer.remove()
+    if rank != 0:
+        return None
+    _, tf_peak, peak_src = load_peaks()
+    kinds = {}
+    for k, a, b, w in prof:
+        t, f, n = kinds.get(k, (0.0, 0.0, 0))
+        kinds[k] = (t + a.elapsed_time(b), f + w, n + 1)
+    tc_ms = sum(kinds.get(k, (0, 0, 0))[0] for k in ("conv3x3_tc", "wgrad3x3_tc"))
+    tc_flop = sum(kinds.get(k, (0, 0, 0))[1] for k in ("conv3x3_tc", "wgrad3x3_tc"))
+    achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    per_kernel = {k: {"ms_per_step": t / args.steps, "launches_per_step": n / args.steps,
+                      "tflops": (f / (t * 1e-3) / 1e12 if k in ("conv3x3_tc", "wgrad3x3_tc") and t > 0 else None)}
+                  for k, (t, f, n) in kinds.items()}
+    imgs = float(Bt) * world * args.steps
+    return {
+        "metric": "mt_consensus_train_img_per_s", "value": imgs / (ms * 1e-3), "unit": "img/s",
+        "ms_per_step": ms / args.steps,
+        "config": {"workload": f"mean-teacher consensus-masking step: teacher forward + S={S} samples + mask, student "
+                               f"Dice-ELBO fwd/bwd + L2, grad all-reduce, Adam, EMA on {Bt}x1x{HW}x{HW} per GPU "
+                               f"(BASELINE config 3, MitoEM shape)",
+                   "batch_per_gpu": Bt, "patch": HW, "samples": S, "parallelism": f"dp{world}"},
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * host_x1.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "final_loss": final_loss,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (fwd + dgrad) and wgrad3x3_tc_kernel",
+                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms},
+        "kernels": per_kernel,
+        "model_tflops": TRAIN_FLOP_PER_PX * float(Bt) * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import punet_oracle as po
-    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, _lib, consensus, ops
+    from probabilistic_domain_adaptation_b200 import _lib, consensus, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -153,9 +272,7 @@ def run_ours(args):
     lib = _lib.load()
 
     T, HW, S = args.tiles, args.size, args.samples
-    sd = po.make_state_dict(0, last_layer_gain=8.0)
-    model = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0).to(dev).eval()
-    model.load_state_dict(sd)
+    model = make_model(dev).eval()
     g = torch.Generator().manual_seed(1 + rank)
     host_x = torch.randn(T, 1, HW, HW, generator=g).pin_memory()
     eps = torch.randn(S, T, 6, generator=torch.Generator().manual_seed(3)).to(dev)
@@ -220,6 +337,12 @@ def run_ours(args):
     fc_gbs = fc_px * 140.0 / (fc_ms * 1e-3) / 1e9 if fc_ms > 0 else 0.0
     fc_tf = fc_px * 2.0 * (4096 + S * 4160) / (fc_ms * 1e-3) / 1e12 if fc_ms > 0 else 0.0
 
+    train = None
+    if args.mode in ("train", "both"):
+        del x_dev, eps
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, dev, world, rank, local, lib, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -251,12 +374,13 @@ def run_ours(args):
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
                      "launches": n_conv, "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms},
-        "roofline_fcomb": {"bound": "hbm (north star) / fp32 FMA (actual)", "achieved": fc_gbs, "peak": hbm_peak,
+        "roofline_fcomb": {"bound": "hbm (north star) / tensor + CUDA-core epilogue (actual)", "achieved": fc_gbs, "peak": hbm_peak,
                            "unit": "GB/s", "frac": fc_gbs / hbm_peak, "algorithmic_bytes_per_px": 140,
                            "achieved_tflops": fc_tf, "kernel_ms_per_step": fc_ms / args.steps,
                            "share_of_step": fc_ms / ms},
         "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
         "cpu_baseline": cpu,
+        "train": train,
     }
     print(json.dumps(line))
     if world > 1:

@@ -163,6 +163,14 @@ int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float
                   const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
                   float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream);
 
+/* torch.optim.Adam step (the optimizer of every reference script, e.g. LIVECell/livecell_punet.py:58) over many
+ * tensors in one launch.  table int64 [n_chunks][5] = (param, grad, exp_avg, exp_avg_sq, numel<=65536), all fp32.
+ * step >= 1 is the step count AFTER this update (bias correction).  inv_scale (device float, may be NULL) multiplies
+ * the gradients first (GradScaler unscale); found_inf (device float, may be NULL) != 0 turns the launch into a no-op. */
+int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, long long step, const float* inv_scale, const float* found_inf,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

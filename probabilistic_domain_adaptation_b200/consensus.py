@@ -12,7 +12,6 @@ Drop-ins for the helper bodies that the reference duplicates in its trainers and
 import torch
 
 from . import ops
-from .autograd_ops import invalidate_packed
 
 
 @torch.no_grad()
@@ -72,7 +71,9 @@ class MomentumUpdater:
     def step(self, momentum):
         self._refresh()
         ops.multi_tensor_ema(self._table, momentum)
-        invalidate_packed(self.teacher)  # parameter memory changed behind autograd's version counters
+        # parameter memory changed behind autograd's back: advance the version counters (packed-weight cache key)
+        from .optim import bump_versions
+        bump_versions(self.teacher.parameters())
 
 
 def adamt_momentum(iteration, momentum=0.999):

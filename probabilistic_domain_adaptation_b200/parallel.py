@@ -1,0 +1,117 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch on the GPU box,
+gloo in the CPU tests).
+
+* Monte-Carlo inference shards TILES across ranks: no data-path collective.
+* Training is data parallel: ONE exchange step per iteration, the gradient all-reduce (average), issued per
+  bucket from post-accumulate-grad hooks so that it overlaps the rest of backward.  The reference itself has no
+  distributed code; the wrapper works on the bare module because ProbabilisticUnet.forward returns None and the
+  loss comes from methods (elbo), which DistributedDataParallel would hide.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [start, stop) share of n_items for `rank` (first n_items % world ranks get one more)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_tiles(tiles, rank=None, world=None):
+    """This rank's share of a sequence of independent tiles / images."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    a, b = shard_range(len(tiles), rank, world)
+    return tiles[a:b]
+
+
+def broadcast_parameters(module, src=0):
+    """Identical initial student / teacher weights on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for p in module.parameters():
+        dist.broadcast(p.data, src)
+
+
+class GradAllReducer:
+    """Bucketed gradient averaging for a bare nn.Module.
+
+    Parameters are grouped into buckets of ~bucket_mb in REVERSE registration order (the order in which backward
+    produces their gradients).  When the last gradient of a bucket has been accumulated, the bucket is packed into a
+    flat buffer and an asynchronous all-reduce (AVG on NCCL, SUM + scale elsewhere) is launched; `finish()` waits for
+    all buckets and rebinds p.grad to its averaged view inside the flat buffer.  Call `finish()` after backward and
+    before optimizer.step()."""
+
+    def __init__(self, module, bucket_mb=25.0, process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.buckets = []  # list of dict(params, flat, views, pending, work)
+        limit = int(bucket_mb * 1024 * 1024)
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= limit:
+                self._add_bucket(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._add_bucket(cur)
+        self._bucket_of = {}
+        for bi, b in enumerate(self.buckets):
+            for p in b["params"]:
+                self._bucket_of[p] = bi
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+
+    def _add_bucket(self, params):
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+        views, off = [], 0
+        for p in params:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.buckets.append({"params": list(params), "flat": flat, "views": views, "pending": len(params),
+                             "work": None})
+
+    def _on_grad(self, p):
+        b = self.buckets[self._bucket_of[p]]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        grads = [p.grad for p in b["params"]]
+        torch._foreach_copy_(b["views"], grads)
+        if self.world > 1:
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            b["work"] = dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True)
+
+    def finish(self):
+        for b in self.buckets:
+            if b["pending"] != 0:  # parameters that received no gradient this iteration
+                missing = [p for p in b["params"] if p.grad is None]
+                if len(missing) == len(b["params"]):
+                    b["pending"] = len(b["params"])
+                    continue
+                for p, v in zip(b["params"], b["views"]):
+                    if p.grad is None:
+                        v.zero_()
+                        p.grad = v
+                self._launch(b)
+            if b["work"] is not None:
+                b["work"].wait()
+                b["work"] = None
+                if not self._avg:
+                    b["flat"].div_(self.world)
+            for p, v in zip(b["params"], b["views"]):
+                p.grad = v
+            b["pending"] = len(b["params"])
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

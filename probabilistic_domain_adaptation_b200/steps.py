@@ -1,0 +1,116 @@
+"""Step bodies of the reference trainers on the fused kernels.
+
+Each function is the per-batch body of one `_train_epoch_impl`, with the same order of operations, the same
+loss and the same in-place effects (optimizer step, EMA), minus logging / progress / checkpointing (torch_em):
+
+  punet_step         prob_utils/my_trainer/punet_trainer.py:24-36
+  mean_teacher_step  prob_utils/my_trainer/mean_teacher_trainer.py:101-131
+  fixmatch_step      prob_utils/my_trainer/fixmatch_trainer.py:67-95
+  adamt_step         prob_utils/my_trainer/adamt_trainer.py:89-128
+  adamatch_step      prob_utils/my_trainer/adamatch_trainer.py:62-102
+
+`backprop(loss)` is torch_em's callable (backward + optimizer.step, with GradScaler under AMP); the default does
+loss.backward(); [grad all-reduce]; optimizer.step().
+"""
+import torch
+
+from . import consensus
+from .my_models.utils import l2_regularisation
+
+
+def default_backprop(optimizer, reducer=None):
+    def backprop(loss):
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        optimizer.step()
+    return backprop
+
+
+def punet_loss(model, x, y, consm=None, use_consm=False):
+    """forward + elbo + 1e-5 * L2(posterior, prior, fcomb.layers)  (punet_trainer.py:30-34)."""
+    model.forward(x, y, training=True)
+    elbo = model.elbo(y, consm) if use_consm else model.elbo(y)
+    reg_loss = l2_regularisation(model.posterior) + l2_regularisation(model.prior) + \
+        l2_regularisation(model.fcomb.layers)
+    return -elbo + 1e-5 * reg_loss
+
+
+def punet_step(model, optimizer, x, y, backprop=None):
+    backprop = backprop or default_backprop(optimizer)
+    optimizer.zero_grad()
+    loss = punet_loss(model, x, y)
+    backprop(loss)
+    return loss
+
+
+def mean_teacher_step(model, teacher, optimizer, ema, x1, x2, n_samples=16, do_consensus_masking=False,
+                      momentum=0.999, backprop=None, eps=None):
+    """Teacher MC pseudo-label + consensus on the weak view, student ELBO step on the strong view, EMA.
+    `ema` is a consensus.MomentumUpdater(model, teacher)."""
+    backprop = backprop or default_backprop(optimizer)
+    with torch.no_grad():
+        y, z = consensus.sample_from_teacher(teacher, x1, n_samples, do_consensus_masking=do_consensus_masking,
+                                             eps=eps)
+    optimizer.zero_grad()
+    loss = punet_loss(model, x2, y, z, use_consm=True)
+    backprop(loss)
+    lr = optimizer.param_groups[0]["lr"]
+    if lr:  # mean_teacher_trainer.py:126 -- always true for a positive learning rate
+        ema.step(momentum)
+    return loss, y, z
+
+
+def distribution_alignment(y, source_distribution):
+    """fixmatch_trainer.py:77-84 (tiny: B x H x W compare / unique on the pseudo-label; stays in torch)."""
+    y_binary = torch.where(y >= 0.5, 1, 0)
+    _, target_distribution = torch.unique(y_binary, return_counts=True)
+    target_distribution = target_distribution / target_distribution.sum()
+    ratio = source_distribution / target_distribution
+    return torch.where(y < 0.5, y * ratio[0], y * ratio[1]).clip(0, 1), ratio
+
+
+def fixmatch_step(model, optimizer, x1, x2, n_samples=16, do_consensus_masking=False, source_distribution=None,
+                  backprop=None, eps=None):
+    """Weak-view MC pseudo-label + consensus from the model itself, ELBO step on the strong view."""
+    backprop = backprop or default_backprop(optimizer)
+    with torch.no_grad():
+        y, z = consensus.sample_from_weak_model(model, x1, n_samples, do_consensus_masking=do_consensus_masking,
+                                                eps=eps)
+    y, z = y.detach(), z.detach()
+    ratio = None
+    if source_distribution is not None:
+        y, ratio = distribution_alignment(y, source_distribution)
+    optimizer.zero_grad()
+    loss = punet_loss(model, x2, y, z, use_consm=True)
+    backprop(loss)
+    return loss, y, z, ratio
+
+
+def _joint_step(model, pseudo_net, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps):
+    optimizer.zero_grad()
+    supervised_loss = punet_loss(model, xs, ys)
+    with torch.no_grad():
+        y, z = consensus.sample_from_teacher(pseudo_net, xt1, n_samples, do_consensus_masking=do_consensus_masking,
+                                             eps=eps)
+    y, z = y.detach(), z.detach()
+    target_loss = punet_loss(model, xt2, y, z, use_consm=True)
+    loss = (supervised_loss + target_loss) / 2
+    backprop(loss)
+    return loss, y, z
+
+
+def adamatch_step(model, optimizer, xs, ys, xt1, xt2, n_samples=16, do_consensus_masking=False, backprop=None,
+                  eps=None):
+    """Joint FixMatch: source ELBO + weak-view pseudo-labelled target ELBO, one backward."""
+    backprop = backprop or default_backprop(optimizer)
+    return _joint_step(model, model, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps)
+
+
+def adamt_step(model, teacher, optimizer, ema, iteration, xs, ys, xt1, xt2, n_samples=16,
+               do_consensus_masking=False, momentum=0.999, backprop=None, eps=None):
+    """Joint mean teacher: source ELBO + teacher pseudo-labelled target ELBO, one backward, warm-up EMA."""
+    backprop = backprop or default_backprop(optimizer)
+    out = _joint_step(model, teacher, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps)
+    ema.step(consensus.adamt_momentum(iteration, momentum))
+    return out

@@ -1,0 +1,128 @@
+"""GPU: trainer step bodies (steps.py), fused Adam and the multi-tensor EMA against the reference arithmetic."""
+import copy
+
+import pytest
+import torch
+
+from oracle import punet_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _model(**kw):
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet
+    m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, **kw).to(_dev())
+    m.load_state_dict(po.make_state_dict(0, last_layer_gain=8.0))
+    return m.train()
+
+
+def test_fused_adam_matches_torch_adam():
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    dev = _dev()
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 1, 3, 3), (64,), (128, 64, 3, 3), (12, 512, 1, 1), (70001,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdam(pa, lr=1e-3, weight_decay=0.01)
+    ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=0.01)
+    for it in range(5):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(dev) * (10.0 ** (it - 2))
+            a.grad, b.grad = gr.clone(), gr.clone()
+        v0 = pa[0]._version
+        oa.step()
+        ob.step()
+        assert pa[0]._version > v0  # the packed-weight cache keys on the version counter
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a - b).abs().max().item()
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    for k in sb:
+        assert torch.allclose(sa[k]["exp_avg"], sb[k]["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(sa[k]["exp_avg_sq"], sb[k]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+        assert float(sa[k]["step"]) == float(sb[k]["step"]) == 5
+
+
+def test_mean_teacher_step_ema_and_progress():
+    """mean_teacher_trainer.py:101-131 on the kernels: the teacher after the step is bit-exactly
+    t * m + p * (1 - m) of the updated student; the student changed; pseudo-label / mask have the right types."""
+    from probabilistic_domain_adaptation_b200 import consensus, steps
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    dev = _dev()
+    model = _model(consensus_masking=True, rl_swap=True)
+    teacher = copy.deepcopy(model)  # before the first forward, as mean_teacher_trainer.py:40
+    for p in teacher.parameters():
+        p.requires_grad = False
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    ema = consensus.MomentumUpdater(model, teacher)
+    x, _, eps, _ = po.synthetic_inputs(2, 64, 64, s=16)
+    x1, x2 = (x + 0.1 * torch.randn_like(x)).to(dev), (x + 0.25 * torch.randn_like(x)).to(dev)
+    t_before = [p.detach().clone() for p in teacher.parameters()]
+    s_before = [p.detach().clone() for p in model.parameters()]
+    with torch.no_grad():
+        y_ref, z_ref = consensus.sample_from_teacher(teacher, x1, 16, do_consensus_masking=True, eps=eps.to(dev))
+    loss, y, z = steps.mean_teacher_step(model, teacher, opt, ema, x1, x2, n_samples=16, do_consensus_masking=True,
+                                         eps=eps.to(dev))
+    assert torch.isfinite(loss)
+    assert z.dtype == torch.int64 and y.dtype == torch.float32 and y.shape == (2, 1, 64, 64)
+    assert torch.equal(y, y_ref) and torch.equal(z, z_ref)
+    changed = sum(float((a - b.detach()).abs().sum()) for a, b in zip(s_before, model.parameters()))
+    assert changed > 0
+    for t0, t1, p in zip(t_before, teacher.parameters(), model.parameters()):
+        assert torch.equal(t1, t0 * 0.999 + p.detach() * (1. - 0.999))  # mean_teacher_trainer.py:55
+    # the teacher's packed weights follow the EMA: a second sampling differs from the first
+    with torch.no_grad():
+        y2, _ = consensus.sample_from_teacher(teacher, x1, 16, do_consensus_masking=True, eps=eps.to(dev))
+    assert not torch.equal(y2, y_ref)
+
+
+def test_joint_and_fixmatch_steps_run():
+    from probabilistic_domain_adaptation_b200 import consensus, steps
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    dev = _dev()
+    model = _model(consensus_masking=True, rl_swap=False)
+    teacher = copy.deepcopy(model)
+    opt = FusedAdam(model.parameters(), lr=1e-5)
+    ema = consensus.MomentumUpdater(model, teacher)
+    x, ys, eps, _ = po.synthetic_inputs(2, 32, 48, s=16)
+    xs, ys = x.to(dev), ys.to(dev)
+    xt1, xt2 = (x.flip(0) + 0.1).to(dev), (x.flip(0) - 0.1).to(dev)
+    l0, y, z = steps.adamatch_step(model, opt, xs, ys, xt1, xt2, eps=eps.to(dev))
+    assert torch.isfinite(l0) and z.dtype == torch.float32 and float(z.max()) <= 1.0
+    l1, y, z = steps.adamt_step(model, teacher, opt, ema, 0, xs, ys, xt1, xt2, eps=eps.to(dev))
+    assert torch.isfinite(l1)
+    # adamt_trainer.py:41 at iteration 0: momentum 0 -> the teacher becomes the student
+    for t, p in zip(teacher.parameters(), model.parameters()):
+        assert torch.equal(t, p.detach())
+    src = torch.tensor([0.7, 0.3], device=dev)
+    l2, y, z, ratio = steps.fixmatch_step(model, opt, xt1, xt2, source_distribution=src, eps=eps.to(dev))
+    assert torch.isfinite(l2) and float(y.min()) >= 0 and float(y.max()) <= 1 and ratio.shape == (2,)
+    l3 = steps.punet_step(model, opt, xs, ys)
+    assert torch.isfinite(l3)
+
+
+def test_grad_allreducer_single_process_rebinds_grads():
+    from probabilistic_domain_adaptation_b200 import steps
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer
+    dev = _dev()
+    model = _model(rl_swap=True)
+    ref = copy.deepcopy(model)
+    x, y, _, _ = po.synthetic_inputs(2, 32, 32)
+    torch.manual_seed(5)
+    steps.punet_loss(ref, x.to(dev), y.to(dev)).backward()
+    red = GradAllReducer(model, bucket_mb=4.0)
+    assert len(red.buckets) > 3
+    torch.manual_seed(5)
+    steps.punet_loss(model, x.to(dev), y.to(dev)).backward()
+    red.finish()
+    for (k, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert p.grad is not None and torch.equal(p.grad, q.grad), k
+    opt = FusedAdam(model.parameters(), lr=1e-4)
+    opt.step()
+    red.remove()

@@ -1,0 +1,71 @@
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic (tile sharding, bucketed gradient averaging)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_everything():
+    from probabilistic_domain_adaptation_b200.parallel import shard_range, shard_tiles
+    for n in (0, 1, 7, 8, 9, 64):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_tiles(list(range(10)), rank=1, world=4) == [3, 4, 5]
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer, broadcast_parameters, shard_tiles
+    torch.manual_seed(100 + rank)  # different initial weights per rank: broadcast must fix that
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 1))
+    broadcast_parameters(net, 0)
+    red = GradAllReducer(net, bucket_mb=0.0005)  # ~500 B buckets -> several buckets
+    torch.manual_seed(0)
+    data = torch.randn(8, 8)
+    target = torch.randn(8, 1)
+    mine = shard_tiles(list(range(8)), rank, world)
+    for it in range(2):  # two iterations: the hooks re-arm
+        net.zero_grad()
+        loss = ((net(data[mine]) - target[mine]) ** 2).mean()
+        loss.backward()
+        red.finish()
+    out[rank] = {"grads": [p.grad.clone() for p in net.parameters()], "n_buckets": len(red.buckets),
+                 "weights": [p.detach().clone() for p in net.parameters()]}
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_average_world2():
+    world = 2
+    port = 29500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0]["n_buckets"] > 1
+    for a, b in zip(out[0]["weights"], out[1]["weights"]):
+        assert torch.equal(a, b)
+    for a, b in zip(out[0]["grads"], out[1]["grads"]):
+        assert torch.equal(a, b)
+    # equals the single-process gradient of the mean over per-rank losses
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                              torch.nn.Linear(16, 1))
+    with torch.no_grad():
+        for p, w in zip(net.parameters(), out[0]["weights"]):
+            p.copy_(w)
+    torch.manual_seed(0)
+    data = torch.randn(8, 8)
+    target = torch.randn(8, 1)
+    loss = 0.5 * (((net(data[:4]) - target[:4]) ** 2).mean() + ((net(data[4:]) - target[4:]) ** 2).mean())
+    loss.backward()
+    for p, g in zip(net.parameters(), out[0]["grads"]):
+        assert torch.allclose(p.grad, g, atol=1e-6)
