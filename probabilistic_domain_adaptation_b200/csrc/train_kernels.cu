@@ -676,8 +676,8 @@ __global__ void fcomb_bwd_finish_kernel(const float* __restrict__ dbz, const flo
 // scalars[0] = 1 / grad_scale (GradScaler unscale, 1 when unused); found_inf (optional) != 0 skips the update.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-adam_kernel(const long long* __restrict__ table, float lr, float beta1, float beta2, float eps, float weight_decay,
-            float bc1, float bc2_sqrt, const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
+adam_kernel(const long long* __restrict__ table, float lr, float beta2, float omb1, float omb2, float eps,
+            float weight_decay, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
   if (found_inf && found_inf[0] != 0.f) return;
   const long long* e = table + 5LL * blockIdx.x;
   float* p = reinterpret_cast<float*>(e[0]);
@@ -692,8 +692,8 @@ adam_kernel(const long long* __restrict__ table, float lr, float beta1, float be
     const float pi = p[i];
     if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
     // torch: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
-    const float vi = fmaf(gi * gi, 1.f - beta2, v[i] * beta2);
+    const float mi = m[i] + (gi - m[i]) * omb1;
+    const float vi = fmaf(gi * gi, omb2, v[i] * beta2);
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -878,8 +878,8 @@ int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double 
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
   PDA_COUNT(1);
-  adam_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), (float)lr, (float)beta1,
-                                                (float)beta2, (float)eps, (float)weight_decay, (float)bc1,
+  adam_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), (float)lr, (float)beta2,
+                                                (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)bc1,
                                                 (float)sqrt(bc2), inv_scale, found_inf);
   return LAUNCH_OK();
 }
