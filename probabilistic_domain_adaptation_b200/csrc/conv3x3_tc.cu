@@ -16,67 +16,88 @@
 
 namespace pda {
 
-template <int BN, int STAGES>
-struct ConvSmem {
-  static constexpr int A_BYTES = 128 * 128;      // 128 pixels x 64 ch bf16
-  static constexpr int B_BYTES = BN * 128;       // BN out-channels x 64 ch bf16
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 1;
-  static constexpr int TMEM_SLOT_OFF = BAR_OFF + NBARS * 8;
-  static constexpr int BIAS_OFF = TMEM_SLOT_OFF + 16;
-  static constexpr int TOTAL = BIAS_OFF + BN * 4;
-  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel.  Work unit = (pixel tile of 16*MT rows x 8 columns of one image, block of BN output channels).
+//
+// Tap reuse: for one 64-channel chunk the producer loads three column-shifted input SLABS (kx = 0,1,2), each
+// [16*MT + 2 rows][8 px][64 ch] with SWIZZLE_128B, so that an 8-pixel output row segment is one 1024-byte swizzle
+// atom.  The A operand of tap (ky, kx) for M-tile mt is then simply slab kx advanced by (16*mt + ky) atoms: the
+// same shared-memory bytes feed three taps and both M-tiles, i.e. 3.2-3.4 pixel-loads per output pixel instead of 9.
+// Weights: one [BN][64] tile per (tap, chunk) through a second ring, or fully resident for a 64->64 layer.
+// Accumulators: MT x BN fp32 columns, double buffered in TMEM, so the epilogue of unit i overlaps the MMAs of
+// unit i+1.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane = one pixel each).
+// ---------------------------------------------------------------------------------------------
+template <int BN, int MT, bool RES>
+struct ConvCfg {
+  static constexpr int SLAB_ROWS = 16 * MT + 2;
+  static constexpr int A_BYTES = SLAB_ROWS * 1024;     // one slab: SLAB_ROWS x (8 px x 128 B)
+  static constexpr int B_BYTES = BN * 128;             // one (tap, chunk) weight tile
+  static constexpr int A_STAGES = 4;
+  static constexpr int B_STAGES = RES ? 9 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6);
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = A_STAGES * A_BYTES;
+  static constexpr int BAR_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
+  static constexpr int BIAS_OFF = SLOT_OFF + 16;
+  static constexpr int MAX_COUT = 512;
+  static constexpr int TOTAL = BIAS_OFF + MAX_COUT * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int BN, int STAGES>
+template <int BN, int MT, bool RES>
 __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
-  using L = ConvSmem<BN, STAGES>;
+  using L = ConvCfg<BN, MT, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + L::BAR_OFF;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT_OFF);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (L::A_STAGES + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + L::B_STAGES + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::SLOT_OFF);
   float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x;
-  const int ty = (tile / p.tiles_x) % p.tiles_y;
-  const int img = tile / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-  const int n0 = blockIdx.y * BN;
   const int ctot = p.c0 + p.c1;
   const int chunks = ctot >> 6;
-  const int num_k = 9 * chunks;
+  const int n_blocks = p.cout / BN;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int units = tiles_per_img * p.B * n_blocks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < L::A_STAGES; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < L::B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 4);  // one arrive per epilogue warp
+    }
     fence_mbar_init();
-  }
-  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), BN < 32 ? 32 : BN);
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
     tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) bias_s[i] = p.bias ? p.bias[n0 + i] : 0.f;
+    for (int i = threadIdx.x - 64; i < p.cout; i += 128) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -86,101 +107,175 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
-      for (int it = 0; it < num_k; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
-        const int tap = it / chunks;
-        const int c = (it - tap * chunks) << 6;
-        const int ky = tap / 3, kx = tap - 3 * ky;
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
-        if (c < p.c0)
-          tma_load_4d(sa, &tmA0, full_bar(s), c, x0 + kx - 1, y0 + ky - 1, img);
-        else
-          tma_load_4d(sa, &tmA1, full_bar(s), c - p.c0, x0 + kx - 1, y0 + ky - 1, img);
-        tma_load_2d(sb, &tmB, full_bar(s), tap * ctot + c, n0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      if (RES) {
+        // whole weight matrix of this (single) n-block: 9 taps x 1 chunk, loaded once
+        mbar_expect_tx(b_full(0), 9 * L::B_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d(sbase + L::B_OFF + tap * L::B_BYTES, &tmB, b_full(0), tap * ctot, 0);
+      }
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int nb = u % n_blocks;
+        const int mtile = u / n_blocks;
+        const int img = mtile / tiles_per_img;
+        const int t = mtile - img * tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int x0 = tx * 8, y0 = ty * (16 * MT);
+        const int n0 = nb * BN;
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int c = ch << 6;
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(a_empty(as), aph ^ 1);
+            mbar_expect_tx(a_full(as), L::A_BYTES);
+            const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
+            if (c < p.c0)
+              tma_load_4d(dst, &tmA0, a_full(as), c, x0 + kx - 1, y0 - 1, img);
+            else
+              tma_load_4d(dst, &tmA1, a_full(as), c - p.c0, x0 + kx - 1, y0 - 1, img);
+            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+            if (!RES) {
+              for (int ky = 0; ky < 3; ++ky) {
+                mbar_wait(b_empty(bs), bph ^ 1);
+                mbar_expect_tx(b_full(bs), L::B_BYTES);
+                tma_load_2d(sbase + L::B_OFF + bs * L::B_BYTES, &tmB, b_full(bs), (ky * 3 + kx) * ctot + c, n0);
+                if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
+              }
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one lane)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-      for (int it = 0; it < num_k; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      uint32_t it = 0;
+      if (RES) {
+        mbar_wait(b_full(0), 0);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        const uint64_t da = umma_desc_k_sw128(sa);
-        const uint64_t db = umma_desc_k_sw128(sa + L::A_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full_bar);
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(acc_empty(buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + buf * (MT * BN);
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(a_full(as), aph);
+            tc_fence_after();
+            const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES;
+            for (int ky = 0; ky < 3; ++ky) {
+              uint32_t sb;
+              if (RES) {
+                sb = sbase + L::B_OFF + (ky * 3 + kx) * L::B_BYTES;
+              } else {
+                mbar_wait(b_full(bs), bph);
+                tc_fence_after();
+                sb = sbase + L::B_OFF + bs * L::B_BYTES;
+              }
+              const uint64_t db = umma_desc_k_sw128(sb);
+              const uint32_t acc = (ch | kx | ky) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t da = umma_desc_k_sw128(sa + (16 * mt + ky) * 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(dcol + mt * BN, da + 2 * k, db + 2 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+              }
+              if (!RES) {
+                umma_commit(b_empty(bs));
+                if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
+              }
+            }
+            umma_commit(a_empty(as));
+            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+          }
+        }
+        umma_commit(acc_full(buf));
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue: 4 warps, one output pixel per thread
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
-    const int lty = row / p.tile_w, ltx = row - lty * p.tile_w;
-    const int y = y0 + lty, x = x0 + ltx;
-    const bool valid = (y < p.H) && (x < p.W);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    __nv_bfloat16* out_px = p.out ? p.out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0 : nullptr;
+    const int lty = row >> 3, ltx = row & 7;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
-    const bool pool_owner = valid && !(lty & 1) && !(ltx & 1);
-    __nv_bfloat16* pool_px =
-        p.out_pool ? p.out_pool + ((static_cast<size_t>(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout + n0 : nullptr;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int nb = u % n_blocks;
+      const int mtile = u / n_blocks;
+      const int img = mtile / tiles_per_img;
+      const int t = mtile - img * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      const int n0 = nb * BN;
+      const int x = tx * 8 + ltx;
+      const uint32_t buf = it & 1;
+      mbar_wait(acc_full(buf), (it >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cb * 32, v);
-      tmem_ld_wait();
-      float f[32];
+      for (int mt = 0; mt < MT; ++mt) {
+        const int y = ty * (16 * MT) + mt * 16 + lty;
+        const bool valid = (y < p.H) && (x < p.W);
+        __nv_bfloat16* out_px =
+            p.out ? p.out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0 : nullptr;
+        const bool pool_owner = valid && !(lty & 1) && !(ltx & 1);
+        __nv_bfloat16* pool_px =
+            p.out_pool ? p.out_pool + ((static_cast<size_t>(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout + n0
+                       : nullptr;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + cb * 32, v);
+          tmem_ld_wait();
+          if (mt == MT - 1 && cb == BN / 32 - 1) {
+            // all TMEM reads of this accumulator buffer are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(buf));
+          }
+          float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]) + bias_s[cb * 32 + j];
-        f[j] = p.relu ? fmaxf(t, 0.f) : t;
-      }
-      if (out_px && valid) {
-        uint4* dst = reinterpret_cast<uint4*>(out_px + cb * 32);
+          for (int j = 0; j < 32; ++j) {
+            float tv = __uint_as_float(v[j]) + bias_s[n0 + cb * 32 + j];
+            f[j] = p.relu ? fmaxf(tv, 0.f) : tv;
+          }
+          if (out_px && valid) {
+            uint4* dst = reinterpret_cast<uint4*>(out_px + cb * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-          dst[j] = o;
-        }
-      }
-      if (pool_px) {
-        // 2x2 average of the fp32 post-ReLU values: partners are lane^1 (x) and lane^tile_w (y)
-        // (H, W even => a valid even pixel always has valid partners).
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              dst[j] = o;
+            }
+          }
+          if (pool_px) {
+            // 2x2 average of the fp32 post-ReLU values: partners are lane^1 (x) and lane^8 (y)
+            // (H, W even => a valid even pixel always has valid partners).
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = valid ? f[j] : 0.f;
-          t += __shfl_xor_sync(0xffffffffu, t, 1);
-          t += __shfl_xor_sync(0xffffffffu, t, p.tile_w);
-          f[j] = 0.25f * t;
-        }
-        if (pool_owner) {
-          uint4* dst = reinterpret_cast<uint4*>(pool_px + cb * 32);
+            for (int j = 0; j < 32; ++j) {
+              float tv = valid ? f[j] : 0.f;
+              tv += __shfl_xor_sync(0xffffffffu, tv, 1);
+              tv += __shfl_xor_sync(0xffffffffu, tv, 8);
+              f[j] = 0.25f * tv;
+            }
+            if (pool_owner) {
+              uint4* dst = reinterpret_cast<uint4*>(pool_px + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            dst[j] = o;
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                dst[j] = o;
+              }
+            }
           }
         }
       }
@@ -189,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,56 +337,61 @@ int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long 
   return r == CUDA_SUCCESS ? PDA_OK : PDA_ERR_TENSORMAP;
 }
 
-template <int BN, int STAGES>
+template <int BN, int MT, bool RES>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvArgs& args,
                        cudaStream_t stream) {
-  using L = ConvSmem<BN, STAGES>;
+  using L = ConvCfg<BN, MT, RES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::DYN_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MT, RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return PDA_ERR_CUDA;
     configured = true;
   }
-  dim3 grid(args.tiles_x * args.tiles_y * args.B, args.cout / BN);
+  const long long units = (long long)args.tiles_x * args.tiles_y * args.B * (args.cout / BN);
+  if (units > 0x7fffffffLL) return PDA_ERR_SHAPE;
+  const int grid = (int)(units < 148 ? units : 148);
   PDA_COUNT(1);
-  conv3x3_tc_kernel<BN, STAGES><<<grid, 192, L::DYN_BYTES, stream>>>(a0, a1, b, args);
+  conv3x3_tc_kernel<BN, MT, RES><<<grid, 192, L::DYN_BYTES, stream>>>(a0, a1, b, args);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, int B, int H, int W, int cout, int relu, int bn_override, cudaStream_t stream) {
-  if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
+  if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
+    return PDA_ERR_SHAPE;
   if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
+  int bn = (bn_override == 64 || bn_override == 128) ? bn_override : ((cout % 128 == 0) ? 128 : 64);
+  if (cout % bn) return PDA_ERR_SHAPE;
+  const int mt = (H > 16) ? 2 : 1;
   ConvArgs a;
   a.B = B; a.H = H; a.W = W; a.c0 = c0; a.c1 = c1; a.cout = cout; a.relu = relu;
-  a.tile_w = (W > 8) ? 16 : 8;
-  a.tile_h = 128 / a.tile_w;
-  a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
+  a.tile_w = 8;
+  a.tile_h = 16 * mt;
+  a.tiles_x = (W + 7) / 8;
   a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
   a.bias = bias;
   a.out = static_cast<__nv_bfloat16*>(out);
   a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
-  int bn = bn_override;
-  if (bn == 0) bn = (cout % 128 == 0) ? 128 : 64;
-  if (cout % bn) return PDA_ERR_SHAPE;
   CUtensorMap tA0, tA1, tB;
-  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, a.tile_w, a.tile_h, 64);
+  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);
   if (r) return r;
   if (c1 > 0) {
-    r = make_act_tensor_map(&tA1, src1, B, H, W, c1, a.tile_w, a.tile_h, 64);
+    r = make_act_tensor_map(&tA1, src1, B, H, W, c1, 8, a.tile_h + 2, 64);
     if (r) return r;
   } else {
     tA1 = tA0;
   }
   r = make_mat_tensor_map(&tB, wpacked, 9LL * (c0 + c1), cout, 64, bn);
   if (r) return r;
-  switch (bn) {
-    case 64: return launch_conv<64, 4>(tA0, tA1, tB, a, stream);
-    case 128: return launch_conv<128, 3>(tA0, tA1, tB, a, stream);
-    case 256: return launch_conv<256, 4>(tA0, tA1, tB, a, stream);
-    default: return PDA_ERR_SHAPE;
+  const bool resident = (bn == 64 && cout == 64 && c0 + c1 == 64 && mt == 2);
+  if (mt == 2) {
+    if (bn == 128) return launch_conv<128, 2, false>(tA0, tA1, tB, a, stream);
+    return resident ? launch_conv<64, 2, true>(tA0, tA1, tB, a, stream)
+                    : launch_conv<64, 2, false>(tA0, tA1, tB, a, stream);
   }
+  if (bn == 128) return launch_conv<128, 1, false>(tA0, tA1, tB, a, stream);
+  return launch_conv<64, 1, false>(tA0, tA1, tB, a, stream);
 }
 
 }  // namespace pda
