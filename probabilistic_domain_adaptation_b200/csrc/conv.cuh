@@ -33,4 +33,31 @@ int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, int B, int H, int W, int cout, int relu, int bn_override, cudaStream_t stream);
 
+// log2(C / 8) for C = 8 * 2^k (the NHWC kernels address 16-byte channel chunks with shifts), else -1
+static inline int c8_shift(int C) {
+  if (C < 8 || (C & 7)) return -1;
+  const int c8 = C >> 3;
+  if (c8 & (c8 - 1)) return -1;
+  int s = 0;
+  while ((1 << s) < c8) ++s;
+  return s;
+}
+
+
+// Element index -> (channel chunk, x, y, image) with 32-bit arithmetic (C8 is a power of two: C in {64..512}).
+struct Px {
+  unsigned c, x, y, b;
+};
+__device__ __forceinline__ Px split_index(unsigned t, int c_shift, unsigned W, unsigned H) {
+  Px p;
+  p.c = t & ((1u << c_shift) - 1u);
+  const unsigned pix = t >> c_shift;
+  const unsigned row = pix / W;
+  p.x = pix - row * W;
+  p.b = row / H;
+  p.y = row - p.b * H;
+  return p;
+}
+
+
 }  // namespace pda

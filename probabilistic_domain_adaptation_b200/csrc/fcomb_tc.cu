@@ -6,11 +6,17 @@
 // The kernel is COMPUTE bound (~1000 FLOP/B at S=16), so the two 64x64 layers run on tcgen05:
 //   per 128-pixel tile:  H1 = F . (W1f_hi + W1f_lo)^T         128x64x64 MMA x2 (bf16 hi/lo split of the fp32 weights
 //                                                            -> ~16-bit mantissa), accumulator in TMEM, read ONCE
-//   per sample s:        A1_s = relu(H1 + bz_s) -> fp16 (saturating) -> swizzled smem operand   (CUDA cores, f32x2)
-//                        H2_s = A1_s . W2^T                  128x64x64 fp16 MMA into one of two TMEM buffers
-//                        logit = w3 . relu(H2_s + b2) + b3 ; p = sigmoid ; mean / consensus in registers
-// bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat.  MMA s+1 is issued before
-// the epilogue of sample s, so tensor pipe, TMEM loads and CUDA-core math overlap; 4 CTAs share an SM.
+//   per sample s:        A1_s = relu(H1 + bz_s) -> fp16 (saturating) -> swizzled smem operand   (producer warps)
+//                        H2_s = [A1_s | 1 1 0..] . [W2 | b2_hi b2_lo 0..]^T   128x64x80 fp16 MMA (bias folded in)
+//                        logit = w3 . relu(H2_s) + b3 ; p = sigmoid ; mean / consensus        (epilogue warps)
+// bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat (fcomb_bz_kernel).
+//
+// Warp-specialised persistent CTA (2 per SM): warps 0-3 = producers (own H1 in registers, write the A1 ring),
+// warps 4-7 = epilogue (TMEM -> relu -> w3 dot with w3 as constant-bank operands -> sigmoid / counters),
+// warp 8 = control (TMA of the feature tile, all tcgen05.mma).  Three mbarrier pipelines (F tile, A1 ring of 3,
+// H2 accumulator ring of 2 in TMEM) let the three roles run concurrently; nothing but the outputs leaves the SM.
+#include <cuda_fp16.h>
+
 #include "conv.cuh"
 #include "ptx.cuh"
 
@@ -18,19 +24,27 @@ namespace pda {
 
 constexpr int FCT = 64;             // feature / hidden channels
 constexpr int FC_TILE = 128;        // pixels per tile == TMEM lanes
-constexpr int FC_TMEM_COLS = 128;   // [0,64): H1 then H2 buffer 0; [64,128): H2 buffer 1
+constexpr int FC_TMEM_COLS = 256;   // [0,64): H1; [64,128), [128,192): H2 ring
+constexpr int FC_A1_STAGES = 3;
+constexpr int FC_THREADS = 288;
+
+// last Fcomb layer as constant-bank operands of the epilogue FFMAs: w3[64], b3.  Refreshed (stream-ordered D2D copy)
+// by every launch; launches that use DIFFERENT weights must therefore not overlap on different streams.
+__constant__ float c_fcomb_w3[FCT + 4];
 
 struct FcombSmem {
-  static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 bf16
-  static constexpr int W_BYTES = FCT * 128;                     // 64 rows x 64 bf16
-  static constexpr int A0_OFF = 0;                              // F tile, later A1 buffer 0
-  static constexpr int A1_OFF = A_BYTES;                        // A1 buffer 1
-  static constexpr int W1_OFF = 2 * A_BYTES;                    // bf16 hi part of W1[:, :64]
+  static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 x 2 B
+  static constexpr int W_BYTES = FCT * 128;                     // 64 rows x 64 x 2 B
+  static constexpr int F_OFF = 0;                               // feature tile (TMA)
+  static constexpr int A1_OFF = A_BYTES;                        // A1 ring
+  static constexpr int W1_OFF = A1_OFF + FC_A1_STAGES * A_BYTES;  // bf16 hi part of W1[:, :64]
   static constexpr int W1L_OFF = W1_OFF + W_BYTES;              // bf16 lo part (w - hi)
   static constexpr int W2_OFF = W1L_OFF + W_BYTES;              // fp16 W2
-  static constexpr int VEC_OFF = W2_OFF + W_BYTES;              // b2[64], w3[64] fp32
-  static constexpr int BAR_OFF = VEC_OFF + 2 * FCT * 4;         // 4 mbarriers
-  static constexpr int SLOT_OFF = BAR_OFF + 4 * 8;
+  static constexpr int W2X_OFF = W2_OFF + W_BYTES;              // fp16 K-extension: col 0 = b2_hi, col 1 = b2_lo
+  static constexpr int AX_OFF = W2X_OFF + W_BYTES;              // 8 rows x 128 B: cols 0,1 = 1.0 (aliased by all rows)
+  static constexpr int BAR_OFF = AX_OFF + 1024;
+  static constexpr int NBARS = 4 + 2 * FC_A1_STAGES + 4;
+  static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[S][64] fp32
   static int bytes(int S) { return BZ_OFF + S * FCT * 4 + 1024; }
 };
@@ -87,10 +101,9 @@ __device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo
   }
 }
 
-__global__ void __launch_bounds__(128, 4)
-fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ z, const float* __restrict__ w1,
-                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                const float* __restrict__ w3, const float* __restrict__ b3, int P, int S, int L, int B,
+__global__ void __launch_bounds__(FC_THREADS, 2)
+fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ bzg, const float* __restrict__ w1,
+                const float* __restrict__ w2, const float* __restrict__ b2, int P, int S, int L, int B,
                 int tiles_per_img, int num_tiles, float upper, float lower, float* __restrict__ mean_prob,
                 float* __restrict__ cons_weight, int64_t* __restrict__ cons_mask, float* __restrict__ logits,
                 float* __restrict__ probs) {
@@ -98,189 +111,249 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t barF = sbase + M::BAR_OFF, barM = barF + 8, barH0 = barF + 16, barH1 = barF + 24;
+  const uint32_t bar0 = sbase + M::BAR_OFF;
+  const uint32_t f_full = bar0, f_empty = bar0 + 8, h1_full = bar0 + 16, h1_empty = bar0 + 24;
+  auto a1_full = [&](int i) { return bar0 + 32 + 8u * i; };
+  auto a1_empty = [&](int i) { return bar0 + 32 + 8u * (FC_A1_STAGES + i); };
+  auto h2_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_STAGES + i); };
+  auto h2_empty = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_STAGES + 2 + i); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + M::SLOT_OFF);
-  float* b2s = reinterpret_cast<float*>(smem + M::VEC_OFF);
-  float* w3s = b2s + FCT;
   float* bzs = reinterpret_cast<float*>(smem + M::BZ_OFF);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kin = FCT + L;
 
   if (tid == 0) {
-    mbar_init(barF, 1);
-    mbar_init(barM, 1);
-    mbar_init(barH0, 1);
-    mbar_init(barH1, 1);
+    mbar_init(f_full, 1);
+    mbar_init(f_empty, 1);
+    mbar_init(h1_full, 1);
+    mbar_init(h1_empty, 4);
+    for (int i = 0; i < FC_A1_STAGES; ++i) {
+      mbar_init(a1_full(i), 4);
+      mbar_init(a1_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(h2_full(i), 1);
+      mbar_init(h2_empty(i), 4);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmF);
   }
-  if (warp == 0) {
+  if (warp == 8) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), FC_TMEM_COLS);
     tmem_relinquish();
   }
   stage_weight_sw128(smem + M::W1_OFF, smem + M::W1L_OFF, w1, kin);
   stage_weight_sw128(smem + M::W2_OFF, nullptr, w2, FCT);
-  if (tid < FCT) {
-    b2s[tid] = b2[tid];
-    w3s[tid] = w3[tid];
+  // K-extension tiles: B rows n carry (b2_hi, b2_lo) in k = 0, 1; the A rows carry (1, 1).  Only the first 16 k
+  // (two 16-byte chunks) of each 128-byte row are read by the K = 16 MMA.
+  for (int i = tid; i < FCT * 8; i += blockDim.x) {
+    const int n = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c == 0) {
+      const float b = b2[n];
+      const float bh = __half2float(__float2half_rn(b));
+      v.x = pack_f16x2(bh, b - bh);
+    }
+    *reinterpret_cast<uint4*>(smem + M::W2X_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
-  fence_proxy_async_smem();  // weight tiles were written by the generic proxy, read by the tensor core
+  if (tid < 64) {
+    const int n = tid >> 3, c = tid & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c == 0) v.x = 0x3C003C00u;  // (1.0h, 1.0h)
+    *reinterpret_cast<uint4*>(smem + M::AX_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+  }
+  fence_proxy_async_smem();  // operand tiles were written by the generic proxy, read by the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float b3v = b3[0];
-  constexpr uint32_t idesc1 = umma_idesc_bf16(128, FCT);  // F (bf16) x W1 hi/lo (bf16)
-  constexpr uint32_t idesc2 = umma_idesc_f16(128, FCT);   // A1 (fp16) x W2 (fp16)
-  const uint64_t dW1 = umma_desc_k_sw128(sbase + M::W1_OFF);
-  const uint64_t dW1L = umma_desc_k_sw128(sbase + M::W1L_OFF);
-  const uint64_t dW2 = umma_desc_k_sw128(sbase + M::W2_OFF);
-  const uint64_t dA0 = umma_desc_k_sw128(sbase + M::A0_OFF), dA1 = umma_desc_k_sw128(sbase + M::A1_OFF);
-  uint8_t* const arow0 = smem + M::A0_OFF + tid * 128;
-  uint8_t* const arow1 = smem + M::A1_OFF + tid * 128;
-  const int sw = tid & 7;
-  uint32_t phF = 0, phM = 0, phH0 = 0, phH1 = 0;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_img;
-    const int p0 = (tile - b * tiles_per_img) * FC_TILE;
-    // ---- F tile -> smem (TMA, rows beyond P are zero-filled), H1 = F . W1f^T
-    if (tid == 0) {
-      mbar_expect_tx(barF, M::A_BYTES);
-      tma_load_3d(sbase + M::A0_OFF, &tmF, barF, 0, p0, b);
-    }
-    // per-(sample, image) bias of layer 1 while the tile is in flight
-    for (int i = tid; i < S * FCT; i += blockDim.x) {
-      const int s = i / FCT, j = i - s * FCT;
-      float acc = b1[j];
-      const float* zr = z + (static_cast<size_t>(s) * B + b) * L;
-      for (int d = 0; d < L; ++d) acc = fmaf(w1[j * kin + FCT + d], zr[d], acc);
-      bzs[i] = acc;
-    }
-    if (tid == 0) {
-      mbar_wait(barF, phF);
+  if (warp < 4) {
+    // ================================================================ producers
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const int sw = tid & 7;
+    uint32_t a_it = 0, t_it = 0;
+    int cur_b = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+      const int b = tile / tiles_per_img;
+      if (b != cur_b) {
+        named_bar_sync(1, 128);  // every producer is done with the previous image's bz
+        for (int i = tid; i < S * (FCT / 4); i += 128) {
+          const int s = i / (FCT / 4), j4 = i - s * (FCT / 4);
+          reinterpret_cast<float4*>(bzs)[i] =
+              __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s) * B + b) * FCT) + j4);
+        }
+        named_bar_sync(1, 128);
+        cur_b = b;
+      }
+      // ---- H1 -> registers (kept for all samples), as packed f32x2
+      mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dA0 + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dA0 + 2 * k, dW1L + 2 * k, idesc1, 1u);
-      umma_commit(barM);
-    }
-    phF ^= 1;
-    __syncthreads();  // bzs visible
-    mbar_wait(barM, phM);
-    phM ^= 1;
-    tc_fence_after();
-    // ---- H1 -> registers (kept for all samples), as packed f32x2
-    uint64_t h1[FCT / 2];
-    {
-      uint32_t v[32];
-      tmem_ld32(lane_addr, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) h1[i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
-      tmem_ld32(lane_addr + 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) h1[16 + i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
-    }
-
-    auto produce = [&](int s) {
-      // A1_s = relu(H1 + bz_s) as fp16, this thread's 128-byte row, 16-byte chunks XOR-swizzled by (row & 7)
-      const float4* bz4 = reinterpret_cast<const float4*>(bzs + s * FCT);
-      uint8_t* row = (s & 1) ? arow1 : arow0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 ba = bz4[2 * c], bb = bz4[2 * c + 1];
-        float x0, x1, x2, x3, x4, x5, x6, x7;
-        unpack_f32x2(add_f32x2(h1[4 * c + 0], pack_f32x2(ba.x, ba.y)), x0, x1);
-        unpack_f32x2(add_f32x2(h1[4 * c + 1], pack_f32x2(ba.z, ba.w)), x2, x3);
-        unpack_f32x2(add_f32x2(h1[4 * c + 2], pack_f32x2(bb.x, bb.y)), x4, x5);
-        unpack_f32x2(add_f32x2(h1[4 * c + 3], pack_f32x2(bb.z, bb.w)), x6, x7);
-        uint4 o;
-        o.x = relu_pack_f16x2(x0, x1);
-        o.y = relu_pack_f16x2(x2, x3);
-        o.z = relu_pack_f16x2(x4, x5);
-        o.w = relu_pack_f16x2(x6, x7);
-        *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = o;
-      }
-    };
-    auto issue = [&](int s) {
-      // all 128 threads: publish smem writes to the async proxy, order prior TMEM reads, then one thread issues
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(1, 128);
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t d = tmem + (s & 1) * FCT;
-        const uint64_t da = (s & 1) ? dA1 : dA0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
-        umma_commit((s & 1) ? barH1 : barH0);
-      }
-    };
-
-    const int pix = p0 + tid;
-    const bool valid = pix < P;
-    const size_t gp = static_cast<size_t>(b) * P + pix;
-    float psum = 0.f;
-    int count = 0;
-    produce(0);
-    issue(0);
-    for (int s = 0; s < S; ++s) {
-      if (s + 1 < S) {
-        produce(s + 1);
-        issue(s + 1);
-      }
-      const int buf = s & 1;
-      if (buf) {
-        mbar_wait(barH1, phH1);
-        phH1 ^= 1;
-      } else {
-        mbar_wait(barH0, phH0);
-        phH0 ^= 1;
-      }
-      tc_fence_after();
-      float logit = b3v;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      uint64_t h1[FCT / 2];
+      {
         uint32_t v[32];
-        tmem_ld32(lane_addr + buf * FCT + half * 32, v);
+        tmem_ld32(lane_addr, v);
         tmem_ld_wait();
-        const float4* b24 = reinterpret_cast<const float4*>(b2s + half * 32);
-        const float4* w34 = reinterpret_cast<const float4*>(w3s + half * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = b24[i], ww = w34[i];
-          logit = fmaf(ww.x, fmaxf(__uint_as_float(v[4 * i + 0]) + bb.x, 0.f), logit);
-          logit = fmaf(ww.y, fmaxf(__uint_as_float(v[4 * i + 1]) + bb.y, 0.f), logit);
-          logit = fmaf(ww.z, fmaxf(__uint_as_float(v[4 * i + 2]) + bb.z, 0.f), logit);
-          logit = fmaf(ww.w, fmaxf(__uint_as_float(v[4 * i + 3]) + bb.w, 0.f), logit);
+        for (int i = 0; i < 16; ++i) h1[i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
+        tmem_ld32(lane_addr + 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h1[16 + i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h1_empty);
+      for (int s = 0; s < S; ++s, ++a_it) {
+        const uint32_t slot = a_it % FC_A1_STAGES;
+        mbar_wait(a1_empty(slot), ((a_it / FC_A1_STAGES) & 1) ^ 1);
+        // A1_s = relu(H1 + bz_s) as fp16, this thread's 128-byte row, 16-byte chunks XOR-swizzled by (row & 7)
+        const float4* bz4 = reinterpret_cast<const float4*>(bzs + s * FCT);
+        uint8_t* row = smem + M::A1_OFF + slot * M::A_BYTES + tid * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 ba = bz4[2 * c], bb = bz4[2 * c + 1];
+          float x0, x1, x2, x3, x4, x5, x6, x7;
+          unpack_f32x2(add_f32x2(h1[4 * c + 0], pack_f32x2(ba.x, ba.y)), x0, x1);
+          unpack_f32x2(add_f32x2(h1[4 * c + 1], pack_f32x2(ba.z, ba.w)), x2, x3);
+          unpack_f32x2(add_f32x2(h1[4 * c + 2], pack_f32x2(bb.x, bb.y)), x4, x5);
+          unpack_f32x2(add_f32x2(h1[4 * c + 3], pack_f32x2(bb.z, bb.w)), x6, x7);
+          uint4 o;
+          o.x = relu_pack_f16x2(x0, x1);
+          o.y = relu_pack_f16x2(x2, x3);
+          o.z = relu_pack_f16x2(x4, x5);
+          o.w = relu_pack_f16x2(x6, x7);
+          *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = o;
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a1_full(slot));
+      }
+    }
+  } else if (warp < 8) {
+    // ================================================================ epilogue
+    const int q = warp & 3;
+    const int prow = q * 32 + lane;  // pixel row of this thread inside the tile
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t e_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int pix = (tile - b * tiles_per_img) * FC_TILE + prow;
+      const bool valid = pix < P;
+      const size_t gp = static_cast<size_t>(b) * P + pix;
+      float psum = 0.f;
+      int count = 0;
+      for (int s = 0; s < S; ++s, ++e_it) {
+        const uint32_t hb = e_it & 1;
+        mbar_wait(h2_full(hb), (e_it >> 1) & 1);
+        tc_fence_after();
+        float l0 = c_fcomb_w3[FCT], l1 = 0.f, l2 = 0.f, l3 = 0.f;  // b3 + four independent chains
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + FCT + hb * FCT + half * 32, v);
+          tmem_ld_wait();
+          if (half == 1) {
+            // both halves are in registers: the accumulator buffer can be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h2_empty(hb));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            l0 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 0], fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), l0);
+            l1 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 1], fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), l1);
+            l2 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 2], fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), l2);
+            l3 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 3], fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), l3);
+          }
+        }
+        const float logit = (l0 + l1) + (l2 + l3);
+        const float pr = __fdividef(1.0f, 1.0f + __expf(-logit));
+        psum += pr;
+        count += (pr >= upper || pr <= lower) ? 1 : 0;
+        if (valid) {
+          if (logits) logits[(static_cast<size_t>(s) * B + b) * P + pix] = logit;
+          if (probs) probs[(static_cast<size_t>(s) * B + b) * P + pix] = pr;
         }
       }
-      const float pr = 1.0f / (1.0f + expf(-logit));
-      psum += pr;
-      count += (pr >= upper || pr <= lower) ? 1 : 0;
       if (valid) {
-        if (logits) logits[(static_cast<size_t>(s) * B + b) * P + pix] = logit;
-        if (probs) probs[(static_cast<size_t>(s) * B + b) * P + pix] = pr;
+        if (mean_prob) mean_prob[gp] = psum / static_cast<float>(S);
+        if (cons_weight) cons_weight[gp] = static_cast<float>(count) / static_cast<float>(S);
+        if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
       }
     }
-    if (valid) {
-      if (mean_prob) mean_prob[gp] = psum / static_cast<float>(S);
-      if (cons_weight) cons_weight[gp] = static_cast<float>(count) / static_cast<float>(S);
-      if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
+  } else if (lane == 0) {
+    // ================================================================ control: TMA + every tcgen05.mma
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, FCT);  // F (bf16) x W1 hi/lo (bf16)
+    constexpr uint32_t idesc2 = umma_idesc_f16(128, FCT);   // A1 (fp16) x W2 (fp16)
+    const uint64_t dW1 = umma_desc_k_sw128(sbase + M::W1_OFF);
+    const uint64_t dW1L = umma_desc_k_sw128(sbase + M::W1L_OFF);
+    const uint64_t dW2 = umma_desc_k_sw128(sbase + M::W2_OFF);
+    const uint64_t dW2X = umma_desc_k_sw128(sbase + M::W2X_OFF);
+    const uint64_t dF = umma_desc_k_sw128(sbase + M::F_OFF);
+    const uint64_t dAX = umma_desc_k_sw128(sbase + M::AX_OFF, /*sbo_bytes=*/0);  // all 8-row groups alias one atom
+    auto load_tile = [&](int tile) {
+      const int b = tile / tiles_per_img;
+      mbar_expect_tx(f_full, M::A_BYTES);
+      tma_load_3d(sbase + M::F_OFF, &tmF, f_full, 0, (tile - b * tiles_per_img) * FC_TILE, b);
+    };
+    auto mma1 = [&](uint32_t t_it) {
+      // H1 = F . (W1 hi + lo)^T once the tile has landed and the producers have drained the previous H1
+      mbar_wait(f_full, t_it & 1);
+      mbar_wait(h1_empty, (t_it & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1L + 2 * k, idesc1, 1u);
+      umma_commit(h1_full);
+      umma_commit(f_empty);
+    };
+    uint32_t a_it = 0, t_it = 0;
+    int tile = blockIdx.x;
+    if (tile < num_tiles) {
+      load_tile(tile);
+      mma1(0);
     }
-    // every thread has finished reading TMEM / bzs before the next tile overwrites them
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    for (; tile < num_tiles; tile += gridDim.x, ++t_it) {
+      const int next = tile + gridDim.x;
+      if (next < num_tiles) {
+        mbar_wait(f_empty, t_it & 1);  // MMA1 of this tile has consumed the feature tile
+        load_tile(next);
+      }
+      for (int s = 0; s < S; ++s, ++a_it) {
+        const uint32_t slot = a_it % FC_A1_STAGES, hb = a_it & 1;
+        mbar_wait(a1_full(slot), (a_it / FC_A1_STAGES) & 1);
+        mbar_wait(h2_empty(hb), ((a_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + FCT + hb * FCT;
+        const uint64_t da = umma_desc_k_sw128(sbase + M::A1_OFF + slot * M::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
+        umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
+        umma_commit(h2_full(hb));
+        umma_commit(a1_empty(slot));
+        // next tile's H1 as soon as half of this tile's samples are issued (the producers copied H1 to registers at
+        // the start of the tile, so the TMEM columns are free; the feature tile was prefetched above)
+        if (s == (S >> 1) && next < num_tiles) mma1(t_it + 1);
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, FC_TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem, FC_TMEM_COLS);
+}
+
+// bz[s][b][j] = b1[j] + sum_d W1[j][64 + d] * z[s][b][d]: the per-(sample, image) bias that replaces the tiled-z concat
+__global__ void fcomb_bz_kernel(const float* __restrict__ z, const float* __restrict__ w1, const float* __restrict__ b1,
+                                float* __restrict__ bz, int SB, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SB * FCT) return;
+  const int sb = i / FCT, j = i - sb * FCT;
+  float acc = b1[j];
+  for (int d = 0; d < L; ++d) acc = fmaf(w1[j * (FCT + L) + FCT + d], z[sb * L + d], acc);
+  bz[i] = acc;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -311,6 +384,12 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PDA_ERR_TENSORMAP;
+  cudaStream_t st = (cudaStream_t)stream;
+  // last layer -> constant bank (stream-ordered device-to-device copies)
+  if (cudaMemcpyToSymbolAsync(c_fcomb_w3, w3, sizeof(float) * FCT, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+      cudaMemcpyToSymbolAsync(c_fcomb_w3, b3, sizeof(float), sizeof(float) * FCT, cudaMemcpyDeviceToDevice, st) !=
+          cudaSuccess)
+    return PDA_ERR_CUDA;
   static int configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(fcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -320,10 +399,20 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   const int tiles_per_img = (P + FC_TILE - 1) / FC_TILE;
   const long long num_tiles = (long long)tiles_per_img * B;
   if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
-  const int grid = (int)(num_tiles < 148 * 4 ? num_tiles : 148 * 4);
-  PDA_COUNT(1);
-  fcomb_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tm, z, w1, b1, w2, b2, w3, b3, P, S, latent, B,
-                                                             tiles_per_img, (int)num_tiles, upper, lower, mean_prob,
-                                                             cons_weight, cons_mask, logits, probs);
-  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+  // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise)
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fcomb_tc_kernel, FC_THREADS, smem) != cudaSuccess ||
+      per_sm < 1)
+    return PDA_ERR_CUDA;
+  if (per_sm > 2) per_sm = 2;  // 2 x 256 TMEM columns
+  const int grid = (int)(num_tiles < 148 * per_sm ? num_tiles : 148 * per_sm);
+  float* bz = nullptr;
+  if (cudaMallocAsync(&bz, sizeof(float) * (size_t)S * B * FCT, st) != cudaSuccess) return PDA_ERR_CUDA;
+  PDA_COUNT(2);
+  fcomb_bz_kernel<<<(S * B * FCT + 255) / 256, 256, 0, st>>>(z, w1, b1, bz, S * B, latent);
+  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, P, S, latent, B, tiles_per_img, (int)num_tiles,
+                                                  upper, lower, mean_prob, cons_weight, cons_mask, logits, probs);
+  const cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(bz, st);
+  return e == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

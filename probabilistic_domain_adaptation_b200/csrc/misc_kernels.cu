@@ -31,61 +31,82 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math.  Each thread owns 8 output channels
-// (weights live in registers for the whole kernel) and walks over pixels; the 8 threads of a pixel
-// write one contiguous 128-byte row (cout = 64).
+// first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math (K = 9 / 18 is too thin for the tensor cores; the
+// layer is bound by its 128 B/px output).  A thread owns 8 output channels of 4 consecutive pixels of one row:
+// 18 (36) input loads and 18 (36) 128-bit shared-memory weight reads feed 288 (576) FMAs; the 8 threads of a pixel
+// write one contiguous 128-byte line.  All index math is 32-bit, one division per 4 pixels.
 // ------------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ w,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int cout,
                   int relu) {
-  const int groups = cout >> 3;
-  const int g = threadIdx.x % groups;              // output-channel group of this thread (fixed)
-  const int lanes_px = blockDim.x / groups;        // pixels processed by a block per iteration
-  const int lpx = threadIdx.x / groups;
-  float wr[CIN][9][8], br[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    br[j] = bias[g * 8 + j];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) wr[ci][t][j] = w[((g * 8 + j) * CIN + ci) * 9 + t];  // OIHW
+  extern __shared__ __align__(16) float wsm[];  // [CIN][9][cout] then bias[cout]
+  float* bsm = wsm + CIN * 9 * cout;
+  for (int i = threadIdx.x; i < CIN * 9 * cout; i += blockDim.x) {
+    const int co = i % cout, t = (i / cout) % 9, ci = i / (9 * cout);
+    wsm[i] = w[(co * CIN + ci) * 9 + t];  // OIHW -> [ci][tap][co]
   }
-  const long long npix = (long long)B * H * W;
-  for (long long pix = (long long)blockIdx.x * lanes_px + lpx; pix < npix; pix += (long long)gridDim.x * lanes_px) {
-    const int x = pix % W;
-    const int y = (pix / W) % H;
-    const long long img_off = (pix / ((long long)W * H)) * H * W;
-    float acc[8];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) bsm[i] = bias[i];
+  __syncthreads();
+  const int groups = cout >> 3;                    // 8-channel groups per pixel
+  const int g = threadIdx.x % groups;
+  const int quads_per_blk = blockDim.x / groups;
+  const int lq = threadIdx.x / groups;
+  const unsigned quads_per_row = (unsigned)(W + 3) >> 2;
+  const unsigned total_quads = quads_per_row * (unsigned)H * (unsigned)B;
+  for (unsigned q = blockIdx.x * quads_per_blk + lq; q < total_quads; q += gridDim.x * quads_per_blk) {
+    const unsigned row = q / quads_per_row;        // = b * H + y
+    const int xq = (int)(q - row * quads_per_row) << 2;
+    const int y = (int)(row % (unsigned)H);
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[px][j] = bsm[g * 8 + j];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      const float* xp = (ci == 0 ? x0 : x1) + img_off;
+      const float* plane = (ci == 0 ? x0 : x1) + (size_t)(row - y) * W;  // start of image b
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = y + ky - 1;
+        float in[6];
+        const bool rowok = (yy >= 0) && (yy < H);
+        const float* rp = plane + (size_t)yy * W;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int xx = xq + k - 1;
+          in[k] = (rowok && xx >= 0 && xx < W) ? __ldg(rp + xx) : 0.f;
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int xx = x + kx - 1;
-          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (long long)yy * W + xx) : 0.f;
+          const float4 wa = *reinterpret_cast<const float4*>(wsm + (ci * 9 + ky * 3 + kx) * cout + g * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wsm + (ci * 9 + ky * 3 + kx) * cout + g * 8 + 4);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[ci][ky * 3 + kx][j], acc[j]);
+          for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(in[px + kx], wv[j], acc[px][j]);
         }
       }
     }
-    if (relu) {
+    __nv_bfloat16* orow = out + ((size_t)row * W + xq) * cout + g * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    for (int px = 0; px < 4; ++px) {
+      if (xq + px < W) {
+        float* a = acc[px];
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(a[0], a[1]);
+        o.y = pack_bf16x2(a[2], a[3]);
+        o.z = pack_bf16x2(a[4], a[5]);
+        o.w = pack_bf16x2(a[6], a[7]);
+        *reinterpret_cast<uint4*>(orow + (size_t)px * cout) = o;
+      }
     }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(out + pix * cout + g * 8) = o;
   }
 }
 
@@ -110,26 +131,23 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
-__global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
-  const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)B * Ho * Wo * C8;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = t % C8;
-    const long long pix = t / C8;
-    const int x = pix % Wo;
-    const int y = (pix / Wo) % Ho;
-    const int b = pix / ((long long)Wo * Ho);
-    const long long base = (((long long)b * H + 2 * y) * W + 2 * x) * C8 + c;
+__global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                                int c_shift) {
+  const unsigned Ho = H >> 1, Wo = W >> 1;
+  const unsigned C8 = 1u << c_shift;
+  const unsigned total = (unsigned)B * Ho * Wo * C8;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const Px q = split_index(t, c_shift, Wo, Ho);
+    const size_t base = ((((size_t)q.b * H + 2 * q.y) * W + 2 * q.x) << c_shift) + q.c;
     float a[8], s[8];
     unpack8(__ldg(in + base), s);
     unpack8(__ldg(in + base + C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += a[i];
-    unpack8(__ldg(in + base + (long long)W * C8), a);
+    unpack8(__ldg(in + base + (size_t)W * C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += a[i];
-    unpack8(__ldg(in + base + (long long)W * C8 + C8), a);
+    unpack8(__ldg(in + base + (size_t)W * C8 + C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = (s[i] + a[i]) * 0.25f;
     out[t] = pack8(s);
@@ -139,29 +157,28 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict_
 // ------------------------------------------------------------------------------------------------
 // bilinear x2, align_corners=True (ATen upsample_bilinear2d arithmetic: src = dst*(in-1)/(out-1))
 // ------------------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h, int w, int C8) {
-  const int Ho = 2 * h, Wo = 2 * w;
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h, int w, int c_shift) {
+  const unsigned Ho = 2 * h, Wo = 2 * w;
+  const unsigned C8 = 1u << c_shift;
   const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)B * Ho * Wo * C8;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = t % C8;
-    const long long pix = t / C8;
-    const int x = pix % Wo;
-    const int y = (pix / Wo) % Ho;
-    const int b = pix / ((long long)Wo * Ho);
-    const float sy = rh * y, sx = rw * x;
+  const unsigned total = (unsigned)B * Ho * Wo * C8;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const Px q = split_index(t, c_shift, Wo, Ho);
+    const float sy = rh * q.y, sx = rw * q.x;
     const int y1 = (int)sy, x1 = (int)sx;
     const int yp = (y1 < h - 1) ? 1 : 0, xp = (x1 < w - 1) ? 1 : 0;
     const float ly1 = sy - y1, lx1 = sx - x1;
     const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const uint4* p = in + (((long long)b * h + y1) * w + x1) * C8 + c;
+    const uint4* p = in + ((((size_t)q.b * h + y1) * w + x1) << c_shift) + q.c;
+    const uint4 r00 = __ldg(p), r01 = __ldg(p + ((size_t)xp << c_shift));
+    const uint4 r10 = __ldg(p + (((size_t)yp * w) << c_shift)), r11 = __ldg(p + (((size_t)yp * w + xp) << c_shift));
     float v00[8], v01[8], v10[8], v11[8], o[8];
-    unpack8(__ldg(p), v00);
-    unpack8(__ldg(p + (long long)xp * C8), v01);
-    unpack8(__ldg(p + (long long)yp * w * C8), v10);
-    unpack8(__ldg(p + ((long long)yp * w + xp) * C8), v11);
+    unpack8(r00, v00);
+    unpack8(r01, v01);
+    unpack8(r10, v10);
+    unpack8(r11, v11);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       o[i] = ly0 * (lx0 * v00[i] + lx1 * v01[i]) + ly1 * (lx0 * v10[i] + lx1 * v11[i]);
@@ -345,14 +362,17 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
   if (!x0 || !w || !bias || !out) return PDA_ERR_ARG;
   if (cout <= 0 || (cout & 7) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
   const int groups = cout >> 3;
-  if (256 % groups) return PDA_ERR_SHAPE;
-  const long long total = (long long)B * H * W * groups;
+  if (256 % groups || cout > 256) return PDA_ERR_SHAPE;
+  const long long quads = (long long)B * H * ((W + 3) / 4);
+  if (quads * groups >= 0x7fffffffLL) return PDA_ERR_SHAPE;
+  const int cin = x1 ? 2 : 1;
+  const size_t smem = sizeof(float) * (cin * 9 * cout + cout);
   PDA_COUNT(1);
   if (x1)
-    conv_first_kernel<2><<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+    conv_first_kernel<2><<<grid_for(quads * groups, 256, 148 * 6), 256, smem, (cudaStream_t)stream>>>(
         x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
   else
-    conv_first_kernel<1><<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+    conv_first_kernel<1><<<grid_for(quads * groups, 256, 148 * 6), 256, smem, (cudaStream_t)stream>>>(
         x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
@@ -391,21 +411,23 @@ int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, co
 
 int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
   if (!in || !out) return PDA_ERR_ARG;
-  if ((H & 1) || (W & 1) || (C & 7) || B <= 0) return PDA_ERR_SHAPE;
+  if ((H & 1) || (W & 1) || B <= 0 || c8_shift(C) < 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
   avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
 int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w, int C, void* stream) {
   if (!in || !out) return PDA_ERR_ARG;
-  if ((C & 7) || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
+  if (c8_shift(C) < 0 || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (2 * h) * (2 * w) * (C / 8);
+  if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, C / 8);
+  upsample2x_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 

@@ -36,11 +36,11 @@ static inline int grid_cap(long long total, int block, int cap = 148 * 16) {
 // AvgPool2d that consumes the block output (unet_blocks.py:17).  NHWC bf16; dFull / dPool may be NULL.
 // ------------------------------------------------------------------------------------------------
 __global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ dpool,
-                                     const uint4* __restrict__ y, uint4* __restrict__ dz, int B, int H, int W, int C8) {
-  const long long total = (long long)B * H * W * C8;
-  const int Hp = H >> 1, Wp = W >> 1;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
+                                     const uint4* __restrict__ y, uint4* __restrict__ dz, int B, int H, int W,
+                                     int c_shift) {
+  const unsigned total = ((unsigned)B * H * W) << c_shift;
+  const unsigned Hp = H >> 1, Wp = W >> 1;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     float g[8], a[8], yv[8];
     if (dfull) {
       unpack8f(__ldg(dfull + t), g);
@@ -49,12 +49,8 @@ __global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint
       for (int i = 0; i < 8; ++i) g[i] = 0.f;
     }
     if (dpool) {
-      const int c = t % C8;
-      const long long pix = t / C8;
-      const int x = pix % W;
-      const int yy = (pix / W) % H;
-      const int b = pix / ((long long)W * H);
-      unpack8f(__ldg(dpool + (((long long)b * Hp + (yy >> 1)) * Wp + (x >> 1)) * C8 + c), a);
+      const Px q = split_index(t, c_shift, W, H);
+      unpack8f(__ldg(dpool + ((((size_t)q.b * Hp + (q.y >> 1)) * Wp + (q.x >> 1)) << c_shift) + q.c), a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = fmaf(0.25f, a[i], g[i]);
     }
@@ -72,18 +68,14 @@ __global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint
 // every input pixel sums the output-gradient pixels whose footprint contains it (deterministic).
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int B, int h, int w,
-                                      int C8) {
+                                      int c_shift) {
   const int Ho = 2 * h, Wo = 2 * w;
   const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)B * h * w * C8;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = t % C8;
-    const long long pix = t / C8;
-    const int x = pix % w;
-    const int y = (pix / w) % h;
-    const int b = pix / ((long long)w * h);
+  const unsigned total = ((unsigned)B * h * w) << c_shift;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const Px q = split_index(t, c_shift, w, h);
+    const int x = q.x, y = q.y;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -109,7 +101,7 @@ __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __r
         if (x1 + xp == x) wx += lx1;
         if (wx == 0.f) continue;
         float g[8];
-        unpack8f(__ldg(dout + (((long long)b * Ho + Y) * Wo + X) * C8 + c), g);
+        unpack8f(__ldg(dout + ((((size_t)q.b * Ho + Y) * Wo + X) << c_shift) + q.c), g);
         const float wgt = wy * wx;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, g[i], acc[i]);
@@ -218,15 +210,14 @@ __global__ void gauss_head_bwd_small_kernel(const float* __restrict__ dmls, cons
 }
 
 __global__ void gauss_head_bwd_enc_kernel(const float* __restrict__ dmean, const uint4* __restrict__ enc,
-                                          uint4* __restrict__ denc, int B, int P, int C8) {
-  const long long total = (long long)B * P * C8;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = t % C8;
-    const int b = t / ((long long)P * C8);
+                                          uint4* __restrict__ denc, int B, int P, int c_shift) {
+  const unsigned total = ((unsigned)B * P) << c_shift;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned c = t & ((1u << c_shift) - 1u);
+    const unsigned b = (t >> c_shift) / (unsigned)P;
     float e[8], g[8];
     unpack8f(__ldg(enc + t), e);
-    const float* dm = dmean + (long long)b * C8 * 8 + c * 8;
+    const float* dm = dmean + (((size_t)b << c_shift) + c) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] = e[i] > 0.f ? dm[i] : 0.f;
     denc[t] = pack8f(g);
@@ -712,22 +703,24 @@ extern "C" {
 int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, int B, int H, int W, int C,
                            void* stream) {
   if (!dz || (!dfull && !dpool)) return PDA_ERR_ARG;
-  if ((C & 7) || B <= 0 || (dpool && ((H & 1) || (W & 1)))) return PDA_ERR_SHAPE;
+  if (c8_shift(C) < 0 || B <= 0 || (dpool && ((H & 1) || (W & 1)))) return PDA_ERR_SHAPE;
   const long long total = (long long)B * H * W * (C / 8);
+  if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
   relu_pool_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
       static_cast<const uint4*>(dfull), static_cast<const uint4*>(dpool), static_cast<const uint4*>(y),
-      static_cast<uint4*>(dz), B, H, W, C / 8);
+      static_cast<uint4*>(dz), B, H, W, c8_shift(C));
   return LAUNCH_OK();
 }
 
 int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream) {
   if (!dout || !din) return PDA_ERR_ARG;
-  if ((C & 7) || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
+  if (c8_shift(C) < 0 || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * h * w * (C / 8);
+  if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  upsample2x_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(static_cast<const uint4*>(dout),
-                                                                      static_cast<uint4*>(din), B, h, w, C / 8);
+  upsample2x_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
+      static_cast<const uint4*>(dout), static_cast<uint4*>(din), B, h, w, c8_shift(C));
   return LAUNCH_OK();
 }
 
@@ -766,7 +759,7 @@ int pda_gauss_head_mean(const float* scratch, float* mean, int B, int P, int C, 
 int pda_gauss_head_bwd(const float* dmls, const float* w_head, const float* mean, const void* enc, float* dw,
                        float* db, float* dmean_scratch, void* denc, int B, int P, int C, int latent, void* stream) {
   if (!dmls || !w_head || !mean || !enc || !dw || !db || !dmean_scratch || !denc) return PDA_ERR_ARG;
-  if ((C & 7) || B <= 0 || P <= 0) return PDA_ERR_SHAPE;
+  if (c8_shift(C) < 0 || B <= 0 || P <= 0 || (long long)B * P * (C / 8) >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   const int nout = 2 * latent;
   int n = nout * C;
   if (B * C > n) n = B * C;
@@ -775,7 +768,7 @@ int pda_gauss_head_bwd(const float* dmls, const float* w_head, const float* mean
                                                                        nout, 1.f / (float)P);
   const long long total = (long long)B * P * (C / 8);
   gauss_head_bwd_enc_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
-      dmean_scratch, static_cast<const uint4*>(enc), static_cast<uint4*>(denc), B, P, C / 8);
+      dmean_scratch, static_cast<const uint4*>(enc), static_cast<uint4*>(denc), B, P, c8_shift(C));
   return LAUNCH_OK();
 }
 
