@@ -105,77 +105,90 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      if (RES) {
-        // whole weight matrix of this (single) n-block: 9 taps x 1 chunk, loaded once
+    // ------------------------------------------------------------ TMA producer
+    // The whole warp runs the (warp-uniform) control flow so that addresses and coordinates live in uniform
+    // registers; one elected lane issues the TMA instructions.
+    const bool leader = elect_one();
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    if (RES) {
+      // whole weight matrix of this (single) n-block: 9 taps x 1 chunk, loaded once
+      if (leader) {
         mbar_expect_tx(b_full(0), 9 * L::B_BYTES);
         for (int tap = 0; tap < 9; ++tap)
           tma_load_2d(sbase + L::B_OFF + tap * L::B_BYTES, &tmB, b_full(0), tap * ctot, 0);
       }
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int nb = u % n_blocks;
-        const int mtile = u / n_blocks;
-        const int img = mtile / tiles_per_img;
-        const int t = mtile - img * tiles_per_img;
-        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-        const int x0 = tx * 8, y0 = ty * (16 * MT);
-        const int n0 = nb * BN;
-        for (int ch = 0; ch < chunks; ++ch) {
-          const int c = ch << 6;
-          for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(a_empty(as), aph ^ 1);
+      __syncwarp();
+    }
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int nb = u % n_blocks;
+      const int mtile = u / n_blocks;
+      const int img = mtile / tiles_per_img;
+      const int t = mtile - img * tiles_per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      const int x0 = tx * 8, y0 = ty * (16 * MT);
+      const int n0 = nb * BN;
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int c = ch << 6;
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(a_empty(as), aph ^ 1);
+          if (leader) {
             mbar_expect_tx(a_full(as), L::A_BYTES);
             const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
             if (c < p.c0)
               tma_load_4d(dst, &tmA0, a_full(as), c, x0 + kx - 1, y0 - 1, img);
             else
               tma_load_4d(dst, &tmA1, a_full(as), c - p.c0, x0 + kx - 1, y0 - 1, img);
-            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
-            if (!RES) {
-              for (int ky = 0; ky < 3; ++ky) {
-                mbar_wait(b_empty(bs), bph ^ 1);
+          }
+          __syncwarp();
+          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+          if (!RES) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(b_empty(bs), bph ^ 1);
+              if (leader) {
                 mbar_expect_tx(b_full(bs), L::B_BYTES);
                 tma_load_2d(sbase + L::B_OFF + bs * L::B_BYTES, &tmB, b_full(bs), (ky * 3 + kx) * ctot + c, n0);
-                if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
               }
+              __syncwarp();
+              if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      uint32_t it = 0;
-      if (RES) {
-        mbar_wait(b_full(0), 0);
-        tc_fence_after();
-      }
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(acc_empty(buf), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t dcol = tmem_base + buf * (MT * BN);
-        for (int ch = 0; ch < chunks; ++ch) {
-          for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(a_full(as), aph);
-            tc_fence_after();
-            const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES;
-            for (int ky = 0; ky < 3; ++ky) {
-              uint32_t sb;
-              if (RES) {
-                sb = sbase + L::B_OFF + (ky * 3 + kx) * L::B_BYTES;
-              } else {
-                mbar_wait(b_full(bs), bph);
-                tc_fence_after();
-                sb = sbase + L::B_OFF + bs * L::B_BYTES;
-              }
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control, elected lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    uint32_t it = 0;
+    if (RES) {
+      mbar_wait(b_full(0), 0);
+      tc_fence_after();
+    }
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(acc_empty(buf), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t dcol = tmem_base + buf * (MT * BN);
+      for (int ch = 0; ch < chunks; ++ch) {
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(a_full(as), aph);
+          tc_fence_after();
+          const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            uint32_t sb;
+            if (RES) {
+              sb = sbase + L::B_OFF + (ky * 3 + kx) * L::B_BYTES;
+            } else {
+              mbar_wait(b_full(bs), bph);
+              tc_fence_after();
+              sb = sbase + L::B_OFF + bs * L::B_BYTES;
+            }
+            if (leader) {
               const uint64_t db = umma_desc_k_sw128(sb);
               const uint32_t acc = (ch | kx | ky) != 0 ? 1u : 0u;
 #pragma unroll
@@ -185,17 +198,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 for (int k = 0; k < 4; ++k)
                   umma_bf16(dcol + mt * BN, da + 2 * k, db + 2 * k, idesc, (acc | k) != 0 ? 1u : 0u);
               }
-              if (!RES) {
-                umma_commit(b_empty(bs));
-                if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
-              }
+              if (!RES) umma_commit(b_empty(bs));
             }
-            umma_commit(a_empty(as));
-            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+            __syncwarp();
+            if (!RES) {
+              if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
+            }
           }
+          if (leader) umma_commit(a_empty(as));
+          __syncwarp();
+          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
         }
-        umma_commit(acc_full(buf));
       }
+      if (leader) umma_commit(acc_full(buf));
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: 4 warps, one output pixel per thread

@@ -282,8 +282,10 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
       }
     }
-  } else if (lane == 0) {
+  } else {
     // ================================================================ control: TMA + every tcgen05.mma
+    // warp-uniform control flow (addresses / descriptors stay in uniform registers); one elected lane issues
+    const bool leader = elect_one();
     constexpr uint32_t idesc1 = umma_idesc_bf16(128, FCT);  // F (bf16) x W1 hi/lo (bf16)
     constexpr uint32_t idesc2 = umma_idesc_f16(128, FCT);   // A1 (fp16) x W2 (fp16)
     const uint64_t dW1 = umma_desc_k_sw128(sbase + M::W1_OFF);
@@ -294,20 +296,26 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     const uint64_t dAX = umma_desc_k_sw128(sbase + M::AX_OFF, /*sbo_bytes=*/0);  // all 8-row groups alias one atom
     auto load_tile = [&](int tile) {
       const int b = tile / tiles_per_img;
-      mbar_expect_tx(f_full, M::A_BYTES);
-      tma_load_3d(sbase + M::F_OFF, &tmF, f_full, 0, (tile - b * tiles_per_img) * FC_TILE, b);
+      if (leader) {
+        mbar_expect_tx(f_full, M::A_BYTES);
+        tma_load_3d(sbase + M::F_OFF, &tmF, f_full, 0, (tile - b * tiles_per_img) * FC_TILE, b);
+      }
+      __syncwarp();
     };
     auto mma1 = [&](uint32_t t_it) {
       // H1 = F . (W1 hi + lo)^T once the tile has landed and the producers have drained the previous H1
       mbar_wait(f_full, t_it & 1);
       mbar_wait(h1_empty, (t_it & 1) ^ 1);
       tc_fence_after();
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1L + 2 * k, idesc1, 1u);
-      umma_commit(h1_full);
-      umma_commit(f_empty);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1L + 2 * k, idesc1, 1u);
+        umma_commit(h1_full);
+        umma_commit(f_empty);
+      }
+      __syncwarp();
     };
     uint32_t a_it = 0, t_it = 0;
     int tile = blockIdx.x;
@@ -326,13 +334,16 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         mbar_wait(a1_full(slot), (a_it / FC_A1_STAGES) & 1);
         mbar_wait(h2_empty(hb), ((a_it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + FCT + hb * FCT;
-        const uint64_t da = umma_desc_k_sw128(sbase + M::A1_OFF + slot * M::A_BYTES);
+        if (leader) {
+          const uint32_t d = tmem + FCT + hb * FCT;
+          const uint64_t da = umma_desc_k_sw128(sbase + M::A1_OFF + slot * M::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
-        umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
-        umma_commit(h2_full(hb));
-        umma_commit(a1_empty(slot));
+          for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
+          umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
+          umma_commit(h2_full(hb));
+          umma_commit(a1_empty(slot));
+        }
+        __syncwarp();
         // next tile's H1 as soon as half of this tile's samples are issued (the producers copied H1 to registers at
         // the start of the tile, so the TMEM columns are free; the feature tile was prefetched above)
         if (s == (S >> 1) && next < num_tiles) mma1(t_it + 1);
@@ -400,11 +411,10 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   const long long num_tiles = (long long)tiles_per_img * B;
   if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
   // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise)
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fcomb_tc_kernel, FC_THREADS, smem) != cudaSuccess ||
-      per_sm < 1)
-    return PDA_ERR_CUDA;
-  if (per_sm > 2) per_sm = 2;  // 2 x 256 TMEM columns
+  // (2 CTAs of 288 threads x 96 registers and 2 x 256 TMEM columns fit; shared memory decides)
+  int per_sm = (227 * 1024) / (smem + 1024);
+  if (per_sm < 1) return PDA_ERR_SHAPE;
+  if (per_sm > 2) per_sm = 2;
   const int grid = (int)(num_tiles < 148 * per_sm ? num_tiles : 148 * per_sm);
   float* bz = nullptr;
   if (cudaMallocAsync(&bz, sizeof(float) * (size_t)S * B * FCT, st) != cudaSuccess) return PDA_ERR_CUDA;

@@ -83,16 +83,18 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const int t = blockIdx.z + it * gridDim.z;
-        const int tx = t % p.tiles_x;
-        const int ty = (t / p.tiles_x) % p.tiles_y;
-        const int img = t / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-        mbar_wait(empty_bar(s), ph ^ 1);
+    // TMA producer: warp-uniform control flow, one elected lane issues
+    const bool leader = elect_one();
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const int t = blockIdx.z + it * gridDim.z;
+      const int tx = t % p.tiles_x;
+      const int ty = (t / p.tiles_x) % p.tiles_y;
+      const int img = t / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      if (leader) {
         mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
 #pragma unroll
@@ -109,15 +111,17 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(sa + L::A_BYTES + j * L::BOX, &tmDZ, full_bar(s), n0 + 64 * j, x0, y0, img);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, /*a_mn_major=*/1, /*b_mn_major=*/1);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, /*a_mn_major=*/1, /*b_mn_major=*/1);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
         // MN-major, 128-byte swizzle: 64-channel blocks L::BOX apart (LBO), 8-pixel K groups 1024 B apart (SBO)
         const uint64_t da = umma_desc_mn_sw128(sa, L::BOX, 1024);
@@ -129,8 +133,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         }
         umma_commit(empty_bar(s));
       }
-      umma_commit(done_bar);
+      __syncwarp();
     }
+    if (leader) umma_commit(done_bar);
+    __syncwarp();
   } else {
     // epilogue: thread = accumulator row = (row pair, input channel); columns = output channels
     const int q = warp & 3;
