@@ -111,7 +111,8 @@ int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, vo
  * --------------------------------------------------------------------------------------------------------- */
 
 /* Weight (+bias) gradient of conv3x3: dW[co][ci][ky][kx] = sum_p dZ[p][co] * X[p + tap][ci] on tcgen05 tensor cores
- * (K = pixels; both operands read as MN-major straight from NHWC).  X = concat(src0, src1) as in the forward.
+ * (K = pixels; both operands read as MN-major straight from NHWC; persistent stream-K schedule).
+ * X = concat(src0, src1) as in the forward.
  * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  scratch: fp32 [cout*9*(c0+c1)].  dw_oihw fp32 OIHW,
  * dbias fp32 [cout] (may be NULL).  accumulate != 0 adds to dw/dbias instead of overwriting. */
 int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
@@ -119,9 +120,9 @@ int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, c
 
 /* dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): ReLU backward fused with the backward of the 2x2 average pool that
  * consumes Y (unet_blocks.py:17,20).  NHWC bf16; dfull or dpool may be NULL; y == NULL skips the ReLU mask
- * (plain AvgPool2d backward). */
-int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, int B, int H, int W, int C,
-                           void* stream);
+ * (plain AvgPool2d backward).  dbias (fp32 [C], may be NULL) receives the conv bias gradient sum_pixels dZ. */
+int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, float* dbias, int B, int H,
+                           int W, int C, void* stream);
 
 /* Backward of the bilinear x2 upsample (unet_blocks.py:51): dout (2h,2w) -> din (h,w), NHWC bf16. */
 int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream);

@@ -33,7 +33,7 @@ SIGNATURES = {
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear_bwd_bf16": [_P, _P, _I, _I, _I, _I, _P],
     "pda_conv3x3_first_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_gauss_head_mean": [_P, _P, _I, _I, _I, _P],

@@ -35,11 +35,16 @@ static inline int grid_cap(long long total, int block, int cap = 148 * 16) {
 // dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): backward of ReLU (unet_blocks.py:20) and of the
 // AvgPool2d that consumes the block output (unet_blocks.py:17).  NHWC bf16; dFull / dPool may be NULL.
 // ------------------------------------------------------------------------------------------------
-__global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ dpool,
-                                     const uint4* __restrict__ y, uint4* __restrict__ dz, int B, int H, int W,
-                                     int c_shift) {
+__global__ void __launch_bounds__(256)
+relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ dpool, const uint4* __restrict__ y,
+                     uint4* __restrict__ dz, float* __restrict__ dbias, int B, int H, int W, int c_shift) {
+  __shared__ float red[256 * 8];
   const unsigned total = ((unsigned)B * H * W) << c_shift;
   const unsigned Hp = H >> 1, Wp = W >> 1;
+  // the grid stride is a multiple of C8, so a thread always sees the same 8 channels: bias-gradient partial sums
+  float bsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     float g[8], a[8], yv[8];
     if (dfull) {
@@ -59,7 +64,28 @@ __global__ void relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
     }
-    dz[t] = pack8f(g);
+    const uint4 packed = pack8f(g);
+    dz[t] = packed;
+    if (dbias) {  // sum the ROUNDED values: exactly what the weight-gradient GEMM sees
+      float r[8];
+      unpack8f(packed, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bsum[i] += r[i];
+    }
+  }
+  if (dbias) {
+    const unsigned C8 = 1u << c_shift;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = bsum[i];
+    __syncthreads();
+    if (threadIdx.x < C8) {
+      for (unsigned r = threadIdx.x + C8; r < blockDim.x; r += C8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bsum[i] += red[r * 8 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(dbias + threadIdx.x * 8 + i, bsum[i]);
+    }
   }
 }
 
@@ -700,16 +726,17 @@ using namespace pda;
 
 extern "C" {
 
-int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, int B, int H, int W, int C,
-                           void* stream) {
+int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, void* dz, float* dbias, int B, int H,
+                           int W, int C, void* stream) {
   if (!dz || (!dfull && !dpool)) return PDA_ERR_ARG;
   if (c8_shift(C) < 0 || B <= 0 || (dpool && ((H & 1) || (W & 1)))) return PDA_ERR_SHAPE;
   const long long total = (long long)B * H * W * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
+  if (dbias && cudaMemsetAsync(dbias, 0, sizeof(float) * C, ST(stream)) != cudaSuccess) return PDA_ERR_CUDA;
   PDA_COUNT(1);
-  relu_pool_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
+  relu_pool_bwd_kernel<<<grid_cap(total, 256, 148 * 8), 256, 0, ST(stream)>>>(
       static_cast<const uint4*>(dfull), static_cast<const uint4*>(dpool), static_cast<const uint4*>(y),
-      static_cast<uint4*>(dz), B, H, W, c8_shift(C));
+      static_cast<uint4*>(dz), dbias, B, H, W, c8_shift(C));
   return LAUNCH_OK();
 }
 

@@ -5,13 +5,19 @@
 //
 //   dW[co][tap][ci] = sum over pixels p of  dZ[p][co] * X[p + tap][ci]
 //
-// GEMM view with the reduction over PIXELS as K: both operands are read straight from their NHWC tensors with the
-// same TMA boxes the forward conv uses ([128 pixels][64 channels], SWIZZLE_128B) and fed to the MMA as MN-major
-// operands (the channel dimension is contiguous), so no transpose is ever materialised:
-//   A (M x K) = X^T shifted by the tap:  M = 128 = two (tap, 64-channel chunk) "row pairs", 64 rows each
-//   B (N x K) = dZ^T:                    N = BN output channels (64 or 128)
-//   D (M x N) fp32 in TMEM, accumulated over this CTA's slice of pixel tiles (split-K across blockIdx.z), then
-//   reduced into a zero-initialised fp32 scratch [cout][9][ctot] with red.global.add (coalesced along ci).
+// GEMM view with the reduction over PIXELS as K.  Both operands are read straight from their NHWC tensors by TMA
+// (SWIZZLE_128B) and fed to the MMA as MN-major operands (the channel dimension is contiguous): no transpose is
+// ever materialised.
+//   work item  = (64 output channels, 64 input channels): all nine taps
+//   pixel tile = 16 rows x 8 px of one image = K 128, as 8 MMAs of K = 16
+//   A (M x K)  = X^T: three column-shifted SLABS [18 rows][8 px][64 ci] (as in the forward conv) hold all nine taps.
+//                M = 128 = a PAIR of taps: the second 64-row block is the first advanced by LBO bytes, which is one
+//                8-px row (next ky) inside a slab or a jump to the next slab.  5 pairs = 9 taps + 1 discarded.
+//   B (N x K)  = dZ^T [64 co]
+//   D          = 5 x (128 x 64) fp32 = 320 TMEM columns, accumulated over the item's pixel tiles.
+// Persistent stream-K schedule: the (item, pixel tile) steps are split into 148 equal contiguous ranges; a CTA flushes
+// its accumulators with coalesced fp32 atomics into a zero-initialised scratch [cout][9][ctot] whenever its range
+// crosses an item boundary.
 #include "conv.cuh"
 #include "ptx.cuh"
 
@@ -20,61 +26,58 @@ namespace pda {
 struct WgradArgs {
   int B, H, W;
   int c0, c1, cout;
-  int tile_w, tile_h, tiles_x, tiles_y;
+  int tiles_x, tiles_y;
   int num_tiles;   // pixel tiles = B * tiles_x * tiles_y
-  int npairs;      // 9 * (c0 + c1) / 64
+  int n64;         // cout / 64
+  int items;       // n64 * (c0 + c1) / 64
   float* scratch;  // [cout][9][ctot] fp32, zero-initialised by the caller
 };
 
-template <int BN, int STAGES>
 struct WgradSmem {
-  static constexpr int BOX = 128 * 128;             // one TMA box: 128 pixels x 64 channels bf16
-  static constexpr int A_BYTES = 2 * BOX;           // two row pairs
-  static constexpr int B_BYTES = (BN / 64) * BOX;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLAB = 18 * 1024;             // [18 rows][8 px][64 ch] bf16
+  static constexpr int DZ_BYTES = 16 * 1024;         // [16 rows][8 px][64 co] bf16
+  static constexpr int STAGE_BYTES = 3 * SLAB + DZ_BYTES;  // slabs first: tap pair 4 over-reads 1 KB into the dZ tile
+  static constexpr int STAGES = 3;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 2) * 8;
   static constexpr int DYN_BYTES = SLOT_OFF + 16 + 1024;
+  static constexpr int TMEM_COLS = 512;              // 5 x 64 used
 };
 
-template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                    const __grid_constant__ CUtensorMap tmDZ, const WgradArgs p) {
-  using L = WgradSmem<BN, STAGES>;
+  using L = WgradSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_base = sbase + L::BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t done_bar = bar_base + 8u * (2 * STAGES);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * L::STAGES);
+  const uint32_t acc_empty = acc_full + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::SLOT_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
   const int ctot = p.c0 + p.c1;
-  const int chunks = ctot >> 6;
-  // the two (tap, channel-chunk) row pairs of this CTA; a dangling second pair repeats the first (discarded)
-  int pair[2] = {2 * (int)blockIdx.x, 2 * (int)blockIdx.x + 1};
-  const bool second_valid = pair[1] < p.npairs;
-  if (!second_valid) pair[1] = pair[0];
-  const int n0 = blockIdx.y * BN;
-  // pixel tiles t = blockIdx.z, blockIdx.z + gridDim.z, ...
-  const int my_tiles = (p.num_tiles - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // this CTA's contiguous range of (item, tile) steps
+  const long long total = (long long)p.items * p.num_tiles;
+  const long long s0 = total * blockIdx.x / gridDim.x, s1 = total * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < L::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(done_bar, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
     fence_mbar_init();
     tma_prefetch_desc(&tmX0);
     tma_prefetch_desc(&tmX1);
     tma_prefetch_desc(&tmDZ);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), BN);
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -83,88 +86,132 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // TMA producer: warp-uniform control flow, one elected lane issues
+    // ------------------------------------------------------------ TMA producer (warp-uniform, elected lane issues)
     const bool leader = elect_one();
-    for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      const int t = blockIdx.z + it * gridDim.z;
-      const int tx = t % p.tiles_x;
-      const int ty = (t / p.tiles_x) % p.tiles_y;
-      const int img = t / (p.tiles_x * p.tiles_y);
-      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-      mbar_wait(empty_bar(s), ph ^ 1);
+    uint32_t it = 0;
+    for (long long st = s0; st < s1; ++st, ++it) {
+      const int item = (int)(st / p.num_tiles);
+      const int t = (int)(st - (long long)item * p.num_tiles);
+      const int nb = item % p.n64, ch = item / p.n64;
+      const int img = t / tiles_per_img;
+      const int tt = t - img * tiles_per_img;
+      const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+      const int x0 = tx * 8, y0 = ty * 16;
+      const int s = it % L::STAGES;
+      mbar_wait(empty_bar(s), ((it / L::STAGES) & 1) ^ 1);
       if (leader) {
         mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
+        const int c = ch << 6;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int tap = pair[h] / chunks;
-          const int c = (pair[h] - tap * chunks) << 6;
-          const int ky = tap / 3, kx = tap - 3 * ky;
+        for (int kx = 0; kx < 3; ++kx) {
           if (c < p.c0)
-            tma_load_4d(sa + h * L::BOX, &tmX0, full_bar(s), c, x0 + kx - 1, y0 + ky - 1, img);
+            tma_load_4d(sa + kx * L::SLAB, &tmX0, full_bar(s), c, x0 + kx - 1, y0 - 1, img);
           else
-            tma_load_4d(sa + h * L::BOX, &tmX1, full_bar(s), c - p.c0, x0 + kx - 1, y0 + ky - 1, img);
+            tma_load_4d(sa + kx * L::SLAB, &tmX1, full_bar(s), c - p.c0, x0 + kx - 1, y0 - 1, img);
         }
-#pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(sa + L::A_BYTES + j * L::BOX, &tmDZ, full_bar(s), n0 + 64 * j, x0, y0, img);
+        tma_load_4d(sa + 3 * L::SLAB, &tmDZ, full_bar(s), nb << 6, x0, y0, img);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, /*a_mn_major=*/1, /*b_mn_major=*/1);
-    for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(full_bar(s), ph);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, /*a_mn_major=*/1, /*b_mn_major=*/1);
+    uint32_t it = 0, flushes = 0;
+    int cur_item = -1;
+    for (long long st = s0; st < s1; ++st, ++it) {
+      const int item = (int)(st / p.num_tiles);
+      const bool first = item != cur_item;
+      if (first) {
+        if (cur_item >= 0) {
+          if (leader) umma_commit(acc_full);  // previous item complete -> epilogue
+          __syncwarp();
+          ++flushes;
+        }
+        mbar_wait(acc_empty, (flushes & 1) ^ 1);  // accumulators drained (passes immediately the first time)
+        tc_fence_after();
+        cur_item = item;
+      }
+      const int s = it % L::STAGES;
+      mbar_wait(full_bar(s), (it / L::STAGES) & 1);
       tc_fence_after();
       if (leader) {
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
-        // MN-major, 128-byte swizzle: 64-channel blocks L::BOX apart (LBO), 8-pixel K groups 1024 B apart (SBO)
-        const uint64_t da = umma_desc_mn_sw128(sa, L::BOX, 1024);
-        const uint64_t db = umma_desc_mn_sw128(sa + L::A_BYTES, L::BOX, 1024);
+        // MN-major SWIZZLE_128B: 64-channel blocks LBO apart, 8-pixel K groups 1024 B apart (SBO)
+        const uint64_t db = umma_desc_mn_sw128(sa + 3 * L::SLAB, 1024, 1024);
+        const uint64_t da0 = umma_desc_mn_sw128(sa, 1024, 1024);                          // (kx0,ky0) (kx0,ky1)
+        const uint64_t da1 = umma_desc_mn_sw128(sa + 2048, L::SLAB - 2048, 1024);         // (kx0,ky2) (kx1,ky0)
+        const uint64_t da2 = umma_desc_mn_sw128(sa + L::SLAB + 1024, 1024, 1024);         // (kx1,ky1) (kx1,ky2)
+        const uint64_t da3 = umma_desc_mn_sw128(sa + 2 * L::SLAB, 1024, 1024);            // (kx2,ky0) (kx2,ky1)
+        const uint64_t da4 = umma_desc_mn_sw128(sa + 2 * L::SLAB + 2048, 1024, 1024);     // (kx2,ky2) (discarded)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          // 16 pixels per MMA = 16 rows of 128 B = 2048 B: +128 in 16-byte units
-          umma_bf16(tmem, da + 128 * k, db + 128 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          // 16 pixels per MMA = 2 rows of 8 px = 2048 B: +128 in 16-byte units
+          const uint32_t acc = (!first || k != 0) ? 1u : 0u;
+          umma_bf16(tmem + 0, da0 + 128 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + 64, da1 + 128 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + 128, da2 + 128 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + 192, da3 + 128 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + 256, da4 + 128 * k, db + 128 * k, idesc, acc);
         }
         umma_commit(empty_bar(s));
       }
       __syncwarp();
     }
-    if (leader) umma_commit(done_bar);
-    __syncwarp();
+    if (cur_item >= 0) {
+      if (leader) umma_commit(acc_full);
+      __syncwarp();
+    }
   } else {
-    // epilogue: thread = accumulator row = (row pair, input channel); columns = output channels
+    // ------------------------------------------------------------ epilogue: accumulator row = (tap of the pair, ci)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int h = row >> 6;
-    const int tap = pair[h] / chunks;
-    const int ci = ((pair[h] - tap * chunks) << 6) + (row & 63);
-    const bool live = (my_tiles > 0) && (h == 0 || second_valid);
-    if (my_tiles > 0) {
-      mbar_wait(done_bar, 0);
+    const int h = row >> 6, ci_l = row & 63;
+    uint32_t flushes = 0;
+    int cur_item = -1;
+    auto flush = [&](int item) {
+      const int nb = item % p.n64, ch = item / p.n64;
+      mbar_wait(acc_full, flushes & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + cb * 32, v);
-        tmem_ld_wait();
-        if (live) {
-          float* dst = p.scratch + (static_cast<size_t>(n0 + cb * 32) * 9 + tap) * ctot + ci;
+      for (int pr = 0; pr < 5; ++pr) {
+        // tap = ky * 3 + kx of this half of pair pr
+        const int lin = 2 * pr + h;             // position in the (kx, ky) slab-major order: lin = kx * 3 + ky
+        const int kx = lin / 3, ky = lin - 3 * kx;
+        const bool live = lin < 9;
+        float* dst = p.scratch + (static_cast<size_t>(nb << 6) * 9 + (ky * 3 + kx)) * ctot + (ch << 6) + ci_l;
+#pragma unroll 1
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + pr * 64 + cb * 32, v);
+          tmem_ld_wait();
+          if (live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + static_cast<size_t>(j) * 9 * ctot, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              atomicAdd(dst + static_cast<size_t>(cb * 32 + j) * 9 * ctot, __uint_as_float(v[j]));
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      ++flushes;
+    };
+    for (long long st = s0; st < s1;) {
+      const int item = (int)(st / p.num_tiles);
+      if (cur_item >= 0 && item != cur_item) flush(cur_item);
+      cur_item = item;
+      // jump to the first step of the next item (or the end of the range)
+      const long long nxt = (long long)(item + 1) * p.num_tiles;
+      st = nxt < s1 ? nxt : s1;
     }
+    if (cur_item >= 0) flush(cur_item);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, BN);
+  if (warp == 1) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
 // scratch [cout][9][ctot] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0)
@@ -180,10 +227,12 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ scratch, float* _
   }
 }
 
-// db[c] = sum over pixels of dZ[p][c]   (dZ: [npix][C] bf16); db must be zero-initialised
-__global__ void __launch_bounds__(256)
+// db[c] = sum over pixels of dZ[p][c]   (dZ: [npix][C] bf16); db must be zero-initialised.
+// Thread t owns channel pair (t % C2) for pixels (t / C2) + k * rows; the rows of a block are reduced through shared
+// memory so that a block issues one atomic per channel.
+__global__ void __launch_bounds__(1024)
 bias_grad_kernel(const __nv_bfloat162* __restrict__ dz, float* __restrict__ db, long long npix, int C2) {
-  // block handles a slab of pixels; thread t handles channel pair (t % C2) for pixels (t / C2) + k * (256 / C2)
+  extern __shared__ float red[];  // [blockDim.x][2]
   const int cpair = threadIdx.x % C2;
   const int prow = threadIdx.x / C2;
   const int rows = blockDim.x / C2;
@@ -193,25 +242,17 @@ bias_grad_kernel(const __nv_bfloat162* __restrict__ dz, float* __restrict__ db, 
     sx += v.x;
     sy += v.y;
   }
-  atomicAdd(db + 2 * cpair, sx);
-  atomicAdd(db + 2 * cpair + 1, sy);
-}
-
-template <int BN, int STAGES>
-static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dz, const WgradArgs& a,
-                        int n_blocks, int ksplit, cudaStream_t stream) {
-  using L = WgradSmem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(wgrad3x3_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             L::DYN_BYTES) != cudaSuccess)
-      return PDA_ERR_CUDA;
-    configured = true;
+  red[2 * threadIdx.x] = sx;
+  red[2 * threadIdx.x + 1] = sy;
+  __syncthreads();
+  if (prow == 0) {
+    for (int r = 1; r < rows; ++r) {
+      sx += red[2 * (r * C2 + cpair)];
+      sy += red[2 * (r * C2 + cpair) + 1];
+    }
+    atomicAdd(db + 2 * cpair, sx);
+    atomicAdd(db + 2 * cpair + 1, sy);
   }
-  dim3 grid((a.npairs + 1) / 2, n_blocks, ksplit);
-  PDA_COUNT(1);
-  wgrad3x3_tc_kernel<BN, STAGES><<<grid, 192, L::DYN_BYTES, stream>>>(x0, x1, dz, a);
-  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
 }  // namespace pda
@@ -227,35 +268,38 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   const int ctot = c0 + c1;
   WgradArgs a;
   a.B = B; a.H = H; a.W = W; a.c0 = c0; a.c1 = c1; a.cout = cout;
-  a.tile_w = (W > 8) ? 16 : 8;
-  a.tile_h = 128 / a.tile_w;
-  a.tiles_x = (W + a.tile_w - 1) / a.tile_w;
-  a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
-  a.num_tiles = a.tiles_x * a.tiles_y * B;
-  a.npairs = 9 * (ctot >> 6);
+  a.tiles_x = (W + 7) / 8;
+  a.tiles_y = (H + 15) / 16;
+  const long long nt = (long long)a.tiles_x * a.tiles_y * B;
+  if (nt > 0x7fffffffLL) return PDA_ERR_SHAPE;
+  a.num_tiles = (int)nt;
+  a.n64 = cout >> 6;
+  a.items = a.n64 * (ctot >> 6);
   a.scratch = scratch;
-  const int bn = (cout % 128 == 0) ? 128 : 64;
-  const int n_blocks = cout / bn;
-  const int m_tiles = (a.npairs + 1) / 2;
-  int ksplit = (148 * 2 + m_tiles * n_blocks - 1) / (m_tiles * n_blocks);
-  if (ksplit > a.num_tiles) ksplit = a.num_tiles;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > 65535) ksplit = 65535;
   CUtensorMap tX0, tX1, tDZ;
-  int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, a.tile_w, a.tile_h, 64);
+  int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, 8, 18, 64);
   if (r) return r;
   if (c1 > 0) {
-    r = make_act_tensor_map(&tX1, src1, B, H, W, c1, a.tile_w, a.tile_h, 64);
+    r = make_act_tensor_map(&tX1, src1, B, H, W, c1, 8, 18, 64);
     if (r) return r;
   } else {
     tX1 = tX0;
   }
-  r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, a.tile_w, a.tile_h, 64);
+  r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 8, 16, 64);
   if (r) return r;
   if (cudaMemsetAsync(scratch, 0, sizeof(float) * 9ull * cout * ctot, stream) != cudaSuccess) return PDA_ERR_CUDA;
-  r = (bn == 128) ? launch_wgrad<128, 3>(tX0, tX1, tDZ, a, n_blocks, ksplit, stream)
-                  : launch_wgrad<64, 4>(tX0, tX1, tDZ, a, n_blocks, ksplit, stream);
-  if (r) return r;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             WgradSmem::DYN_BYTES) != cudaSuccess)
+      return PDA_ERR_CUDA;
+    configured = true;
+  }
+  const long long steps = (long long)a.items * a.num_tiles;
+  const int grid = (int)(steps < 148 ? steps : 148);
+  PDA_COUNT(1);
+  wgrad3x3_tc_kernel<<<grid, 192, WgradSmem::DYN_BYTES, stream>>>(tX0, tX1, tDZ, a);
+  if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
   const long long n = 9LL * cout * ctot;
   PDA_COUNT(1);
   wgrad_scatter_kernel<<<(int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256), 256, 0, stream>>>(
@@ -267,10 +311,11 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
     const int threads = C2 >= 256 ? C2 : 256;
     const long long npix = (long long)B * H * W;
     int blocks = (int)((npix + 63) / 64);
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 2) blocks = 148 * 2;
     if (threads > 1024) return PDA_ERR_SHAPE;
     PDA_COUNT(1);
-    bias_grad_kernel<<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat162*>(dz), dbias, npix, C2);
+    bias_grad_kernel<<<blocks, threads, threads * 2 * sizeof(float), stream>>>(
+        static_cast<const __nv_bfloat162*>(dz), dbias, npix, C2);
   }
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

@@ -221,17 +221,19 @@ def conv3x3_wgrad(src0, src1, dz, want_bias=True):
     return dw, db
 
 
-def relu_pool_bwd(dfull, dpool, y, shape=None):
-    """dZ = (dFull + 0.25 * up2(dPool)) * (y > 0); y None = no ReLU mask.  NHWC bf16."""
+def relu_pool_bwd(dfull, dpool, y, shape=None, want_bias=False):
+    """dZ = (dFull + 0.25 * up2(dPool)) * (y > 0); y None = no ReLU mask.  NHWC bf16.
+    want_bias: also returns db = sum over pixels of dZ (the conv bias gradient) -> (dz, db)."""
     _need_cuda(dfull, dpool, y)
     lib = _lib.load()
     ref = y if y is not None else dfull
     B, H, W, C = ref.shape if ref is not None else shape
     dev = (ref if ref is not None else dpool).device
     dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
-    _lib.check(lib.pda_relu_pool_bwd_bf16(_ptr(dfull), _ptr(dpool), _ptr(y), dz.data_ptr(), B, H, W, C, _stream()),
-               "relu_pool_bwd")
-    return dz
+    db = torch.empty((C,), dtype=torch.float32, device=dev) if want_bias else None
+    _lib.check(lib.pda_relu_pool_bwd_bf16(_ptr(dfull), _ptr(dpool), _ptr(y), dz.data_ptr(), _ptr(db), B, H, W, C,
+                                          _stream()), "relu_pool_bwd")
+    return (dz, db) if want_bias else dz
 
 
 def upsample2x_bwd(dout):

@@ -34,18 +34,21 @@ class Conv3x3Fn(torch.autograd.Function):
             return (None,) * 7
         g_full = None if g_full is None else g_full.contiguous()
         g_pool = None if g_pool is None else g_pool.contiguous()
-        dz = ops.relu_pool_bwd(g_full, g_pool, full if ctx.relu else None, shape=full.shape)
-        c0 = x.shape[3]
-        dx = dsrc1 = dw = db = None
         need_x, need_s1, need_w, need_b = ctx.needs_input_grad[:4]
+        # the bias gradient (sum over pixels of dZ) comes out of the same pass that builds dZ
+        dz, db = ops.relu_pool_bwd(g_full, g_pool, full if ctx.relu else None, shape=full.shape, want_bias=True)
+        if not need_b:
+            db = None
+        c0 = x.shape[3]
+        dx = dsrc1 = dw = None
         if need_x or need_s1:
             wrot = packed_weight(ctx.conv, rot180=True)  # (c0 + c1, 9 * cout)
             if need_x:
                 dx, _ = ops.conv3x3(dz, None, wrot[:c0], None, relu=False)
             if need_s1 and src1 is not None:
                 dsrc1, _ = ops.conv3x3(dz, None, wrot[c0:], None, relu=False)
-        if need_w or need_b:
-            dw, db = ops.conv3x3_wgrad(x, src1, dz)
+        if need_w:
+            dw, _ = ops.conv3x3_wgrad(x, src1, dz, want_bias=False)
         return dx, dsrc1, dw, db, None, None, None
 
 
