@@ -176,7 +176,7 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     opt = FusedAdam(model.parameters(), lr=1e-5)
     reducer = GradAllReducer(model)
     ema = consensus.MomentumUpdater(model, teacher)
-    backprop = steps.default_backprop(opt, reducer)
+    backprop = steps.default_backprop(opt, reducer, model)
     g = torch.Generator().manual_seed(11 + rank)
     x = torch.randn(Bt, 1, HW, HW, generator=g)
     host_x1 = (x + 0.1 * torch.randn(Bt, 1, HW, HW, generator=g)).pin_memory()

@@ -40,6 +40,10 @@ void pda_reset_launch_count(void);
  * With rot180 != 0 the taps are reversed and cin/cout swapped ([cin][8-tap][cout]): the dgrad operand. */
 int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, void* stream);
 
+/* Same for many convs in one launch (after an optimizer or EMA step).  table: device int64 [n_chunks][6] =
+ * (w_oihw ptr, packed ptr, rot180-packed ptr or 0, cout, cin, first output element of the chunk); chunks of 16384. */
+int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* stream);
+
 /* First layer of every net (cin = 1, or 2 for the posterior whose input is cat(patch, segm),
  * probabilistic_unet.py:118): x0/x1 are fp32 [B][H][W] planes (x1 may be NULL), w is OIHW fp32.
  * Replaces unet_blocks.py:19-20 / probabilistic_unet.py:56-57 for block 0.  out: NHWC bf16. */

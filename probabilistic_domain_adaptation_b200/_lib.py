@@ -20,6 +20,7 @@ SIGNATURES = {
     "pda_launch_count": [],
     "pda_reset_launch_count": [],
     "pda_pack_conv3x3_weights": [_P, _P, _I, _I, _I, _P],
+    "pda_pack_conv3x3_weights_multi": [_P, _I, _P],
     "pda_conv3x3_first": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_bf16_simt": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -23,6 +23,44 @@ def packed_weight(conv, rot180=False):
     return packed
 
 
+_PACK_CHUNK = 16384
+
+
+def refresh_packed(module, rot180=True):
+    """Re-packs the bf16 operands of every tensor-core conv of `module` in ONE launch (call after an optimizer or
+    EMA step; `packed_weight` would otherwise repack lazily, one launch per conv and orientation)."""
+    import torch.nn as nn
+    from . import _lib
+    convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3)
+             and m.in_channels % 64 == 0 and m.weight.is_cuda]
+    if not convs:
+        return
+    state = module.__dict__.get("_pda_pack_state")
+    key = tuple((c.weight.data_ptr(), c.weight.device) for c in convs) + (rot180,)
+    if state is None or state["key"] != key:
+        bufs, rows = [], []
+        for c in convs:
+            w = c.weight
+            cout, cin = w.shape[0], w.shape[1]
+            packed = torch.empty((cout, 9 * cin), dtype=torch.bfloat16, device=w.device)
+            rot = torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=w.device) if rot180 else None
+            bufs.append((packed, rot))
+            for start in range(0, 9 * cout * cin, _PACK_CHUNK):
+                rows.append((w.data_ptr(), packed.data_ptr(), 0 if rot is None else rot.data_ptr(), cout, cin, start))
+        table = torch.tensor(rows, dtype=torch.int64).to(convs[0].weight.device)
+        state = {"key": key, "bufs": bufs, "table": table}
+        module.__dict__["_pda_pack_state"] = state
+    lib = _lib.load()
+    _lib.check(lib.pda_pack_conv3x3_weights_multi(state["table"].data_ptr(), state["table"].shape[0],
+                                                  torch.cuda.current_stream().cuda_stream), "pack_weights_multi")
+    for c, (packed, rot) in zip(convs, state["bufs"]):
+        w = c.weight
+        stamp = (w._version, w.data_ptr(), w.device)
+        c.__dict__["_pda_packed"] = (stamp, packed)
+        if rot is not None:
+            c.__dict__["_pda_packed_rot"] = (stamp, rot)
+
+
 def invalidate_packed(module):
     """Call after kernels wrote parameter memory behind autograd's back (the fused EMA update)."""
     for m in module.modules():

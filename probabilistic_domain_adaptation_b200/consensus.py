@@ -73,7 +73,9 @@ class MomentumUpdater:
         ops.multi_tensor_ema(self._table, momentum)
         # parameter memory changed behind autograd's back: advance the version counters (packed-weight cache key)
         from .optim import bump_versions
+        from .autograd_ops import refresh_packed
         bump_versions(self.teacher.parameters())
+        refresh_packed(self.teacher, rot180=False)  # the teacher only runs forward
 
 
 def adamt_momentum(iteration, momentum=0.999):

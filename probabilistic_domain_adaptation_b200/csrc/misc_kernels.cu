@@ -30,6 +30,33 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
+// multi-tensor variant: one launch refreshes the bf16 operands of many convs after an optimizer / EMA step.
+// table rows: (w_ptr, packed_ptr, rot_ptr or 0, cout, cin, first output element of this chunk); chunk = 16384 outputs
+__global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __restrict__ table) {
+  const long long* e = table + 6LL * blockIdx.x;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  __nv_bfloat16* orot = reinterpret_cast<__nv_bfloat16*>(e[2]);
+  const int cout = (int)e[3], cin = (int)e[4];
+  const int start = (int)e[5];
+  const int n = 9 * cout * cin;
+  const int end = min(n, start + 16384);
+  for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
+    {
+      const int ci = i % cin;
+      const int tap = (i / cin) % 9;
+      const int co = i / (9 * cin);
+      o[i] = __float2bfloat16(w[(co * cin + ci) * 9 + tap]);
+    }
+    if (orot) {
+      const int co = i % cout;
+      const int tap = (i / cout) % 9;
+      const int ci = i / (9 * cout);
+      orot[i] = __float2bfloat16(w[(co * cin + ci) * 9 + (8 - tap)]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // first layer: cin in {1,2} fp32 planes -> NHWC bf16, fp32 math (K = 9 / 18 is too thin for the tensor cores; the
 // layer is bound by its 128 B/px output).  A thread owns 8 output channels of 4 consecutive pixels of one row:
@@ -354,6 +381,14 @@ int pda_pack_conv3x3_weights(const float* w, void* o, int cout, int cin, int rot
   PDA_COUNT(1);
   pack_w_kernel<<<grid_for(9LL * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
       w, static_cast<__nv_bfloat16*>(o), cout, cin, rot180);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* stream) {
+  if (!table) return PDA_ERR_ARG;
+  if (n_chunks <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
+  pack_w_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(table));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 

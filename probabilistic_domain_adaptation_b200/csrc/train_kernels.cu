@@ -391,9 +391,17 @@ __global__ void __launch_bounds__(256) l2_partial_kernel(const long long* __rest
   const float* w = reinterpret_cast<const float*>(e[0]);
   const int n = (int)e[1];
   double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = w[i];
-    s += (double)v * (double)v;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldg(w4 + i);
+      // fp32 products are exact in double; four per load keeps the loop short
+      s += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += (double)w[i] * (double)w[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)w[i] * (double)w[i];
   }
   __shared__ double sh[8];
 #pragma unroll
@@ -436,7 +444,17 @@ l2_bwd_kernel(const long long* __restrict__ table, const float* __restrict__ nor
   const int n = (int)e[2];
   const float nrm = norms[(int)e[3]];
   const float k = nrm > 0.f ? gout[0] / nrm : 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = k * w[i];
+  if (((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g)) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+      v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+      reinterpret_cast<float4*>(g)[i] = v;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) g[i] = k * w[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = k * w[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -704,17 +722,33 @@ adam_kernel(const long long* __restrict__ table, float lr, float beta2, float om
   const int n = (int)e[4];
   const float gs = inv_scale ? inv_scale[0] : 1.f;
   const float step_size = lr / bc1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float gi = g[i] * gs;
-    const float pi = p[i];
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gs;
     if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
     // torch: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float mi = m[i] + (gi - m[i]) * omb1;
-    const float vi = fmaf(gi * gi, omb2, v[i] * beta2);
-    m[i] = mi;
-    v[i] = vi;
+    mi = mi + (gi - mi) * omb1;
+    vi = fmaf(gi * gi, omb2, vi * beta2);
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);
+    pi = pi - step_size * (mi / denom);
+  };
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i],
+             v4 = reinterpret_cast<float4*>(v)[i];
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+      update(p4.x, g4.x, m4.x, v4.x);
+      update(p4.y, g4.y, m4.y, v4.y);
+      update(p4.z, g4.z, m4.z, v4.z);
+      update(p4.w, g4.w, m4.w, v4.w);
+      reinterpret_cast<float4*>(p)[i] = p4;
+      reinterpret_cast<float4*>(m)[i] = m4;
+      reinterpret_cast<float4*>(v)[i] = v4;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) update(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) update(p[i], g[i], m[i], v[i]);
   }
 }
 
@@ -734,7 +768,9 @@ int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, 
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   if (dbias && cudaMemsetAsync(dbias, 0, sizeof(float) * C, ST(stream)) != cudaSuccess) return PDA_ERR_CUDA;
   PDA_COUNT(1);
-  relu_pool_bwd_kernel<<<grid_cap(total, 256, 148 * 8), 256, 0, ST(stream)>>>(
+  // with the fused bias reduction every block ends with C atomics on the same C addresses: keep the grid at two
+  // blocks per SM (each thread then strides over more pixels, which is what feeds its register partial sums)
+  relu_pool_bwd_kernel<<<grid_cap(total, 256, dbias ? 148 * 2 : 148 * 8), 256, 0, ST(stream)>>>(
       static_cast<const uint4*>(dfull), static_cast<const uint4*>(dpool), static_cast<const uint4*>(y),
       static_cast<uint4*>(dz), dbias, B, H, W, c8_shift(C));
   return LAUNCH_OK();

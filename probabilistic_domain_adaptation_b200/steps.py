@@ -15,15 +15,19 @@ loss.backward(); [grad all-reduce]; optimizer.step().
 import torch
 
 from . import consensus
+from .autograd_ops import refresh_packed
 from .my_models.utils import l2_regularisation
 
 
-def default_backprop(optimizer, reducer=None):
+def default_backprop(optimizer, reducer=None, model=None):
+    """backward + [gradient all-reduce] + optimizer step (+ one-launch refresh of the packed bf16 conv operands)."""
     def backprop(loss):
         loss.backward()
         if reducer is not None:
             reducer.finish()
         optimizer.step()
+        if model is not None:
+            refresh_packed(model, rot180=True)
     return backprop
 
 
