@@ -44,6 +44,17 @@ static inline int c8_shift(int C) {
 }
 
 
+// Launch shape of the row-decomposed NHWC elementwise kernels: x = 256-thread blocks across one row's (x, chunk)
+// elements, y = blocks striding over the rows, sized to ~`target` blocks in total.
+static inline dim3 row_grid(long long row_elems, long long rows, int target = 148 * 8) {
+  const long long gx = (row_elems + 255) / 256;
+  long long gy = (target + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy > 65535) gy = 65535;
+  if (gy < 1) gy = 1;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
 // Element index -> (channel chunk, x, y, image) with 32-bit arithmetic (C8 is a power of two: C in {64..512}).
 struct Px {
   unsigned c, x, y, b;

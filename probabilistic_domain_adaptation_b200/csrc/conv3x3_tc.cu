@@ -25,18 +25,21 @@ namespace pda {
 // same shared-memory bytes feed three taps and both M-tiles, i.e. 3.2-3.4 pixel-loads per output pixel instead of 9.
 // Weights: one [BN][64] tile per (tap, chunk) through a second ring, or fully resident for a 64->64 layer.
 // Accumulators: MT x BN fp32 columns, double buffered in TMEM, so the epilogue of unit i overlaps the MMAs of
-// unit i+1.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (one TMEM lane = one pixel each).
+// unit i+1.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue: two warpgroups share the unit's
+// [128 px x 64 ch] sub-tiles; a warp turns its 32 TMEM lanes (= 4 rows x 8 px) into bias + ReLU + bf16, stages them in
+// a swizzled 4 KB shared-memory box and writes it with ONE TMA store (full 128-byte lines, clipped at the image edge).
 // ---------------------------------------------------------------------------------------------
 template <int BN, int MT, bool RES>
 struct ConvCfg {
   static constexpr int SLAB_ROWS = 16 * MT + 2;
   static constexpr int A_BYTES = SLAB_ROWS * 1024;     // one slab: SLAB_ROWS x (8 px x 128 B)
   static constexpr int B_BYTES = BN * 128;             // one (tap, chunk) weight tile
-  static constexpr int A_STAGES = 4;
+  static constexpr int A_STAGES = 3;
   static constexpr int B_STAGES = RES ? 9 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6);
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
-  static constexpr int BAR_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int STG_OFF = B_OFF + B_STAGES * B_BYTES;   // 8 epilogue warps x 4 KB output staging
+  static constexpr int BAR_OFF = STG_OFF + 8 * 4096;
   static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BIAS_OFF = SLOT_OFF + 16;
@@ -48,10 +51,13 @@ struct ConvCfg {
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
 };
 
+constexpr int CONV_THREADS = 320;
+
 template <int BN, int MT, bool RES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const ConvArgs p) {
   using L = ConvCfg<BN, MT, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,19 +91,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), 4);  // one arrive per epilogue warp
+      mbar_init(acc_empty(s), 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
     tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.cout; i += 128) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x - 64; i < p.cout; i += CONV_THREADS - 64) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -214,11 +221,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ epilogue: 4 warps, one output pixel per thread
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ------------------------------------------------------------ epilogue: 8 warps, one output pixel per thread
+    constexpr int NG = BN / 64;            // 64-channel groups per accumulator
+    constexpr int NSUB = MT * NG;          // [128 px x 64 ch] sub-tiles per unit
+    const int ew = warp - 2;               // 0..7
+    const int wg = ew >> 2;                // warpgroup: takes the sub-tiles with index % 2 == wg
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int lty = row >> 3, ltx = row & 7;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
+    uint8_t* stage = smem + L::STG_OFF + ew * 4096;
+    const uint32_t stage_u32 = sbase + L::STG_OFF + ew * 4096;
+    const int sw = lane & 7;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int nb = u % n_blocks;
@@ -231,23 +245,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t buf = it & 1;
       mbar_wait(acc_full(buf), (it >> 1) & 1);
       tc_fence_after();
+      if (wg >= NSUB) {  // nothing to read for this warpgroup (MT = 1, BN = 64)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
+      }
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int sub = wg; sub < NSUB; sub += 2) {
+        const int mt = sub / NG, g = sub - mt * NG;
         const int y = ty * (16 * MT) + mt * 16 + lty;
         const bool valid = (y < p.H) && (x < p.W);
-        __nv_bfloat16* out_px =
-            p.out ? p.out + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0 : nullptr;
         const bool pool_owner = valid && !(lty & 1) && !(ltx & 1);
         __nv_bfloat16* pool_px =
-            p.out_pool ? p.out_pool + ((static_cast<size_t>(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout + n0
-                       : nullptr;
-#pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
+            p.out_pool
+                ? p.out_pool + ((static_cast<size_t>(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout + n0 + g * 64
+                : nullptr;
+        if (p.out) {
+          // the previous TMA store of this warp has finished reading the staging box
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + cb * 32, v);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + g * 64 + cb * 32,
+                    v);
           tmem_ld_wait();
-          if (mt == MT - 1 && cb == BN / 32 - 1) {
-            // all TMEM reads of this accumulator buffer are done: hand it back to the MMA warp
+          if (cb == 1 && sub + 2 >= NSUB) {
+            // last TMEM read of this warp for this unit: hand the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(buf));
@@ -255,11 +279,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float tv = __uint_as_float(v[j]) + bias_s[n0 + cb * 32 + j];
+            float tv = __uint_as_float(v[j]) + bias_s[n0 + g * 64 + cb * 32 + j];
             f[j] = p.relu ? fmaxf(tv, 0.f) : tv;
           }
-          if (out_px && valid) {
-            uint4* dst = reinterpret_cast<uint4*>(out_px + cb * 32);
+          if (p.out) {
+            // this pixel's 64 bytes of the 128-byte row, 16-byte chunks XOR-swizzled by (row & 7) as TMA expects
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -267,7 +291,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              dst[j] = o;
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((cb * 4 + j) ^ sw) << 4)) = o;
             }
           }
           if (pool_px) {
@@ -294,8 +318,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
           }
         }
+        if (p.out) {
+          fence_proxy_async_smem();  // staging written by the generic proxy, read by the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            // this warp's 32 pixels = 4 rows x 8 px of the tile
+            tma_store_4d(&tmOut, stage_u32, n0 + g * 64, tx * 8, ty * (16 * MT) + mt * 16 + q * 4, img);
+            tma_store_commit();
+          }
+        }
       }
     }
+    if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
   }
 
   tc_fence_before();
@@ -354,8 +388,8 @@ int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long 
 }
 
 template <int BN, int MT, bool RES>
-static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvArgs& args,
-                       cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                       const ConvArgs& args, cudaStream_t stream) {
   using L = ConvCfg<BN, MT, RES>;
   static bool configured = false;
   if (!configured) {
@@ -368,7 +402,7 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   if (units > 0x7fffffffLL) return PDA_ERR_SHAPE;
   const int grid = (int)(units < 148 ? units : 148);
   PDA_COUNT(1);
-  conv3x3_tc_kernel<BN, MT, RES><<<grid, 192, L::DYN_BYTES, stream>>>(a0, a1, b, args);
+  conv3x3_tc_kernel<BN, MT, RES><<<grid, CONV_THREADS, L::DYN_BYTES, stream>>>(a0, a1, b, o, args);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
@@ -400,14 +434,19 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   }
   r = make_mat_tensor_map(&tB, wpacked, 9LL * (c0 + c1), cout, 64, bn);
   if (r) return r;
+  CUtensorMap tO = tA0;  // unused when out == nullptr
+  if (out) {
+    r = make_act_tensor_map(&tO, out, B, H, W, cout, 8, 4, 64);  // one epilogue warp = 4 rows x 8 px x 64 ch
+    if (r) return r;
+  }
   const bool resident = (bn == 64 && cout == 64 && c0 + c1 == 64 && mt == 2);
   if (mt == 2) {
-    if (bn == 128) return launch_conv<128, 2, false>(tA0, tA1, tB, a, stream);
-    return resident ? launch_conv<64, 2, true>(tA0, tA1, tB, a, stream)
-                    : launch_conv<64, 2, false>(tA0, tA1, tB, a, stream);
+    if (bn == 128) return launch_conv<128, 2, false>(tA0, tA1, tB, tO, a, stream);
+    return resident ? launch_conv<64, 2, true>(tA0, tA1, tB, tO, a, stream)
+                    : launch_conv<64, 2, false>(tA0, tA1, tB, tO, a, stream);
   }
-  if (bn == 128) return launch_conv<128, 1, false>(tA0, tA1, tB, a, stream);
-  return launch_conv<64, 1, false>(tA0, tA1, tB, a, stream);
+  if (bn == 128) return launch_conv<128, 1, false>(tA0, tA1, tB, tO, a, stream);
+  return launch_conv<64, 1, false>(tA0, tA1, tB, tO, a, stream);
 }
 
 }  // namespace pda

@@ -158,14 +158,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
-__global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
-                                int c_shift) {
+// The NHWC elementwise kernels use a 2-D decomposition: blockIdx.x / threadIdx.x cover (x, 16-byte channel chunk) of
+// one output row, blockIdx.y strides over the B * H output rows: one 32-bit division per row instead of three 64-bit
+// ones per element.
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int c_shift) {
   const unsigned Ho = H >> 1, Wo = W >> 1;
   const unsigned C8 = 1u << c_shift;
-  const unsigned total = (unsigned)B * Ho * Wo * C8;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const Px q = split_index(t, c_shift, Wo, Ho);
-    const size_t base = ((((size_t)q.b * H + 2 * q.y) * W + 2 * q.x) << c_shift) + q.c;
+  const unsigned xc = blockIdx.x * blockDim.x + threadIdx.x;  // x * C8 + c
+  if (xc >= Wo * C8) return;
+  const unsigned x = xc >> c_shift, c = xc & (C8 - 1);
+  for (unsigned r = blockIdx.y; r < (unsigned)B * Ho; r += gridDim.y) {
+    const unsigned b = r / Ho, y = r - b * Ho;
+    const size_t base = ((((size_t)b * H + 2 * y) * W + 2 * x) << c_shift) + c;
     float a[8], s[8];
     unpack8(__ldg(in + base), s);
     unpack8(__ldg(in + base + C8), a);
@@ -177,7 +182,7 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict_
     unpack8(__ldg(in + base + (size_t)W * C8 + C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = (s[i] + a[i]) * 0.25f;
-    out[t] = pack8(s);
+    out[((size_t)r * Wo << c_shift) + xc] = pack8(s);
   }
 }
 
@@ -190,15 +195,20 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
   const unsigned C8 = 1u << c_shift;
   const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const unsigned total = (unsigned)B * Ho * Wo * C8;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const Px q = split_index(t, c_shift, Wo, Ho);
-    const float sy = rh * q.y, sx = rw * q.x;
-    const int y1 = (int)sy, x1 = (int)sx;
-    const int yp = (y1 < h - 1) ? 1 : 0, xp = (x1 < w - 1) ? 1 : 0;
-    const float ly1 = sy - y1, lx1 = sx - x1;
-    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const uint4* p = in + ((((size_t)q.b * h + y1) * w + x1) << c_shift) + q.c;
+  const unsigned xc = blockIdx.x * blockDim.x + threadIdx.x;  // X * C8 + c
+  if (xc >= Wo * C8) return;
+  const unsigned X = xc >> c_shift, c = xc & (C8 - 1);
+  const float sx = rw * X;
+  const int x1 = (int)sx;
+  const int xp = (x1 < w - 1) ? 1 : 0;
+  const float lx1 = sx - x1, lx0 = 1.f - lx1;
+  for (unsigned r = blockIdx.y; r < (unsigned)B * Ho; r += gridDim.y) {
+    const unsigned b = r / Ho, Y = r - b * Ho;
+    const float sy = rh * Y;
+    const int y1 = (int)sy;
+    const int yp = (y1 < h - 1) ? 1 : 0;
+    const float ly1 = sy - y1, ly0 = 1.f - ly1;
+    const uint4* p = in + ((((size_t)b * h + y1) * w + x1) << c_shift) + c;
     const uint4 r00 = __ldg(p), r01 = __ldg(p + ((size_t)xp << c_shift));
     const uint4 r10 = __ldg(p + (((size_t)yp * w) << c_shift)), r11 = __ldg(p + (((size_t)yp * w + xp) << c_shift));
     float v00[8], v01[8], v10[8], v11[8], o[8];
@@ -209,7 +219,7 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       o[i] = ly0 * (lx0 * v00[i] + lx1 * v01[i]) + ly1 * (lx0 * v10[i] + lx1 * v11[i]);
-    out[t] = pack8(o);
+    out[((size_t)r * Wo << c_shift) + xc] = pack8(o);
   }
 }
 
@@ -450,7 +460,7 @@ int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, voi
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  avgpool2_kernel<<<row_grid((W / 2) * (C / 8), B * (H / 2)), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
@@ -461,7 +471,7 @@ int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w,
   const long long total = (long long)B * (2 * h) * (2 * w) * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  upsample2x_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+  upsample2x_kernel<<<row_grid(2 * w * (C / 8), B * 2 * h), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

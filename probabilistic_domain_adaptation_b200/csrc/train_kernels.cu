@@ -39,52 +39,58 @@ __global__ void __launch_bounds__(256)
 relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ dpool, const uint4* __restrict__ y,
                      uint4* __restrict__ dz, float* __restrict__ dbias, int B, int H, int W, int c_shift) {
   __shared__ float red[256 * 8];
-  const unsigned total = ((unsigned)B * H * W) << c_shift;
+  const unsigned C8 = 1u << c_shift;
   const unsigned Hp = H >> 1, Wp = W >> 1;
-  // the grid stride is a multiple of C8, so a thread always sees the same 8 channels: bias-gradient partial sums
+  const unsigned xc = blockIdx.x * blockDim.x + threadIdx.x;  // x * C8 + c: a thread keeps its 8 channels
+  const bool active = xc < (unsigned)W * C8;
+  const unsigned x = xc >> c_shift, c = xc & (C8 - 1);
   float bsum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    float g[8], a[8], yv[8];
-    if (dfull) {
-      unpack8f(__ldg(dfull + t), g);
-    } else {
+  if (active) {
+    for (unsigned r = blockIdx.y; r < (unsigned)B * H; r += gridDim.y) {
+      const size_t t = ((size_t)r * W << c_shift) + xc;
+      float g[8], a[8], yv[8];
+      if (dfull) {
+        unpack8f(__ldg(dfull + t), g);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = 0.f;
-    }
-    if (dpool) {
-      const Px q = split_index(t, c_shift, W, H);
-      unpack8f(__ldg(dpool + ((((size_t)q.b * Hp + (q.y >> 1)) * Wp + (q.x >> 1)) << c_shift) + q.c), a);
+        for (int i = 0; i < 8; ++i) g[i] = 0.f;
+      }
+      if (dpool) {
+        const unsigned b = r / (unsigned)H, yy = r - b * H;
+        unpack8f(__ldg(dpool + ((((size_t)b * Hp + (yy >> 1)) * Wp + (x >> 1)) << c_shift) + c), a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = fmaf(0.25f, a[i], g[i]);
-    }
-    if (y) {  // y == nullptr: plain average-pool backward, no ReLU mask
-      unpack8f(__ldg(y + t), yv);
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(0.25f, a[i], g[i]);
+      }
+      if (y) {  // y == nullptr: plain average-pool backward, no ReLU mask
+        unpack8f(__ldg(y + t), yv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
-    }
-    const uint4 packed = pack8f(g);
-    dz[t] = packed;
-    if (dbias) {  // sum the ROUNDED values: exactly what the weight-gradient GEMM sees
-      float r[8];
-      unpack8f(packed, r);
+        for (int i = 0; i < 8; ++i) g[i] = yv[i] > 0.f ? g[i] : 0.f;
+      }
+      const uint4 packed = pack8f(g);
+      dz[t] = packed;
+      if (dbias) {  // sum the ROUNDED values: exactly what the weight-gradient GEMM sees
+        float rr[8];
+        unpack8f(packed, rr);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) bsum[i] += r[i];
+        for (int i = 0; i < 8; ++i) bsum[i] += rr[i];
+      }
     }
   }
   if (dbias) {
-    const unsigned C8 = 1u << c_shift;
+    // threads of a block with the same channel chunk: tid, tid + C8, ... (256 % C8 == 0)
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = bsum[i];
     __syncthreads();
     if (threadIdx.x < C8) {
-      for (unsigned r = threadIdx.x + C8; r < blockDim.x; r += C8) {
+      for (unsigned rr = threadIdx.x + C8; rr < blockDim.x; rr += C8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bsum[i] += red[r * 8 + i];
+        for (int i = 0; i < 8; ++i) bsum[i] += red[rr * 8 + i];
       }
+      const unsigned cc = (blockIdx.x * blockDim.x + threadIdx.x) & (C8 - 1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(dbias + threadIdx.x * 8 + i, bsum[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(dbias + cc * 8 + i, bsum[i]);
     }
   }
 }
@@ -93,21 +99,25 @@ relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ 
 // backward of F.interpolate(bilinear, x2, align_corners=True) (unet_blocks.py:51), gather form:
 // every input pixel sums the output-gradient pixels whose footprint contains it (deterministic).
 // ------------------------------------------------------------------------------------------------
-__global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int B, int h, int w,
-                                      int c_shift) {
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int B, int h, int w, int c_shift) {
   const int Ho = 2 * h, Wo = 2 * w;
+  const unsigned C8 = 1u << c_shift;
   const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float rw = (Wo > 1) ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const unsigned total = ((unsigned)B * h * w) << c_shift;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const Px q = split_index(t, c_shift, w, h);
-    const int x = q.x, y = q.y;
+  const unsigned xc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xc >= (unsigned)w * C8) return;
+  const int x = xc >> c_shift;
+  const unsigned c = xc & (C8 - 1);
+  const int X0 = max(0, 2 * x - 2), X1 = min(Wo - 1, 2 * x + 3);
+  for (unsigned r = blockIdx.y; r < (unsigned)B * h; r += gridDim.y) {
+    const unsigned b = r / (unsigned)h;
+    const int y = r - b * h;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     // candidate output rows / columns: source coordinate rh*Y lies in (y-1, y+1)
     const int Y0 = max(0, 2 * y - 2), Y1 = min(Ho - 1, 2 * y + 3);
-    const int X0 = max(0, 2 * x - 2), X1 = min(Wo - 1, 2 * x + 3);
     for (int Y = Y0; Y <= Y1; ++Y) {
       const float sy = rh * Y;
       const int y1 = (int)sy;
@@ -127,13 +137,13 @@ __global__ void upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __r
         if (x1 + xp == x) wx += lx1;
         if (wx == 0.f) continue;
         float g[8];
-        unpack8f(__ldg(dout + ((((size_t)q.b * Ho + Y) * Wo + X) << c_shift) + q.c), g);
+        unpack8f(__ldg(dout + ((((size_t)b * Ho + Y) * Wo + X) << c_shift) + c), g);
         const float wgt = wy * wx;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, g[i], acc[i]);
       }
     }
-    din[t] = pack8f(acc);
+    din[((size_t)r * w << c_shift) + xc] = pack8f(acc);
   }
 }
 
@@ -770,7 +780,8 @@ int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, 
   PDA_COUNT(1);
   // with the fused bias reduction every block ends with C atomics on the same C addresses: keep the grid at two
   // blocks per SM (each thread then strides over more pixels, which is what feeds its register partial sums)
-  relu_pool_bwd_kernel<<<grid_cap(total, 256, dbias ? 148 * 2 : 148 * 8), 256, 0, ST(stream)>>>(
+  relu_pool_bwd_kernel<<<row_grid((long long)W * (C / 8), (long long)B * H, dbias ? 148 * 2 : 148 * 8), 256, 0,
+                         ST(stream)>>>(
       static_cast<const uint4*>(dfull), static_cast<const uint4*>(dpool), static_cast<const uint4*>(y),
       static_cast<uint4*>(dz), dbias, B, H, W, c8_shift(C));
   return LAUNCH_OK();
@@ -782,7 +793,7 @@ int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, 
   const long long total = (long long)B * h * w * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  upsample2x_bwd_kernel<<<grid_cap(total, 256), 256, 0, ST(stream)>>>(
+  upsample2x_bwd_kernel<<<row_grid((long long)w * (C / 8), (long long)B * h), 256, 0, ST(stream)>>>(
       static_cast<const uint4*>(dout), static_cast<uint4*>(din), B, h, w, c8_shift(C));
   return LAUNCH_OK();
 }
