@@ -34,6 +34,13 @@ CONV_CASES = [
     (1, 16, 16, 512, 256, 256, False, 256),
     (1, 32, 16, 256, 0, 256, True, 64),
     (1, 64, 64, 64, 0, 128, False, 128),
+    # persistent kernel paths: two M-tiles per unit with ragged edges, concat with streamed weights, many units per CTA
+    (1, 40, 24, 64, 64, 64, False, 0),
+    (2, 34, 18, 128, 0, 128, True, 0),
+    (1, 18, 10, 64, 0, 64, True, 0),
+    (3, 48, 72, 64, 0, 64, False, 0),
+    (1, 96, 160, 64, 0, 64, True, 0),
+    (1, 17, 9, 128, 64, 256, False, 0),
 ]
 
 

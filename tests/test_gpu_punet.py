@@ -60,6 +60,26 @@ def test_fcomb_kernel_parity_and_bit_exact_consensus(precision, shape):
             assert 0.0 < frac < 1.0, frac
 
 
+def test_fcomb_many_tiles_and_images():
+    """Enough tiles that every persistent CTA processes several (image changes inside a CTA's tile sequence)."""
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    sd = po.make_state_dict(0, last_layer_gain=8.0)
+    g = torch.Generator().manual_seed(77)
+    b, h, w_ = 5, 136, 200  # 5 x 213 tiles (ragged last tile)
+    feat = torch.relu(torch.randn(b, 64, h, w_, generator=g)).to(torch.bfloat16)
+    z = torch.randn(7, b, 6, generator=g)
+    ref = torch.stack([po.fcomb_logits(sd, feat.float(), z[s]) for s in range(7)], 0)
+    k = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
+    w = [sd[f"{n}.{p}"].to(dev).contiguous() for n in k for p in ("weight", "bias")]
+    out = ops.fcomb_mc_consensus(feat.permute(0, 2, 3, 1).contiguous().to(dev), z.to(dev), *w, want_mask=True,
+                                 want_logits=True, want_probs=True)
+    assert (out["logits"].cpu() - ref).abs().max().item() < 1e-2 * 8.0
+    y, c = po.consensus_from_probs(out["probs"].cpu(), do_consensus_masking=True)
+    assert torch.equal(out["mask"].cpu(), c) and torch.allclose(out["mean"].cpu(), y, atol=1e-6)
+    assert 0.0 < out["mask"].float().mean().item() < 1.0
+
+
 @pytest.mark.parametrize("S", [1, 3, 8, 64])
 def test_fcomb_sample_counts(S):
     from probabilistic_domain_adaptation_b200 import ops

@@ -35,6 +35,10 @@ CONV_BWD_CASES = [
     (1, 5, 9, 128, 0, 256, False),
     (1, 32, 32, 128, 64, 64, True),
     (3, 16, 8, 512, 0, 512, False),
+    # stream-K ranges that cross item boundaries, ragged tiles
+    (2, 34, 18, 64, 0, 64, True),
+    (1, 48, 40, 64, 64, 128, False),
+    (1, 17, 9, 128, 0, 64, False),
 ]
 
 
