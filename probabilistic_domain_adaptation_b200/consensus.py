@@ -83,6 +83,50 @@ def adamt_momentum(iteration, momentum=0.999):
     return min(1 - 1 / (iteration + 1), momentum)
 
 
+class HostPredictor:
+    """End-to-end Monte-Carlo prediction with HOST buffers, pipelined: the host->device copy of step i+1 and the
+    device->host copy of step i run on their own streams while step i / i+1 computes (the prediction driver of
+    punet_predictions.py:35-63 feeds one tile batch after the other).  `submit` enqueues one batch; `flush` makes the
+    current stream wait for every outstanding copy."""
+
+    def __init__(self, model, n_samples, do_consensus_masking, depth=2):
+        self.model, self.n_samples, self.masking, self.depth = model, n_samples, do_consensus_masking, depth
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.xbuf = [None] * depth
+        self.in_done = [torch.cuda.Event() for _ in range(depth)]
+        self.compute_done = [torch.cuda.Event() for _ in range(depth)]
+        self.i = 0
+
+    @torch.no_grad()
+    def submit(self, host_images, out_mean, out_cons, eps=None):
+        slot = self.i % self.depth
+        self.i += 1
+        cur = torch.cuda.current_stream(self.dev)
+        if self.xbuf[slot] is None or self.xbuf[slot].shape != host_images.shape:
+            self.xbuf[slot] = torch.empty(host_images.shape, dtype=torch.float32, device=self.dev)
+            self.compute_done[slot].record(cur)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.compute_done[slot])  # the step that last read this input slot is done
+            self.xbuf[slot].copy_(host_images, non_blocking=True)
+            self.in_done[slot].record(self.s_in)
+        cur.wait_event(self.in_done[slot])
+        mean, cons = sample_from_teacher(self.model, self.xbuf[slot], self.n_samples,
+                                         do_consensus_masking=self.masking, eps=eps)
+        self.compute_done[slot].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.compute_done[slot])
+            out_mean.copy_(mean, non_blocking=True)
+            out_cons.copy_(cons, non_blocking=True)
+        mean.record_stream(self.s_out)
+        cons.record_stream(self.s_out)
+        return out_mean, out_cons
+
+    def flush(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.s_out)
+
+
 @torch.no_grad()
 def predict_host(model, host_images, n_samples, do_consensus_masking, out_mean, out_cons, eps=None):
     """End-to-end call with HOST buffers (pinned): H2D of the image batch, forward + fused MC consensus,

@@ -177,3 +177,24 @@ def test_rejects_bad_width_like_reference():
     m = _model()
     with pytest.raises(AssertionError):
         m.forward(torch.zeros(1, 1, 32, 36, device=dev), None, training=False)
+
+
+def test_host_predictor_pipeline_matches_direct_call():
+    """HostPredictor (pinned host buffers, copy streams, two slots in flight) returns exactly what the direct
+    device call returns, for a sequence of different batches."""
+    from probabilistic_domain_adaptation_b200 import consensus
+    dev = _dev()
+    m = _model(8.0)
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.randn(2, 1, 64, 96, generator=g).pin_memory() for _ in range(5)]
+    eps = torch.randn(16, 2, 6, generator=g).to(dev)
+    pred = consensus.HostPredictor(m, 16, True)
+    outs = [(torch.empty(2, 1, 64, 96).pin_memory(), torch.empty(2, 1, 64, 96, dtype=torch.int64).pin_memory())
+            for _ in range(5)]
+    for x, (om, oc) in zip(batches, outs):
+        pred.submit(x, om, oc, eps=eps)
+    pred.flush()
+    torch.cuda.synchronize()
+    for x, (om, oc) in zip(batches, outs):
+        mean, mask = consensus.sample_from_teacher(m, x.to(dev), 16, do_consensus_masking=True, eps=eps)
+        assert torch.equal(om, mean.cpu()) and torch.equal(oc, mask.cpu())

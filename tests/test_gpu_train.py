@@ -337,8 +337,8 @@ def test_training_gradients_match_oracle_autograd(rl_swap):
         if abs(r - 1) > worst_r[0]:
             worst_r = (abs(r - 1), k)
     print("rl_swap", rl_swap, "worst gradient cosine", worst_c, "worst norm deviation", worst_r)
-    assert worst_c[0] > 0.97, worst_c
-    assert worst_r[0] < 0.10, worst_r
+    assert worst_c[0] > 0.99, worst_c   # measured: 0.996
+    assert worst_r[0] < 0.05, worst_r   # measured: 0.014
 
 
 def test_optimizer_step_reduces_loss():
