@@ -163,10 +163,17 @@ int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const f
                                 void* grad_base, void* stream);
 
 /* Fcomb backward for one latent sample z [B][L]: dlogit [B][P] -> dfeat [B][P][64] bf16, parameter grads, dz [B][L].
- * scratch: fp32 [64*64 + B*64]. */
+ * Five chained tcgen05 GEMMs per 128-pixel tile (bf16 operands, fp32 accumulate).  scratch: fp32 [64*64 + 2*B*64]. */
 int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
                   float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream);
+
+/* Same contract in exact-order fp32 on CUDA cores: the numerics baseline of the tensor-core kernel above (~10x
+ * slower; explicit opt-in only).  scratch: fp32 [64*64 + B*64]. */
+int pda_fcomb_bwd_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
+                       const float* b2, const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat,
+                       float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, float* dz,
+                       float* scratch, void* stream);
 
 /* torch.optim.Adam step (the optimizer of every reference script, e.g. LIVECell/livecell_punet.py:58) over many
  * tensors in one launch.  table int64 [n_chunks][5] = (param, grad, exp_avg, exp_avg_sq, numel<=65536), all fp32.

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pda_multi_tensor_adam": [_P, _I, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_longlong,
                               _P, _P, _P],
     "pda_fcomb_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pda_fcomb_bwd_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None}
 

@@ -30,6 +30,10 @@ int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, i
 int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long long outer, int box_inner,
                         int box_outer);
 
+int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
+                 const float* w3, const float* dlogit, int B, int P, int L, void* dfeat, float* dw1f, float* dw2,
+                 float* db2, float* dw3, float* db3, float* dbz, float* bz, cudaStream_t st);
+
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, int B, int H, int W, int cout, int relu, int bn_override, cudaStream_t stream);
 

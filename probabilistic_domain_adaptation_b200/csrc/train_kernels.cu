@@ -905,6 +905,31 @@ int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const f
 int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
                   float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream) {
+  // scratch: fp32, at least 64*64 + 2*B*64 elements (dW1f accumulator, per-image column sums, per-image layer-1 bias)
+  if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !dlogit || !dfeat || !dw1 || !db1 || !dw2 || !db2 || !dw3 ||
+      !db3 || !dz || !scratch)
+    return PDA_ERR_ARG;
+  if (B <= 0 || P <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  cudaStream_t st = ST(stream);
+  float* dw1f = scratch;
+  float* dbz = scratch + FB * FB;
+  float* bz = dbz + (size_t)B * FB;
+  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (FB * FB + (size_t)B * FB), st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(dw2, 0, sizeof(float) * FB * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(db2, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(dw3, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(db3, 0, sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
+  const int r = fcomb_bwd_tc(feat, z, w1, b1, w2, b2, w3, dlogit, B, P, latent, dfeat, dw1f, dw2, db2, dw3, db3, dbz,
+                             bz, st);
+  if (r) return r;
+  PDA_COUNT(1);
+  fcomb_bwd_finish_kernel<<<1, 256, 0, st>>>(dbz, dw1f, w1, z, dw1, db1, dz, B, latent);
+  return LAUNCH_OK();
+}
+
+int pda_fcomb_bwd_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
+                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream) {
   // scratch: fp32, at least 64*64 + B*64 elements (dW1f accumulator, per-image column sums)
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !dlogit || !dfeat || !dw1 || !db1 || !dw2 || !db2 || !dw3 ||
       !db3 || !dz || !scratch)

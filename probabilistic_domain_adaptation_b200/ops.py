@@ -375,8 +375,9 @@ def multi_tensor_l2norm_bwd(table, norms, gout, total):
     return flat
 
 
-def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit):
-    """Backward of Fcomb for one latent sample: feat (B,H,W,64) bf16, z (B,L), dlogit (B,1,H,W) fp32."""
+def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit, precision="bf16"):
+    """Backward of Fcomb for one latent sample: feat (B,H,W,64) bf16, z (B,L), dlogit (B,1,H,W) fp32.
+    precision "bf16": tensor-core kernel; "fp32": the exact CUDA-core baseline."""
     _need_cuda(feat, z, w1, dlogit)
     lib = _lib.load()
     B, H, W, C = feat.shape
@@ -388,11 +389,12 @@ def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit):
     dw3 = torch.empty_like(w3)
     db3 = torch.empty(1, dtype=torch.float32, device=dev)
     dz = torch.empty((B, L), dtype=torch.float32, device=dev)
-    scratch = torch.empty(64 * 64 + B * 64, dtype=torch.float32, device=dev)
+    scratch = torch.empty(64 * 64 + 2 * B * 64, dtype=torch.float32, device=dev)
     z = z.contiguous().float()
     dlogit = dlogit.contiguous().float()
+    fn = lib.pda_fcomb_bwd if precision == "bf16" else lib.pda_fcomb_bwd_fp32
     with _Timed("fcomb_bwd", float(B * H * W)):
-        rc = lib.pda_fcomb_bwd(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+        rc = fn(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                b2.data_ptr(), w3.data_ptr(), dlogit.data_ptr(), B, H * W, L, dfeat.data_ptr(),
                                dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(),
                                db3.data_ptr(), dz.data_ptr(), scratch.data_ptr(), _stream())

@@ -195,36 +195,49 @@ def test_l2_regularisation_forward_backward():
         assert torch.allclose(l2_regularisation(m), ref, rtol=1e-6)
 
 
-@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9)])
-def test_fcomb_backward(shape):
-    from probabilistic_domain_adaptation_b200.training import FcombTrainFn
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9), (5, 136, 200)])
+def test_fcomb_backward(shape, precision):
+    """Fcomb backward (tensor-core kernel with bf16 operands / exact fp32 CUDA-core baseline) vs fp64 autograd."""
+    from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
     sd = po.make_state_dict(0, last_layer_gain=4.0)
     g = torch.Generator().manual_seed(23)
     b, h, w_ = shape
-    feat = torch.relu(torch.randn(b, h, w_, 64, generator=g)).to(dev).to(torch.bfloat16).requires_grad_(True)
-    z = torch.randn(b, 6, generator=g).to(dev).requires_grad_(True)
+    feat = torch.relu(torch.randn(b, h, w_, 64, generator=g)).to(dev).to(torch.bfloat16)
+    z = torch.randn(b, 6, generator=g).to(dev)
     keys = ["fcomb.layers.0", "fcomb.layers.2", "fcomb.last_layer"]
-    w = [sd[f"{n}.{p}"].to(dev).contiguous().requires_grad_(True) for n in keys for p in ("weight", "bias")]
+    w = [sd[f"{n}.{p}"].to(dev).contiguous() for n in keys for p in ("weight", "bias")]
     go = torch.randn(b, 1, h, w_, generator=g).to(dev)
-    logits = FcombTrainFn.apply(feat, z, *w)
-    (logits * go).sum().backward()
-    fr = feat.detach().double().requires_grad_(True)
-    zr = z.detach().double().requires_grad_(True)
-    sdr = {}
-    wr = []
+    dfeat, dw1, db1, dw2, db2, dw3, db3, dz = ops.fcomb_bwd(feat, z, w[0], w[1], w[2], w[3], w[4], go,
+                                                             precision=precision)
+    fr = feat.double().requires_grad_(True)
+    zr = z.double().requires_grad_(True)
+    sdr, wr = {}, []
     for n in keys:
         for p in ("weight", "bias"):
             t = sd[f"{n}.{p}"].to(dev).double().requires_grad_(True)
             sdr[f"{n}.{p}"] = t
             wr.append(t)
     ref = po.fcomb_logits(sdr, fr.permute(0, 3, 1, 2), zr)
-    assert (logits.double() - ref).abs().max().item() < 5e-3 * 4.0
     (ref * go.double()).sum().backward()
-    _close_grad(feat.grad, fr.grad, cos=0.9995, ratio=1e-2, what="dfeat")
-    assert torch.allclose(z.grad.double(), zr.grad, rtol=2e-3, atol=1e-4 * zr.grad.abs().max().item())
-    for a, r, n in zip(w, wr, ["w1", "b1", "w2", "b2", "w3", "b3"]):
-        assert torch.allclose(a.grad.double(), r.grad, rtol=2e-3, atol=2e-4 * r.grad.abs().max().item()), n
+    tight = precision == "fp32"
+    _close_grad(dfeat, fr.grad, cos=0.9995, ratio=1e-2, what="dfeat")
+    mine = [dw1, db1, dw2, db2, dw3, db3]
+    for a, r, n in zip(mine, wr, ["w1", "b1", "w2", "b2", "w3", "b3"]):
+        if tight:
+            assert torch.allclose(a.double(), r.grad.reshape(a.shape), rtol=2e-3,
+                                  atol=2e-4 * r.grad.abs().max().item()), n
+        else:
+            # the recompute uses the forward kernel's operands (fp16 hidden layer): its ReLU masks are those of the
+            # function actually evaluated and differ from the fp64 reference's for pre-activations within ~2^-11 of
+            # zero (~0.05 % of the units); gradients travel as bf16
+            _close_grad(a, r.grad.reshape(a.shape), cos=0.9995, ratio=1e-2, what=n)
+            assert (a.double() - r.grad.reshape(a.shape)).abs().max().item() < 6e-2 * r.grad.abs().max().item(), n
+    if tight:
+        assert torch.allclose(dz.double(), zr.grad, rtol=2e-3, atol=1e-4 * zr.grad.abs().max().item())
+    else:
+        _close_grad(dz, zr.grad, cos=0.9995, ratio=1e-2, what="dz")
 
 
 TRAIN_CASES = ["train_bce_64x64", "train_dice_64x64", "train_dice_weight_64x64", "train_dice_mask_48x80",
