@@ -54,9 +54,12 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w_oihw, con
  * Input = channel concat of src0 (c0 ch) and src1 (c1 ch, may be NULL/0) -- the torch.cat of
  * unet_blocks.py:56 is never materialised.  out and/or out_pool may be NULL.
  * Replaces unet_blocks.py:17-24 (DownConvBlock) and probabilistic_unet.py:53-61 (Encoder).
- * bn_tile: 0 = auto, else 64/128/256 output channels per CTA. */
+ * relu_mask (NHWC bf16 [B][H][W][cout], may be NULL): outputs are zeroed where relu_mask <= 0 -- the ReLU backward of
+ * the layer that produced this conv's input, fused into the epilogue when the kernel runs as dgrad.
+ * bn_tile: 0 = auto, else 64/128 output channels per CTA. */
 int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
-                     void* out, void* out_pool, int B, int H, int W, int cout, int relu, int bn_tile, void* stream);
+                     void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
+                     int bn_tile, void* stream);
 
 /* Same contract on plain CUDA cores (one thread per output element).  Cross-check kernel for the
  * parity tests; the product path never selects it implicitly. */

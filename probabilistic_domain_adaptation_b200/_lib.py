@@ -22,7 +22,7 @@ SIGNATURES = {
     "pda_pack_conv3x3_weights": [_P, _P, _I, _I, _I, _P],
     "pda_pack_conv3x3_weights_multi": [_P, _I, _P],
     "pda_conv3x3_first": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pda_conv3x3_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pda_conv3x3_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_bf16_simt": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_avgpool2_bf16": [_P, _P, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear_bf16": [_P, _P, _I, _I, _I, _I, _P],

@@ -23,6 +23,8 @@ struct ConvArgs {
   const float* bias;
   __nv_bfloat16* out;       // NHWC [B][H][W][cout] or nullptr
   __nv_bfloat16* out_pool;  // NHWC [B][H/2][W/2][cout] (2x2 average of the post-ReLU fp32 values) or nullptr
+  const __nv_bfloat16* mask;  // NHWC [B][H][W][cout] or nullptr: outputs are zeroed where mask <= 0 (ReLU backward
+                              // of the layer that produced this conv's input, fused into the dgrad epilogue)
 };
 
 void* get_encode_tiled();  // cuTensorMapEncodeTiled driver entry point (or nullptr)
@@ -35,7 +37,8 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
                  float* db2, float* dw3, float* db3, float* dbz, float* bz, cudaStream_t st);
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
-               void* out_pool, int B, int H, int W, int cout, int relu, int bn_override, cudaStream_t stream);
+               void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
+               cudaStream_t stream);
 
 // log2(C / 8) for C = 8 * 2^k (the NHWC kernels address 16-byte channel chunks with shifts), else -1
 static inline int c8_shift(int C) {

@@ -269,6 +269,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + g * 64 + cb * 32,
                     v);
+          uint4 mk[4];
+          if (p.mask) {  // issued before the TMEM wait so that both latencies overlap
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0 + g * 64 + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mk[j] = valid ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
+          }
           tmem_ld_wait();
           if (cb == 1 && sub + 2 >= NSUB) {
             // last TMEM read of this warp for this unit: hand the accumulator buffer back to the MMA warp
@@ -281,6 +288,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int j = 0; j < 32; ++j) {
             float tv = __uint_as_float(v[j]) + bias_s[n0 + g * 64 + cb * 32 + j];
             f[j] = p.relu ? fmaxf(tv, 0.f) : tv;
+          }
+          if (p.mask) {
+            // bf16 mask values are post-ReLU activations (>= 0): "> 0" <=> magnitude bits non-zero and sign clear
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                if (h == 0u || h >= 0x8000u) f[8 * j + e] = 0.f;
+              }
+            }
           }
           if (p.out) {
             // this pixel's 64 bytes of the 128-byte row, 16-byte chunks XOR-swizzled by (row & 7) as TMA expects
@@ -407,7 +426,8 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 }
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
-               void* out_pool, int B, int H, int W, int cout, int relu, int bn_override, cudaStream_t stream) {
+               void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
+               cudaStream_t stream) {
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
     return PDA_ERR_SHAPE;
   if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
@@ -423,6 +443,7 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   a.bias = bias;
   a.out = static_cast<__nv_bfloat16*>(out);
   a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+  a.mask = static_cast<const __nv_bfloat16*>(mask);
   CUtensorMap tA0, tA1, tB;
   int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);
   if (r) return r;

@@ -423,9 +423,10 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
 }
 
 int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
-                     void* out, void* out_pool, int B, int H, int W, int cout, int relu, int bn_tile, void* stream) {
+                     void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
+                     int bn_tile, void* stream) {
   if (!src0 || !w_packed || (!out && !out_pool) || (c1 > 0 && !src1)) return PDA_ERR_ARG;
-  return conv3x3_tc(src0, c0, src1, c1, w_packed, bias, out, out_pool, B, H, W, cout, relu, bn_tile,
+  return conv3x3_tc(src0, c0, src1, c1, w_packed, bias, out, out_pool, relu_mask, B, H, W, cout, relu, bn_tile,
                     (cudaStream_t)stream);
 }
 

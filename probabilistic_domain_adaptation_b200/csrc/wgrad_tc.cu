@@ -31,6 +31,8 @@ struct WgradArgs {
   int n64;         // cout / 64
   int items;       // n64 * (c0 + c1) / 64
   float* scratch;  // [cout][9][ctot] fp32, zero-initialised by the caller
+  float* dbias;    // [cout] fp32, zero-initialised, or nullptr: bias gradient = column sums of dZ, from one extra
+                   // "ones" MMA on the items of input-channel chunk 0
 };
 
 struct WgradSmem {
@@ -38,10 +40,11 @@ struct WgradSmem {
   static constexpr int DZ_BYTES = 16 * 1024;         // [16 rows][8 px][64 co] bf16
   static constexpr int STAGE_BYTES = 3 * SLAB + DZ_BYTES;  // slabs first: tap pair 4 over-reads 1 KB into the dZ tile
   static constexpr int STAGES = 3;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int ONES_OFF = STAGES * STAGE_BYTES;  // 1 KB of bf16 ones: an MN-major A block whose rows all alias
+  static constexpr int BAR_OFF = ONES_OFF + 1024;
   static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 2) * 8;
   static constexpr int DYN_BYTES = SLOT_OFF + 16 + 1024;
-  static constexpr int TMEM_COLS = 512;              // 5 x 64 used
+  static constexpr int TMEM_COLS = 512;              // 5 x 64 tap pairs + 64 for the bias column sums
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -80,6 +83,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 128)
+    reinterpret_cast<uint4*>(smem + L::ONES_OFF)[threadIdx.x - 64] =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -145,6 +152,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const uint64_t da2 = umma_desc_mn_sw128(sa + L::SLAB + 1024, 1024, 1024);         // (kx1,ky1) (kx1,ky2)
         const uint64_t da3 = umma_desc_mn_sw128(sa + 2 * L::SLAB, 1024, 1024);            // (kx2,ky0) (kx2,ky1)
         const uint64_t da4 = umma_desc_mn_sw128(sa + 2 * L::SLAB + 2048, 1024, 1024);     // (kx2,ky2) (discarded)
+        const uint64_t d1s = umma_desc_mn_sw128(sbase + L::ONES_OFF, 0, 0);               // all-ones rows
+        const bool bias_item = p.dbias != nullptr && item / p.n64 == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // 16 pixels per MMA = 2 rows of 8 px = 2048 B: +128 in 16-byte units
@@ -154,6 +163,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
           umma_bf16(tmem + 128, da2 + 128 * k, db + 128 * k, idesc, acc);
           umma_bf16(tmem + 192, da3 + 128 * k, db + 128 * k, idesc, acc);
           umma_bf16(tmem + 256, da4 + 128 * k, db + 128 * k, idesc, acc);
+          if (bias_item) umma_bf16(tmem + 320, d1s, db + 128 * k, idesc, acc);  // every row = sum_px dZ[px][co]
         }
         umma_commit(empty_bar(s));
       }
@@ -190,6 +200,20 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               atomicAdd(dst + static_cast<size_t>(cb * 32 + j) * 9 * ctot, __uint_as_float(v[j]));
+          }
+        }
+      }
+      if (p.dbias != nullptr && ch == 0 && q == 0) {
+        // all 128 rows of the ones-block accumulator are identical: row 0 carries the bias gradient of this co block.
+        // (tcgen05.ld is warp-collective: the whole warp of lane quarter 0 loads, lane 0 publishes)
+#pragma unroll 1
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem + 320 + cb * 32, v);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(p.dbias + (nb << 6) + cb * 32 + j, __uint_as_float(v[j]));
           }
         }
       }
@@ -276,6 +300,9 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   a.n64 = cout >> 6;
   a.items = a.n64 * (ctot >> 6);
   a.scratch = scratch;
+  a.dbias = dbias;
+  if (dbias && !accumulate && cudaMemsetAsync(dbias, 0, sizeof(float) * cout, stream) != cudaSuccess)
+    return PDA_ERR_CUDA;
   CUtensorMap tX0, tX1, tDZ;
   int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, 8, 18, 64);
   if (r) return r;
@@ -304,18 +331,5 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   PDA_COUNT(1);
   wgrad_scatter_kernel<<<(int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256), 256, 0, stream>>>(
       scratch, dw_oihw, cout, ctot, accumulate);
-  if (dbias) {
-    if (!accumulate && cudaMemsetAsync(dbias, 0, sizeof(float) * cout, stream) != cudaSuccess) return PDA_ERR_CUDA;
-    const int C2 = cout / 2;
-    if (256 % C2 && C2 < 256) return PDA_ERR_SHAPE;
-    const int threads = C2 >= 256 ? C2 : 256;
-    const long long npix = (long long)B * H * W;
-    int blocks = (int)((npix + 63) / 64);
-    if (blocks > 148 * 2) blocks = 148 * 2;
-    if (threads > 1024) return PDA_ERR_SHAPE;
-    PDA_COUNT(1);
-    bias_grad_kernel<<<blocks, threads, threads * 2 * sizeof(float), stream>>>(
-        static_cast<const __nv_bfloat162*>(dz), dbias, npix, C2);
-  }
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

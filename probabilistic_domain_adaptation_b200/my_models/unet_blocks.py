@@ -41,6 +41,12 @@ def run_conv_stack(convs, x, first_input=None, pool_last=False, keep_full=True, 
     cin<=2 first layer.  src1: optional second K-segment (channel concat) of the first conv.
     Returns (full, pooled) of the last conv.
     """
+    from ..autograd_ops import _needs_grad
+    plist = [t for c in convs for t in (c.weight, c.bias)]
+    if _needs_grad(x, src1, *plist):
+        # training: the whole block is one autograd node (cross-layer fusion in its backward)
+        from ..training import conv_stack_train
+        return conv_stack_train(convs, x, src1, first_input, pool_last)
     full, pooled = x, None
     for j, conv in enumerate(convs):
         last = j == len(convs) - 1

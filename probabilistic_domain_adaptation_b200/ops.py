@@ -75,8 +75,10 @@ def conv3x3_first(x0, x1, w, bias, relu=True):
     return out
 
 
-def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=False, bn_tile=0, simt=False):
-    """src0/src1: NHWC bf16 (src1 optional, channel-concatenated after src0); returns (full, pooled)."""
+def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=False, bn_tile=0, simt=False,
+            relu_mask=None):
+    """src0/src1: NHWC bf16 (src1 optional, channel-concatenated after src0); returns (full, pooled).
+    relu_mask (B,H,W,cout) bf16: the output is zeroed where relu_mask <= 0 (fused ReLU backward, dgrad use)."""
     _need_cuda(src0, src1, w_packed, bias)
     lib = _lib.load()
     B, H, W, c0 = src0.shape
@@ -86,13 +88,18 @@ def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=Fal
     assert src0.is_contiguous() and (src1 is None or src1.is_contiguous())
     full = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=src0.device) if want_full else None
     pool = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=src0.device) if want_pool else None
+    if relu_mask is not None:
+        assert relu_mask.shape == (B, H, W, cout) and relu_mask.is_contiguous() and relu_mask.dtype == torch.bfloat16
     if simt or FORCE_SIMT_CONV:
         rc = lib.pda_conv3x3_bf16_simt(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
                                        _ptr(full), _ptr(pool), B, H, W, cout, int(relu), _stream())
+        if rc == 0 and relu_mask is not None:  # the cross-check conv has no fused mask epilogue
+            full = relu_pool_bwd(full, None, relu_mask)
     else:
         with _Timed("conv3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
             rc = lib.pda_conv3x3_bf16(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
-                                      _ptr(full), _ptr(pool), B, H, W, cout, int(relu), int(bn_tile), _stream())
+                                      _ptr(full), _ptr(pool), _ptr(relu_mask), B, H, W, cout, int(relu),
+                                      int(bn_tile), _stream())
     _lib.check(rc, "conv3x3")
     return full, pool
 

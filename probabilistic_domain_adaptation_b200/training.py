@@ -35,21 +35,103 @@ class Conv3x3Fn(torch.autograd.Function):
         g_full = None if g_full is None else g_full.contiguous()
         g_pool = None if g_pool is None else g_pool.contiguous()
         need_x, need_s1, need_w, need_b = ctx.needs_input_grad[:4]
-        # the bias gradient (sum over pixels of dZ) comes out of the same pass that builds dZ
-        dz, db = ops.relu_pool_bwd(g_full, g_pool, full if ctx.relu else None, shape=full.shape, want_bias=True)
-        if not need_b:
-            db = None
+        dz = ops.relu_pool_bwd(g_full, g_pool, full if ctx.relu else None, shape=full.shape)
         c0 = x.shape[3]
-        dx = dsrc1 = dw = None
+        dx = dsrc1 = dw = db = None
         if need_x or need_s1:
             wrot = packed_weight(ctx.conv, rot180=True)  # (c0 + c1, 9 * cout)
             if need_x:
                 dx, _ = ops.conv3x3(dz, None, wrot[:c0], None, relu=False)
             if need_s1 and src1 is not None:
                 dsrc1, _ = ops.conv3x3(dz, None, wrot[c0:], None, relu=False)
-        if need_w:
-            dw, _ = ops.conv3x3_wgrad(x, src1, dz, want_bias=False)
+        if need_w or need_b:
+            # the bias gradient (column sums of dZ) rides along in the weight-gradient kernel
+            dw, db = ops.conv3x3_wgrad(x, src1, dz, want_bias=True)
         return dx, dsrc1, dw, db, None, None, None
+
+
+class ConvStackFn(torch.autograd.Function):
+    """One block of the reference nets -- n x [conv3x3 + ReLU] with an optional fused 2x2 average pool of the last
+    output (DownConvBlock / the conv_block of UpConvBlock / one Encoder block: unet_blocks.py:16-24,
+    probabilistic_unet.py:53-61) -- as a single autograd node, so that the backward can fuse across its layers:
+
+      dZ_last = (dFull + pool^T dPool) * (Y_last > 0)                      one elementwise kernel per block
+      for j = last .. 1:  dW_j, db_j = wgrad(Y_{j-1}, dZ_j)                bias gradient from the same kernel
+                          dZ_{j-1}   = dgrad(dZ_j, rot180 W_j) * (Y_{j-1} > 0)   ReLU mask fused in the dgrad epilogue
+      first layer:        dW_0, db_0 (+ dX, dBridge when the block input needs a gradient)
+
+    args: x (NHWC bf16 or None), src1 (bridge or None), x0 / x1 (fp32 planes of a cin <= 2 first layer or None),
+    convs (list of nn.Conv2d containers), pool_last, then weight_0, bias_0, weight_1, bias_1, ...
+    """
+
+    @staticmethod
+    def forward(ctx, x, src1, x0, x1, convs, pool_last, *params):
+        n = len(convs)
+        ys = []
+        cur = x
+        pooled = None
+        for j, conv in enumerate(convs):
+            last = j == n - 1
+            if j == 0 and x0 is not None:
+                cur = ops.conv3x3_first(x0, x1, conv.weight.detach(), conv.bias.detach(), True)
+                if last and pool_last:
+                    pooled = ops.avgpool2(cur)
+            else:
+                cur, pooled = ops.conv3x3(cur, src1 if j == 0 else None, packed_weight(conv), conv.bias.detach(), True,
+                                          True, last and pool_last)
+            ys.append(cur)
+        ctx.convs, ctx.pool_last, ctx.first_planes = convs, pool_last, x0 is not None
+        ctx.save_for_backward(x, src1, x0, x1, *ys)
+        ctx.set_materialize_grads(False)
+        return cur, pooled
+
+    @staticmethod
+    def backward(ctx, g_full, g_pool):
+        convs = ctx.convs
+        n = len(convs)
+        x, src1, x0, x1, *ys = ctx.saved_tensors
+        none = (None,) * (6 + 2 * n)
+        if g_full is None and g_pool is None:
+            return none
+        g_full = None if g_full is None else g_full.contiguous()
+        g_pool = None if g_pool is None else g_pool.contiguous()
+        if ctx.first_planes and n == 1 and g_pool is not None:
+            # pooled output of a single first-layer conv (not a reference configuration): unfused pool backward
+            gp = ops.relu_pool_bwd(None, g_pool, None, shape=ys[0].shape)
+            g_full = gp if g_full is None else ops.relu_pool_bwd(g_full, g_pool, None, shape=ys[0].shape)
+            g_pool = None
+        dz = ops.relu_pool_bwd(g_full, g_pool, ys[-1], shape=ys[-1].shape)
+        grads = [None] * (2 * n)
+        dx = dsrc1 = None
+        for j in range(n - 1, -1, -1):
+            conv = convs[j]
+            need_w = ctx.needs_input_grad[6 + 2 * j] or ctx.needs_input_grad[7 + 2 * j]
+            if j == 0 and ctx.first_planes:
+                if need_w:
+                    grads[0], grads[1] = ops.conv3x3_first_bwd(x0, x1, ys[0], dz)  # (mask by ys[0] is idempotent)
+                break
+            xin = ys[j - 1] if j > 0 else x
+            s1 = src1 if j == 0 else None
+            if need_w:
+                grads[2 * j], grads[2 * j + 1] = ops.conv3x3_wgrad(xin, s1, dz, want_bias=True)
+            if j > 0:
+                dz, _ = ops.conv3x3(dz, None, packed_weight(conv, rot180=True), None, relu=False, relu_mask=ys[j - 1])
+            else:
+                c0 = x.shape[3]
+                wrot = packed_weight(conv, rot180=True)  # (c0 + c1, 9 * cout): contiguous row slices per segment
+                if ctx.needs_input_grad[0]:
+                    dx, _ = ops.conv3x3(dz, None, wrot[:c0], None, relu=False)
+                if src1 is not None and ctx.needs_input_grad[1]:
+                    dsrc1, _ = ops.conv3x3(dz, None, wrot[c0:], None, relu=False)
+        return (dx, dsrc1, None, None, None, None, *grads)
+
+
+def conv_stack_train(convs, x, src1, first_input, pool_last):
+    x0, x1 = first_input if first_input is not None else (None, None)
+    params = []
+    for c in convs:
+        params += [c.weight, c.bias]
+    return ConvStackFn.apply(x, src1, x0, x1, list(convs), pool_last, *params)
 
 
 def conv3x3_train(x, src1, conv, relu, want_full, want_pool):
