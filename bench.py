@@ -40,6 +40,7 @@ def parse():
                     help="infer: MC inference leg only; train: mean-teacher step leg only")
     ap.add_argument("--train-batch", type=int, default=4, help="images per GPU per mean-teacher step (MitoEM: 4)")
     ap.add_argument("--train-size", type=int, default=512)
+    ap.add_argument("--no-extras", action="store_true", help="skip the S sweep and the source-training step")
     return ap.parse_args()
 
 
@@ -119,6 +120,37 @@ def cpu_reference_run(size, samples, tiles, steps, warmup):
         step()
     dt = (time.perf_counter() - t0) / steps
     return tiles * size * size * samples / dt, dt, cores
+
+
+def cpu_reference_train_step(batch, size, samples):
+    """One mean-teacher consensus step of the reference on host cores (oracle port, fp32 autograd + torch Adam):
+    teacher MC + consensus mask, student Dice-ELBO + L2, backward, Adam, EMA.  Returns (img/s, s/step, cores)."""
+    import torch
+    from oracle import punet_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    student = {k: v.clone().requires_grad_(True) for k, v in po.make_state_dict(0, last_layer_gain=8.0).items()}
+    teacher = {k: v.detach().clone() for k, v in student.items()}
+    opt = torch.optim.Adam(list(student.values()), lr=1e-5)
+    x, _, eps, eps_post = po.synthetic_inputs(batch, size, size, s=samples)
+    x1, x2 = x + 0.1, x - 0.1
+
+    def step():
+        with torch.no_grad():
+            y, z, _ = po.sample_from_teacher(teacher, x1, eps, do_consensus_masking=True)
+        opt.zero_grad()
+        out = po.training_loss(student, x2, y, eps_post, z, beta=1.0, consensus_masking=True, rl_swap=True)
+        out["loss"].backward()
+        opt.step()
+        with torch.no_grad():
+            new = po.momentum_update(teacher, {k: v.detach() for k, v in student.items()}, 0.999)
+            teacher.update(new)
+
+    step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return batch / dt, dt, cores
 
 
 def run_reference(args):
@@ -224,8 +256,33 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     ms_e2e, _, _ = timed(step_e2e, args.steps)
     final_loss = float(loss.item())
     reducer.remove()
+
+    # BASELINE config 2: source training step (punet_trainer.py:24-36) on LIVECell shape 8x1x512x512
+    src = None
+    if not args.no_extras:
+        Bs = 8
+        xs = torch.randn(Bs, 1, HW, HW, generator=g).to(dev)
+        ys = (torch.rand(Bs, 1, HW, HW, generator=g) > 0.5).float().to(dev)
+        red2 = GradAllReducer(model)
+        bp2 = steps.default_backprop(opt, red2, model)
+        for _ in range(2):
+            steps.punet_step(model, opt, xs, ys, backprop=bp2)
+        ms_src, _, _ = timed(lambda: steps.punet_step(model, opt, xs, ys, backprop=bp2), max(3, args.steps // 2))
+        red2.remove()
+        nsrc = max(3, args.steps // 2)
+        src = {"metric": "punet_source_train_img_per_s", "value": Bs * world * nsrc / (ms_src * 1e-3), "unit": "img/s",
+               "ms_per_step": ms_src / nsrc,
+               "config": {"workload": f"source ELBO step (Dice + KL + L2, Adam) on {Bs}x1x{HW}x{HW} per GPU "
+                                      f"(BASELINE config 2, LIVECell shape)", "parallelism": f"dp{world}"}}
     if rank != 0:
         return None
+    cpu_train = None
+    if world == 1 and not args.no_cpu_baseline:
+        cval, cdt, cores = cpu_reference_train_step(1, 256, S)
+        cpu_train = {"value": cval, "unit": "img/s", "cores": cores, "kind": "port",
+                     "sample": f"1 image 256x256 (1/16 of the pixels of a {HW}x{HW} image), S={S}, 1 timed step "
+                               f"after 1 warm-up ({cdt:.1f} s); per-pixel cost is size-independent",
+                     "value_at_bench_shape": cval * (256.0 * 256.0) / (HW * HW)}
     _, tf_peak, peak_src = load_peaks()
     kinds = {}
     for k, a, b, w in prof:
@@ -253,6 +310,8 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
                      "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms},
         "kernels": per_kernel,
+        "cpu_baseline": cpu_train,
+        "source_train": src,
         "model_tflops": TRAIN_FLOP_PER_PX * float(Bt) * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
     }
 
@@ -357,6 +416,17 @@ def run_ours(args):
     fc_gbs = fc_px * 140.0 / (fc_ms * 1e-3) / 1e9 if fc_ms > 0 else 0.0
     fc_tf = fc_px * 2.0 * (4096 + S * 4160) / (fc_ms * 1e-3) / 1e12 if fc_ms > 0 else 0.0
 
+    # BASELINE config 5: S sweep on the same tiles (device-resident timing)
+    sweep = None
+    if not args.no_extras:
+        sweep = {}
+        for s_ in (8, 32, 64):
+            eps_s = torch.randn(s_, T, 6, generator=torch.Generator().manual_seed(3)).to(dev)
+            fn = lambda: consensus.sample_from_teacher(model, x_dev, s_, do_consensus_masking=True, eps=eps_s)  # noqa: E731
+            fn()
+            ms_s, _, _, _ = timed(fn, max(3, args.steps // 4))
+            sweep[str(s_)] = float(T) * HW * HW * s_ * world * max(3, args.steps // 4) / (ms_s * 1e-3)
+
     train = None
     if args.mode in ("train", "both"):
         del x_dev, eps
@@ -400,6 +470,7 @@ def run_ours(args):
                            "share_of_step": fc_ms / ms},
         "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
         "cpu_baseline": cpu,
+        "mc_sweep_px_samples_per_s": sweep,
         "train": train,
     }
     print(json.dumps(line))
