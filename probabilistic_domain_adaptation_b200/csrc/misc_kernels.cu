@@ -202,24 +202,44 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
   const int x1 = (int)sx;
   const int xp = (x1 < w - 1) ? 1 : 0;
   const float lx1 = sx - x1, lx0 = 1.f - lx1;
-  for (unsigned r = blockIdx.y; r < (unsigned)B * Ho; r += gridDim.y) {
-    const unsigned b = r / Ho, Y = r - b * Ho;
-    const float sy = rh * Y;
-    const int y1 = (int)sy;
-    const int yp = (y1 < h - 1) ? 1 : 0;
-    const float ly1 = sy - y1, ly0 = 1.f - ly1;
-    const uint4* p = in + ((((size_t)b * h + y1) * w + x1) << c_shift) + c;
-    const uint4 r00 = __ldg(p), r01 = __ldg(p + ((size_t)xp << c_shift));
-    const uint4 r10 = __ldg(p + (((size_t)yp * w) << c_shift)), r11 = __ldg(p + (((size_t)yp * w + xp) << c_shift));
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    unpack8(r00, v00);
-    unpack8(r01, v01);
-    unpack8(r10, v10);
-    unpack8(r11, v11);
+  const unsigned rows = (unsigned)B * Ho;
+  // two output rows per iteration: eight independent 16-byte loads in flight per thread
+  for (unsigned r0 = blockIdx.y; r0 < rows; r0 += 2 * gridDim.y) {
+    uint4 q[2][4];
+    float ly1[2];
+    unsigned rr[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o[i] = ly0 * (lx0 * v00[i] + lx1 * v01[i]) + ly1 * (lx0 * v10[i] + lx1 * v11[i]);
-    out[((size_t)r * Wo << c_shift) + xc] = pack8(o);
+    for (int u = 0; u < 2; ++u) {
+      const unsigned r = r0 + u * gridDim.y;
+      rr[u] = r;
+      if (r < rows) {
+        const unsigned b = r / Ho, Y = r - b * Ho;
+        const float sy = rh * Y;
+        const int y1 = (int)sy;
+        const int yp = (y1 < h - 1) ? 1 : 0;
+        ly1[u] = sy - y1;
+        const uint4* p = in + ((((size_t)b * h + y1) * w + x1) << c_shift) + c;
+        q[u][0] = __ldg(p);
+        q[u][1] = __ldg(p + ((size_t)xp << c_shift));
+        q[u][2] = __ldg(p + (((size_t)yp * w) << c_shift));
+        q[u][3] = __ldg(p + (((size_t)yp * w + xp) << c_shift));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (rr[u] < rows) {
+        const float l1 = ly1[u], l0 = 1.f - l1;
+        float v00[8], v01[8], v10[8], v11[8], o[8];
+        unpack8(q[u][0], v00);
+        unpack8(q[u][1], v01);
+        unpack8(q[u][2], v10);
+        unpack8(q[u][3], v11);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = l0 * (lx0 * v00[i] + lx1 * v01[i]) + l1 * (lx0 * v10[i] + lx1 * v11[i]);
+        out[((size_t)rr[u] * Wo << c_shift) + xc] = pack8(o);
+      }
+    }
   }
 }
 

@@ -183,7 +183,7 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
     return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs}
 
 
-_EMA_CHUNK = 65536
+_EMA_CHUNK = 16384  # elements per 256-thread block of the multi-tensor kernels (<= 65536)
 
 
 def build_ema_table(teacher_params, student_params):

@@ -4,7 +4,7 @@ import torch
 
 from . import _lib, ops
 
-_CHUNK = 65536
+_CHUNK = 16384  # elements per 256-thread block of the multi-tensor kernel
 
 
 class FusedAdam(torch.optim.Optimizer):
