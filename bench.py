@@ -427,6 +427,23 @@ def run_ours(args):
             ms_s, _, _, _ = timed(fn, max(3, args.steps // 4))
             sweep[str(s_)] = float(T) * HW * HW * s_ * world * max(3, args.steps // 4) / (ms_s * 1e-3)
 
+    # whole-image tiled prediction (blocks of 384 + halo 64 as punet_predictions.py:41-49), image
+    # uploaded from pinned host memory, blocks sharded over the ranks
+    tiled_res = None
+    if not args.no_extras:
+        from probabilistic_domain_adaptation_b200 import tiled
+        IH = 2048
+        himg = (torch.randn(IH, IH, generator=g) * 30 + 100).pin_memory()
+        fn = lambda: tiled.predict_with_halo(himg, model, S, (384, 384), (64, 64), 8, rank=rank, world=world)  # noqa: E731
+        fn()
+        nrep = max(3, args.steps // 4)
+        ms_t, _, _, _ = timed(fn, nrep)
+        tiled_res = {"metric": "tiled_prediction_image_px_samples_per_s", "value": float(IH) * IH * S * nrep / (ms_t * 1e-3),
+                     "unit": "px*samples/s", "ms_per_image": ms_t / nrep,
+                     "config": {"workload": f"{IH}x{IH} image, blocks 384 + halo 64 (36 blocks of <= 512x512), S={S}, "
+                                            f"per-block standardisation, host image -> device mean-probability image",
+                                "parallelism": f"blocks sharded x{world}"}}
+
     train = None
     if args.mode in ("train", "both"):
         del x_dev, eps
@@ -471,6 +488,7 @@ def run_ours(args):
         "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
         "cpu_baseline": cpu,
         "mc_sweep_px_samples_per_s": sweep,
+        "tiled_prediction": tiled_res,
         "train": train,
     }
     print(json.dumps(line))

@@ -111,6 +111,16 @@ int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
 int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream);
 
+/* Tiled prediction driver (the reference calls torch_em.util.prediction.predict_with_halo,
+ * punet_predictions.py:41-49, one block at a time from numpy).  rois / inner: device int32 [T][4] = (y0, x0, h, w) in
+ * image coordinates; all T outer blocks have the same size th x tw.
+ * gather: out[t] = (image[roi_t] - mean_t) / (std_t + 1e-7)  (per-block standardisation, population std);
+ *         stats: double [2*T] scratch.   scatter: out_image[inner_t] = pred[t][inner_t - roi_t origin]. */
+int pda_tile_gather_standardize(const float* image, int H, int W, const int32_t* rois, int T, int th, int tw,
+                                double* stats, float* out, void* stream);
+int pda_tile_scatter(const float* pred, int T, int th, int tw, const int32_t* rois, const int32_t* inner, float* out,
+                     int H, int W, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Training (backward) entry points.  They replace what torch.autograd runs behind loss.backward() in the step
  * bodies punet_trainer.py:24-36 / mean_teacher_trainer.py:111-119 (cuDNN dgrad/wgrad, ATen elementwise backward).
@@ -155,6 +165,12 @@ int pda_recon_loss_fwd(const float* logits, const float* segm, const float* cons
                        long long n, int dice, double* partial, float* out2, float* stats3, void* stream);
 int pda_recon_loss_bwd(const float* logits, const float* segm, const float* consm_f32, const int64_t* consm_i64,
                        long long n, int dice, const float* stats3, const float* gout2, float* dlogits, void* stream);
+
+/* Validation metric dice_score (my_utils/util.py:17-44; punet_trainer.py:78-81 calls it on the Monte-Carlo mean and the
+ * ground truth after a device->host copy): 2 sum(gt*seg) / (sum(gt) + sum(seg) + 1e-7).  thr_seg / thr_gt: NaN = no
+ * threshold, else x -> (x > thr).  partial: double [3 * pda_recon_loss_blocks(n)].  out: fp32 [1]. */
+int pda_dice_score(const float* seg, const float* gt, long long n, float thr_seg, float thr_gt, double* partial,
+                   float* out, void* stream);
 
 /* l2_regularisation (utils.py:32-40): out = sum_t ||W_t||_2 over many tensors in two launches.
  * table int64 [n_chunks][4] = (ptr, numel<=65536, tensor_index, 0);

@@ -140,8 +140,27 @@ def train_case(name, b, h, w, rl_swap, consm_kind, with_grads):
     print(name, "elbo", elbo.item(), "kl", model.kl.item(), "reg", reg.item())
 
 
+def dice_case():
+    """prob_utils/my_utils/util.py imports only numpy + torch: the reference function itself is executed."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location(
+        "ref_util", os.path.join(ref_import.REFERENCE_ROOT, "prob_utils", "my_utils", "util.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.RandomState(0)
+    seg = rng.rand(2, 96, 80).astype(np.float32)
+    gt = (rng.rand(2, 96, 80) > 0.6).astype(np.float32)
+    cases = {(ts, tg): ref.dice_score(seg, gt, ts, tg) for ts, tg in [(None, None), (0.5, None), (0.5, 0.5), (0.9, 0.1)]}
+    torch.save({"desc": "reference prob_utils/my_utils/util.py:dice_score on rand(seed 0) seg (2,96,80) / gt = rand > 0.6",
+                "seg": torch.from_numpy(seg), "gt": torch.from_numpy(gt), "cases": cases},
+               os.path.join(GOLD, "dice_score.pt"))
+    print("dice_score", cases)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    dice_case()
     torch.set_num_threads(os.cpu_count())
     mc_case("mc_64x64_s16", 1, 64, 64, 16, 24.0)
     mc_case("mc_40x72_s4_b2", 2, 40, 72, 4, 24.0)

@@ -265,6 +265,17 @@ def adamt_momentum(iteration, momentum=0.999):
     return min(1 - 1 / (iteration + 1), momentum)
 
 
+def dice_score(segmentation, groundtruth, threshold_seg=None, threshold_gt=None):
+    """prob_utils/my_utils/util.py:17-44 (numpy): 2 sum(gt * seg) / (sum(gt) + sum(seg) + 1e-7), optional thresholds."""
+    import numpy as np
+    assert segmentation.shape == groundtruth.shape
+    seg = segmentation if threshold_seg is None else segmentation > threshold_seg
+    gt = groundtruth if threshold_gt is None else groundtruth > threshold_gt
+    nom = 2 * np.sum(gt * seg)
+    denom = np.sum(gt) + np.sum(seg)
+    return float(nom) / float(denom + 1e-7)
+
+
 def distribution_alignment(y, source_distribution):
     """fixmatch_trainer.py:77-84."""
     y_binary = torch.where(y >= 0.5, 1, 0)

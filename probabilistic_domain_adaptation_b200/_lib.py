@@ -32,6 +32,8 @@ SIGNATURES = {
     "pda_kl_diag_gauss": [_P, _P, _P, _I, _I, _P],
     "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
+    "pda_tile_gather_standardize": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P],
+    "pda_tile_scatter": [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -43,6 +45,7 @@ SIGNATURES = {
     "pda_recon_loss_blocks": [_c.c_longlong],
     "pda_recon_loss_fwd": [_P, _P, _P, _P, _c.c_longlong, _I, _P, _P, _P, _P],
     "pda_recon_loss_bwd": [_P, _P, _P, _P, _c.c_longlong, _I, _P, _P, _P, _P],
+    "pda_dice_score": [_P, _P, _c.c_longlong, _F, _F, _P, _P, _P],
     "pda_multi_tensor_l2norm_fwd": [_P, _I, _I, _P, _P, _P, _P],
     "pda_multi_tensor_l2norm_bwd": [_P, _I, _P, _P, _P, _P],
     "pda_multi_tensor_adam": [_P, _I, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_longlong,

@@ -392,6 +392,74 @@ __global__ void avgpool2_f32_to_bf16_kernel(const float* __restrict__ in, __nv_b
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tiled prediction (the reference feeds torch_em.util.prediction.predict_with_halo one block at a time,
+// punet_predictions.py:41-49): gather a batch of equally sized outer blocks from the image, standardise each block
+// with its own mean / population std ((x - mean) / (std + 1e-7), torch_em.transform.raw.standardize), and scatter the
+// inner (halo-cropped) part of a prediction batch back into the output image.  rois: int32 [T][4] = (y0, x0, h, w).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_stats_kernel(const float* __restrict__ img, int W, const int* __restrict__ rois, int th, int tw,
+                  double* __restrict__ stats) {
+  const int t = blockIdx.y;
+  const int y0 = rois[4 * t], x0 = rois[4 * t + 1];
+  const int n = th * tw;
+  double s = 0.0, q = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = i / tw, x = i - y * tw;
+    const double v = (double)img[(size_t)(y0 + y) * W + x0 + x];
+    s += v;
+    q += v * v;
+  }
+  __shared__ double sh[2][8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    q += __shfl_xor_sync(0xffffffffu, q, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s;
+    sh[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int k = 0; k < 8; ++k) a += sh[threadIdx.x][k];
+    atomicAdd(stats + 2 * t + threadIdx.x, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tile_gather_standardize_kernel(const float* __restrict__ img, int W, const int* __restrict__ rois, int th, int tw,
+                               const double* __restrict__ stats, float* __restrict__ out) {
+  const int t = blockIdx.y;
+  const int y0 = rois[4 * t], x0 = rois[4 * t + 1];
+  const int n = th * tw;
+  const double mean = stats[2 * t] / n;
+  double var = stats[2 * t + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float m = (float)mean, inv = 1.0f / ((float)sqrt(var) + 1e-7f);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = i / tw, x = i - y * tw;
+    out[(size_t)t * n + i] = (img[(size_t)(y0 + y) * W + x0 + x] - m) * inv;
+  }
+}
+
+// inner: int32 [T][4] = (y0, x0, h, w) in IMAGE coordinates; outer origin from rois
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(const float* __restrict__ pred, int th, int tw, const int* __restrict__ rois,
+                    const int* __restrict__ inner, float* __restrict__ out, int W) {
+  const int t = blockIdx.y;
+  const int oy = rois[4 * t], ox = rois[4 * t + 1];
+  const int iy = inner[4 * t], ix = inner[4 * t + 1], ih = inner[4 * t + 2], iw = inner[4 * t + 3];
+  const int n = ih * iw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = i / iw, x = i - y * iw;
+    out[(size_t)(iy + y) * W + ix + x] = pred[((size_t)t * th + (iy - oy + y)) * tw + (ix - ox + x)];
+  }
+}
+
 static inline int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g < 1) g = 1;
@@ -536,6 +604,31 @@ int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, vo
   // the reference multiplies by the python doubles m and (1. - m), each rounded to fp32 by ATen
   PDA_COUNT(1);
   ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, (float)momentum, (float)(1.0 - momentum));
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_tile_gather_standardize(const float* image, int H, int W, const int32_t* rois, int T, int th, int tw,
+                                double* stats, float* out, void* stream) {
+  if (!image || !rois || !stats || !out) return PDA_ERR_ARG;
+  if (T <= 0 || th <= 0 || tw <= 0 || th > H || tw > W || T > 65535) return PDA_ERR_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * T, st) != cudaSuccess) return PDA_ERR_CUDA;
+  int gx = (th * tw + 256 * 8 - 1) / (256 * 8);
+  if (gx > 64) gx = 64;
+  PDA_COUNT(2);
+  tile_stats_kernel<<<dim3(gx, T), 256, 0, st>>>(image, W, rois, th, tw, stats);
+  tile_gather_standardize_kernel<<<dim3(gx, T), 256, 0, st>>>(image, W, rois, th, tw, stats, out);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+int pda_tile_scatter(const float* pred, int T, int th, int tw, const int32_t* rois, const int32_t* inner, float* out,
+                     int H, int W, void* stream) {
+  if (!pred || !rois || !inner || !out) return PDA_ERR_ARG;
+  if (T <= 0 || th <= 0 || tw <= 0 || T > 65535 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
+  int gx = (th * tw + 256 * 8 - 1) / (256 * 8);
+  if (gx > 64) gx = 64;
+  PDA_COUNT(1);
+  tile_scatter_kernel<<<dim3(gx, T), 256, 0, (cudaStream_t)stream>>>(pred, th, tw, rois, inner, out, W);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 

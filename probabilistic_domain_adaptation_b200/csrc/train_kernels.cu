@@ -762,6 +762,56 @@ adam_kernel(const long long* __restrict__ table, float lr, float beta2, float om
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Validation metric (my_utils/util.py:17-44, called at punet_trainer.py:78-81): dice = 2 sum(gt * seg) /
+// (sum(gt) + sum(seg) + 1e-7), optional thresholds (NaN = none: soft dice of the MC mean).  fp64 partial sums.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dice_partial_kernel(const float* __restrict__ seg, const float* __restrict__ gt, long long n, float thr_seg,
+                    float thr_gt, double* __restrict__ partial) {
+  const bool ts = thr_seg == thr_seg, tg = thr_gt == thr_gt;  // NaN -> no threshold
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = seg[i], b = gt[i];
+    if (ts) a = a > thr_seg ? 1.f : 0.f;
+    if (tg) b = b > thr_gt ? 1.f : 0.f;
+    s0 += (double)(a * b);
+    s1 += (double)b;
+    s2 += (double)a;
+  }
+  __shared__ double sh[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane == 0) {
+    sh[0][warp] = s0;
+    sh[1][warp] = s1;
+    sh[2][warp] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += sh[threadIdx.x][k];
+    partial[blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void dice_final_kernel(const double* __restrict__ partial, int nblocks, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nblocks; ++k) {
+    s0 += partial[3 * k];
+    s1 += partial[3 * k + 1];
+    s2 += partial[3 * k + 2];
+  }
+  out[0] = (float)(2.0 * s0 / (s1 + s2 + 1e-7));
+}
+
 }  // namespace pda
 
 using namespace pda;
@@ -973,6 +1023,17 @@ int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double 
   adam_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), (float)lr, (float)beta2,
                                                 (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)bc1,
                                                 (float)sqrt(bc2), inv_scale, found_inf);
+  return LAUNCH_OK();
+}
+
+int pda_dice_score(const float* seg, const float* gt, long long n, float thr_seg, float thr_gt, double* partial,
+                   float* out, void* stream) {
+  if (!seg || !gt || !partial || !out) return PDA_ERR_ARG;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  const int blocks = pda_recon_loss_blocks(n);
+  PDA_COUNT(2);
+  dice_partial_kernel<<<blocks, 256, 0, ST(stream)>>>(seg, gt, n, thr_seg, thr_gt, partial);
+  dice_final_kernel<<<1, 32, 0, ST(stream)>>>(partial, blocks, out);
   return LAUNCH_OK();
 }
 

@@ -407,3 +407,19 @@ def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit, precision="bf16"):
                                db3.data_ptr(), dz.data_ptr(), scratch.data_ptr(), _stream())
     _lib.check(rc, "fcomb_bwd")
     return dfeat, dw1, db1, dw2, db2, dw3, db3, dz
+
+
+def dice_score(seg, gt, threshold_seg=None, threshold_gt=None):
+    """my_utils/util.py:17-44 on the device: fp32 tensors of equal shape -> 0-dim fp32 tensor (no host sync)."""
+    _need_cuda(seg, gt)
+    lib = _lib.load()
+    assert seg.shape == gt.shape, f"{seg.shape}, {gt.shape}"
+    seg, gt = seg.contiguous().float(), gt.contiguous().float()
+    n = seg.numel()
+    partial = torch.empty(3 * lib.pda_recon_loss_blocks(n), dtype=torch.float64, device=seg.device)
+    out = torch.empty(1, dtype=torch.float32, device=seg.device)
+    nan = float("nan")
+    _lib.check(lib.pda_dice_score(seg.data_ptr(), gt.data_ptr(), n, nan if threshold_seg is None else threshold_seg,
+                                  nan if threshold_gt is None else threshold_gt, partial.data_ptr(), out.data_ptr(),
+                                  _stream()), "dice_score")
+    return out[0]

@@ -65,6 +65,23 @@ def mean_teacher_step(model, teacher, optimizer, ema, x1, x2, n_samples=16, do_c
     return loss, y, z
 
 
+@torch.no_grad()
+def validation_step(model, x, y, n_samples=8):
+    """Per-batch body of PUNetTrainer._validate_impl (punet_trainer.py:62-86): forward(training=True) + ELBO + L2,
+    mean of n_samples sigmoid(sample(testing=False)), dice_score(mean, gt).  Returns (loss, dice, 1 - dice) as 0-dim
+    DEVICE tensors: the reference copies the full-resolution prediction to the host for every validation batch; here
+    nothing synchronises until the caller reads the three scalars."""
+    from . import ops
+    model.forward(x, y, training=True)
+    elbo = model.elbo(y)
+    reg_loss = l2_regularisation(model.posterior) + l2_regularisation(model.prior) + \
+        l2_regularisation(model.fcomb.layers)
+    loss = -elbo + 1e-5 * reg_loss
+    pred = consensus.sample_from_model(model, n_samples)
+    dice = ops.dice_score(pred, y)
+    return loss, dice, 1.0 - dice
+
+
 def distribution_alignment(y, source_distribution):
     """fixmatch_trainer.py:77-84 (tiny: B x H x W compare / unique on the pseudo-label; stays in torch)."""
     y_binary = torch.where(y >= 0.5, 1, 0)

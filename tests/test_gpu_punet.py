@@ -198,3 +198,45 @@ def test_host_predictor_pipeline_matches_direct_call():
     for x, (om, oc) in zip(batches, outs):
         mean, mask = consensus.sample_from_teacher(m, x.to(dev), 16, do_consensus_masking=True, eps=eps)
         assert torch.equal(om, mean.cpu()) and torch.equal(oc, mask.cpu())
+
+
+def test_tiled_prediction_matches_host_blocking():
+    """Device tiled prediction (batched gather + standardise, MC mean, scatter) vs the numpy restatement of
+    predict_with_halo driving the SAME device model one block at a time (isolates the driver), and vs the CPU oracle
+    model on one block (end to end)."""
+    from oracle import tiled_oracle
+    from probabilistic_domain_adaptation_b200 import consensus, tiled
+    dev = _dev()
+    m = _model(8.0)
+    g = torch.Generator().manual_seed(3)
+    image = (torch.randn(200, 264, generator=g) * 37.0 + 120.0)
+    eps = torch.randn(8, 1, 6, generator=g)
+    bs, halo = (64, 96), (16, 24)
+
+    def eps_fn(chunk):  # same latent draws for every block
+        return eps.expand(8, len(chunk), 6).contiguous().to(dev)
+
+    out = tiled.predict_with_halo(image, m, prior_samples=8, block_shape=bs, halo=halo, batch_tiles=3, eps_fn=eps_fn)
+
+    def predict_fn(tile):
+        t = torch.from_numpy(tile)[None, None].to(dev)
+        return consensus.punet_mc_prediction(m, t, 8, eps=eps.to(dev)).cpu().numpy()[0, 0]
+
+    ref = tiled_oracle.predict_with_halo(image.numpy(), predict_fn, bs, halo)
+    err = float((out.cpu() - torch.from_numpy(ref)).abs().max())
+    # per-block statistics in fp64 on the device vs numpy fp32: the standardised inputs differ by ~1e-6, which the bf16
+    # layers turn into rounding flips -- compare at the bf16 tolerance (1e-2 on unit-gain logits, last-layer gain 8)
+    assert err < 2e-2, err
+    assert float((out.cpu() - torch.from_numpy(ref)).abs().mean()) < 1e-3
+    # sharding: two ranks fill disjoint blocks whose sum is the full image
+    o0 = tiled.predict_with_halo(image, m, 8, bs, halo, 3, rank=0, world=2, eps_fn=eps_fn)
+    o1 = tiled.predict_with_halo(image, m, 8, bs, halo, 3, rank=1, world=2, eps_fn=eps_fn)
+    assert torch.equal(o0 + o1, out) and float((o0 * o1).abs().max()) == 0.0
+    # end to end against the CPU oracle model on the first block
+    sd = po.make_state_dict(0, last_layer_gain=8.0)
+    (oy, ox, oh, ow), (iy, ix, ih, iw) = tiled.blocking(image.shape, bs, halo)[0]
+    tile = torch.from_numpy(tiled_oracle.standardize(image.numpy()[oy:oy + oh, ox:ox + ow]))[None, None]
+    with torch.no_grad():
+        logits, _, _, _ = po.mc_logits(sd, tile, eps)
+    y = torch.sigmoid(logits).mean(0)[0, 0]
+    assert float((out.cpu()[iy:iy + ih, ix:ix + iw] - y[iy - oy:iy - oy + ih, ix - ox:ix - ox + iw]).abs().max()) < 0.05

@@ -178,3 +178,28 @@ def test_trainer_mixins_override_reference_helpers():
     y, z = fm.sample_from_weak_model(x)
     assert z.dtype == torch.float32 and y.shape == (1, 1, 32, 32)
     assert fm.sample_from_model().shape == (1, 1, 32, 32)
+
+
+def test_dice_score_and_validation_step(golden):
+    """Device dice_score vs the reference-derived fixture (my_utils/util.py:17-44) and the validation-step body
+    (punet_trainer.py:62-86) vs the same arithmetic on the host."""
+    from probabilistic_domain_adaptation_b200 import consensus, ops, steps
+    dev = _dev()
+    g = golden("dice_score")
+    for (ts, tg), ref in g["cases"].items():
+        mine = ops.dice_score(g["seg"].to(dev), g["gt"].to(dev), ts, tg).item()
+        assert abs(mine - ref) < 1e-6 * max(1.0, abs(ref)), ((ts, tg), mine, ref)
+    model = _model(rl_swap=True).eval()
+    x, y, _, _ = po.synthetic_inputs(2, 32, 48)
+    torch.manual_seed(11)
+    loss, dice, metric = steps.validation_step(model, x.to(dev), y.to(dev), n_samples=8)
+    assert loss.dim() == 0 and dice.dim() == 0 and torch.isfinite(loss)
+    # same RNG stream -> same prediction -> same dice through the numpy reference arithmetic
+    model.forward(x.to(dev), y.to(dev), training=True)
+    model.elbo(y.to(dev))
+    torch.manual_seed(11)
+    model.forward(x.to(dev), y.to(dev), training=True)
+    _ = model.posterior_latent_space.rsample()  # elbo() draws one posterior sample before the prior samples
+    pred = consensus.sample_from_model(model, 8)
+    ref = po.dice_score(pred.cpu().numpy().squeeze(), y.numpy().squeeze())
+    assert abs(dice.item() - ref) < 1e-5 and abs(metric.item() - (1.0 - ref)) < 1e-5

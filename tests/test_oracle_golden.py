@@ -93,3 +93,9 @@ def test_analytic_known_answers():
     y, z = po.consensus_from_probs(p[[0, 1, 3, 4]], do_consensus_masking=True)
     assert z.item() == 1 and z.dtype == torch.int64
     assert po.adamt_momentum(0) == 0.0 and po.adamt_momentum(10 ** 6) == 0.999
+
+
+def test_dice_score_matches_reference(golden):
+    g = golden("dice_score")
+    for (ts, tg), ref in g["cases"].items():
+        assert po.dice_score(g["seg"].numpy(), g["gt"].numpy(), ts, tg) == ref
