@@ -455,6 +455,13 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # DRAM traffic per launch from the ncu capture of this exact workload (profiles/r01c_conv_dram_traffic.md):
+    # 31 conv launches move 15.16 GB per step against 16.55 GB algorithmic (activations in + out + weights; the L2
+    # absorbs part of the weight / bridge re-reads), the fcomb launch 579 MB against 587 MB.
+    default_wl = (T, HW, S) == (4, 1024, 16)
+    conv_traffic = 489.2e6 if default_wl else None
+    conv_traffic_alg = 533.8e6 if default_wl else None
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         csize = min(HW, 512)
@@ -478,11 +485,15 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, all layers)",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": conv_traffic,
+                     "traffic_algorithmic": conv_traffic_alg,
+                     "traffic_source": "profiles/r01c_conv_dram_traffic.md (ncu dram__bytes_read+write, mean per launch)",
                      "launches": n_conv, "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms},
         "roofline_fcomb": {"bound": "hbm (north star) / tensor + CUDA-core epilogue (actual)", "achieved": fc_gbs, "peak": hbm_peak,
                            "unit": "GB/s", "frac": fc_gbs / hbm_peak, "algorithmic_bytes_per_px": 140,
+                           "traffic": 579.2e6 if default_wl else None,
+                           "tensor_frac": fc_tf / tf_peak,
                            "achieved_tflops": fc_tf, "kernel_ms_per_step": fc_ms / args.steps,
                            "share_of_step": fc_ms / ms},
         "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,

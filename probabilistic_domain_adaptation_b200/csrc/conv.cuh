@@ -51,6 +51,16 @@ static inline int c8_shift(int C) {
 }
 
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember, per device, the largest value already
+// requested for one kernel (state: zero-initialised int[64]).  Returns true when the attribute must be (re)set.
+static inline bool dyn_smem_attr_needed(int* state, int bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (state[dev] >= bytes) return false;
+  state[dev] = bytes;
+  return true;
+}
+
 // Launch shape of the row-decomposed NHWC elementwise kernels: x = 256-thread blocks across one row's (x, chunk)
 // elements, y = blocks striding over the rows, sized to ~`target` blocks in total.
 static inline dim3 row_grid(long long row_elems, long long rows, int target = 148 * 8) {

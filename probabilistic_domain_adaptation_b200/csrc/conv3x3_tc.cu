@@ -410,12 +410,11 @@ template <int BN, int MT, bool RES>
 static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                        const ConvArgs& args, cudaStream_t stream) {
   using L = ConvCfg<BN, MT, RES>;
-  static bool configured = false;
-  if (!configured) {
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, L::DYN_BYTES)) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MT, RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return PDA_ERR_CUDA;
-    configured = true;
   }
   const long long units = (long long)args.tiles_x * args.tiles_y * args.B * (args.cout / BN);
   if (units > 0x7fffffffLL) return PDA_ERR_SHAPE;

@@ -424,12 +424,11 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
     return PDA_ERR_TENSORMAP;
   if (cudaMemcpyToSymbolAsync(c_fb_w3, w3, sizeof(float) * FB_C, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return PDA_ERR_CUDA;
-  static bool configured = false;
-  if (!configured) {
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, FbSmem::DYN_BYTES)) {
     if (cudaFuncSetAttribute(fcomb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::DYN_BYTES) !=
         cudaSuccess)
       return PDA_ERR_CUDA;
-    configured = true;
   }
   const int tiles_per_img = (P + 127) / 128;
   const long long num_tiles = (long long)tiles_per_img * B;

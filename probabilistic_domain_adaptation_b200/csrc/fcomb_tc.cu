@@ -401,11 +401,10 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
       cudaMemcpyToSymbolAsync(c_fcomb_w3, b3, sizeof(float), sizeof(float) * FCT, cudaMemcpyDeviceToDevice, st) !=
           cudaSuccess)
     return PDA_ERR_CUDA;
-  static int configured = 0;
-  if (smem > configured) {
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, smem)) {
     if (cudaFuncSetAttribute(fcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return PDA_ERR_CUDA;
-    configured = smem;
   }
   const int tiles_per_img = (P + FC_TILE - 1) / FC_TILE;
   const long long num_tiles = (long long)tiles_per_img * B;

@@ -994,11 +994,10 @@ int pda_fcomb_bwd_fp32(const void* feat, const float* z, const float* w1, const 
   if (cudaMemsetAsync(dw3, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
   if (cudaMemsetAsync(db3, 0, sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
   const int smem = sizeof(float) * (2 * FB * FB + 4 * 128 * FB_LD + 320);
-  static bool configured = false;
-  if (!configured) {
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, smem)) {
     if (cudaFuncSetAttribute(fcomb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return PDA_ERR_CUDA;
-    configured = true;
   }
   const int tiles_per_img = (P + 127) / 128;
   const long long num_tiles = (long long)tiles_per_img * B;

@@ -315,12 +315,11 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 8, 16, 64);
   if (r) return r;
   if (cudaMemsetAsync(scratch, 0, sizeof(float) * 9ull * cout * ctot, stream) != cudaSuccess) return PDA_ERR_CUDA;
-  static bool configured = false;
-  if (!configured) {
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, WgradSmem::DYN_BYTES)) {
     if (cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              WgradSmem::DYN_BYTES) != cudaSuccess)
       return PDA_ERR_CUDA;
-    configured = true;
   }
   const long long steps = (long long)a.items * a.num_tiles;
   const int grid = (int)(steps < 148 ? steps : 148);
