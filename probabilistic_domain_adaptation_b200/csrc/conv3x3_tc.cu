@@ -35,7 +35,7 @@ struct ConvCfg {
   static constexpr int A_BYTES = SLAB_ROWS * 1024;     // one slab: SLAB_ROWS x (8 px x 128 B)
   static constexpr int B_BYTES = BN * 128;             // one (tap, chunk) weight tile
   static constexpr int A_STAGES = 3;
-  static constexpr int B_STAGES = RES ? 9 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6);
+  static constexpr int B_STAGES = RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6));
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
   static constexpr int STG_OFF = B_OFF + B_STAGES * B_BYTES;   // 8 epilogue warps x 4 KB output staging
@@ -430,9 +430,13 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
     return PDA_ERR_SHAPE;
   if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
-  int bn = (bn_override == 64 || bn_override == 128) ? bn_override : ((cout % 128 == 0) ? 128 : 64);
+  // N = 256 halves the shared-memory bytes per MAC of the B operand (N = 128 tiles sit exactly at the 128 B/clk
+  // shared-memory port limit); its 2 x 256 accumulator columns leave room for one M-tile per unit only
+  int bn = (bn_override == 64 || bn_override == 128 || bn_override == 256)
+               ? bn_override
+               : ((cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : 64);
   if (cout % bn) return PDA_ERR_SHAPE;
-  const int mt = (H > 16) ? 2 : 1;
+  const int mt = (H > 16 && bn != 256) ? 2 : 1;
   ConvArgs a;
   a.B = B; a.H = H; a.W = W; a.c0 = c0; a.c1 = c1; a.cout = cout; a.relu = relu;
   a.tile_w = 8;
@@ -465,6 +469,7 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
     return resident ? launch_conv<64, 2, true>(tA0, tA1, tB, tO, a, stream)
                     : launch_conv<64, 2, false>(tA0, tA1, tB, tO, a, stream);
   }
+  if (bn == 256) return launch_conv<256, 1, false>(tA0, tA1, tB, tO, a, stream);
   if (bn == 128) return launch_conv<128, 1, false>(tA0, tA1, tB, tO, a, stream);
   return launch_conv<64, 1, false>(tA0, tA1, tB, tO, a, stream);
 }

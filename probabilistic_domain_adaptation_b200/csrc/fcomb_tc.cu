@@ -415,13 +415,27 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   if (per_sm < 1) return PDA_ERR_SHAPE;
   if (per_sm > 2) per_sm = 2;
   const int grid = (int)(num_tiles < 148 * per_sm ? num_tiles : 148 * per_sm);
-  float* bz = nullptr;
-  if (cudaMallocAsync(&bz, sizeof(float) * (size_t)S * B * FCT, st) != cudaSuccess) return PDA_ERR_CUDA;
+  // per-device grow-only scratch for bz[S][B][64] (no allocator call on the hot path; like the constant-bank copy of
+  // w3 it is shared by all launches of this process on the device: launches on different streams must not overlap)
+  static float* bz_buf[64];
+  static size_t bz_cap[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
+  const size_t need = sizeof(float) * (size_t)S * B * FCT;
+  if (bz_cap[dev] < need) {
+    if (bz_buf[dev]) cudaFree(bz_buf[dev]);
+    const size_t cap = need < (1u << 20) ? (1u << 20) : need;
+    if (cudaMalloc(&bz_buf[dev], cap) != cudaSuccess) {
+      bz_buf[dev] = nullptr;
+      bz_cap[dev] = 0;
+      return PDA_ERR_CUDA;
+    }
+    bz_cap[dev] = cap;
+  }
+  float* bz = bz_buf[dev];
   PDA_COUNT(2);
   fcomb_bz_kernel<<<(S * B * FCT + 255) / 256, 256, 0, st>>>(z, w1, b1, bz, S * B, latent);
   fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, P, S, latent, B, tiles_per_img, (int)num_tiles,
                                                   upper, lower, mean_prob, cons_weight, cons_mask, logits, probs);
-  const cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(bz, st);
-  return e == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
