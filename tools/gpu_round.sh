@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU visit: parity tests, smoke, bench line (optionally ncu with NCU=1)
 mkdir -p gpurun_out
-for f in tests/test_gpu_conv.py tests/test_gpu_punet.py tests/test_gpu_train.py; do
+for f in tests/test_gpu_conv.py tests/test_gpu_punet.py tests/test_gpu_train.py tests/test_gpu_steps.py; do
   echo "=== $f"
   timeout 240 python -m pytest $f -m gpu -q --timeout 60 -p no:cacheprovider -s -x 2>&1 | tail -${TAIL:-30}
 done
