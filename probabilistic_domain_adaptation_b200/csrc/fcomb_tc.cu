@@ -45,8 +45,9 @@ struct FcombSmem {
   static constexpr int BAR_OFF = AX_OFF + 1024;
   static constexpr int NBARS = 4 + 2 * FC_A1_STAGES + 4;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
-  static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[S][64] fp32
-  static int bytes(int S) { return BZ_OFF + S * FCT * 4 + 1024; }
+  static constexpr int BZ_CHUNK = 16;                           // samples whose layer-1 bias is staged at a time
+  static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[BZ_CHUNK][64] fp32
+  static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 4 + 1024; }
 };
 
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -173,19 +174,24 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const int sw = tid & 7;
     uint32_t a_it = 0, t_it = 0;
-    int cur_b = -1;
+    int cur_b = -1, cur_chunk = -1;
+    // stages bz[s0 .. s0 + BZ_CHUNK) of image b (S <= BZ_CHUNK: once per image; else once per chunk of samples)
+    auto stage_bz = [&](int b, int chunk) {
+      named_bar_sync(1, 128);  // every producer is done with the previous contents
+      const int s0 = chunk * M::BZ_CHUNK;
+      const int ns = min(M::BZ_CHUNK, S - s0);
+      for (int i = tid; i < ns * (FCT / 4); i += 128) {
+        const int s = i / (FCT / 4), j4 = i - s * (FCT / 4);
+        reinterpret_cast<float4*>(bzs)[i] =
+            __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s0 + s) * B + b) * FCT) + j4);
+      }
+      named_bar_sync(1, 128);
+      cur_b = b;
+      cur_chunk = chunk;
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img;
-      if (b != cur_b) {
-        named_bar_sync(1, 128);  // every producer is done with the previous image's bz
-        for (int i = tid; i < S * (FCT / 4); i += 128) {
-          const int s = i / (FCT / 4), j4 = i - s * (FCT / 4);
-          reinterpret_cast<float4*>(bzs)[i] =
-              __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s) * B + b) * FCT) + j4);
-        }
-        named_bar_sync(1, 128);
-        cur_b = b;
-      }
+      if (b != cur_b || cur_chunk != 0) stage_bz(b, 0);
       // ---- H1 -> registers (kept for all samples), as packed f32x2
       mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
@@ -205,10 +211,11 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       __syncwarp();
       if (lane == 0) mbar_arrive(h1_empty);
       for (int s = 0; s < S; ++s, ++a_it) {
+        if (s / M::BZ_CHUNK != cur_chunk) stage_bz(b, s / M::BZ_CHUNK);
         const uint32_t slot = a_it % FC_A1_STAGES;
         mbar_wait(a1_empty(slot), ((a_it / FC_A1_STAGES) & 1) ^ 1);
         // A1_s = relu(H1 + bz_s) as fp16, this thread's 128-byte row, 16-byte chunks XOR-swizzled by (row & 7)
-        const float4* bz4 = reinterpret_cast<const float4*>(bzs + s * FCT);
+        const float4* bz4 = reinterpret_cast<const float4*>(bzs + (s % M::BZ_CHUNK) * FCT);
         uint8_t* row = smem + M::A1_OFF + slot * M::A_BYTES + tid * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -383,7 +390,6 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) return PDA_ERR_ARG;
   if (B <= 0 || P <= 0 || S <= 0 || latent <= 0) return PDA_ERR_SHAPE;
   const int smem = FcombSmem::bytes(S);
-  if (smem > 220 * 1024) return PDA_ERR_SHAPE;
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   if (!enc) return PDA_ERR_DRIVER;
   CUtensorMap tm;
