@@ -6,7 +6,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libpda_b200.so")
+LIB_PATH = os.environ.get("PDA_B200_LIB") or os.path.join(PKG, "libpda_b200.so")  # override: A/B experiments only
 
 _c = ctypes
 _P = _c.c_void_p

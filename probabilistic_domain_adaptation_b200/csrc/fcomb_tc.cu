@@ -6,15 +6,20 @@
 // The kernel is COMPUTE bound (~1000 FLOP/B at S=16), so the two 64x64 layers run on tcgen05:
 //   per 128-pixel tile:  H1 = F . (W1f_hi + W1f_lo)^T         128x64x64 MMA x2 (bf16 hi/lo split of the fp32 weights
 //                                                            -> ~16-bit mantissa), accumulator in TMEM, read ONCE
-//   per sample s:        A1_s = relu(H1 + bz_s) -> fp16 (saturating) -> swizzled smem operand   (producer warps)
-//                        H2_s = [A1_s | 1 1 0..] . [W2 | b2_hi b2_lo 0..]^T   128x64x80 fp16 MMA (bias folded in)
+//   per sample s:        A1_s = relu(H1 + bz_s) in packed fp16 (H1 and bz_s rounded to fp16 once; one HFMA2.RELU per
+//                        two channels) -> tcgen05.st -> TMEM: the A operand of the next MMA never touches shared
+//                        memory (no swizzled stores, no generic->async proxy fence)              (producer warps)
+//                        H2_s = [A1_s | 1 1 0..] . [W2 | b2_hi b2_lo 0..]^T   128x64x80 fp16 MMA, A from TMEM for the
+//                        first 64 k, the bias block (ones) from shared memory
 //                        logit = w3 . relu(H2_s) + b3 ; p = sigmoid ; mean / consensus        (epilogue warps)
 // bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat (fcomb_bz_kernel).
 //
 // Warp-specialised persistent CTA (2 per SM): warps 0-3 = producers (own H1 in registers, write the A1 ring),
 // warps 4-7 = epilogue (TMEM -> relu -> w3 dot with w3 as constant-bank operands -> sigmoid / counters),
-// warp 8 = control (TMA of the feature tile, all tcgen05.mma).  Three mbarrier pipelines (F tile, A1 ring of 3,
-// H2 accumulator ring of 2 in TMEM) let the three roles run concurrently; nothing but the outputs leaves the SM.
+// warp 8 = control (TMA of the feature tile, all tcgen05.mma).  Three mbarrier pipelines (F tile, A1 ring of 2 and
+// H2 accumulator ring of 2, both in TMEM) let the three roles run concurrently; nothing but the outputs leaves the SM.
+// Measured (profiles/r01e_fcomb_variants.md): 1.62 ms -> 0.99 ms at 4 x 1024^2 px, S = 16 against the version that
+// staged A1 in shared memory with fp32 adds; the kernel is now issue-bound (67 % of the issue slots).
 #include <cuda_fp16.h>
 
 #include "conv.cuh"
@@ -24,8 +29,9 @@ namespace pda {
 
 constexpr int FCT = 64;             // feature / hidden channels
 constexpr int FC_TILE = 128;        // pixels per tile == TMEM lanes
-constexpr int FC_TMEM_COLS = 256;   // [0,64): H1; [64,128), [128,192): H2 ring
-constexpr int FC_A1_STAGES = 3;
+constexpr int FC_TMEM_COLS = 256;   // [0,64): H1; [64,128), [128,192): H2 ring; [192,224), [224,256): A1 ring (fp16 x2)
+constexpr int FC_A1_STAGES = 2;
+constexpr int FC_A1_COL = 3 * FCT;
 constexpr int FC_THREADS = 288;
 
 // last Fcomb layer as constant-bank operands of the epilogue FFMAs: w3[64], b3.  Refreshed (stream-ordered D2D copy)
@@ -36,8 +42,7 @@ struct FcombSmem {
   static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 x 2 B
   static constexpr int W_BYTES = FCT * 128;                     // 64 rows x 64 x 2 B
   static constexpr int F_OFF = 0;                               // feature tile (TMA)
-  static constexpr int A1_OFF = A_BYTES;                        // A1 ring
-  static constexpr int W1_OFF = A1_OFF + FC_A1_STAGES * A_BYTES;  // bf16 hi part of W1[:, :64]
+  static constexpr int W1_OFF = A_BYTES;                        // bf16 hi part of W1[:, :64]
   static constexpr int W1L_OFF = W1_OFF + W_BYTES;              // bf16 lo part (w - hi)
   static constexpr int W2_OFF = W1L_OFF + W_BYTES;              // fp16 W2
   static constexpr int W2X_OFF = W2_OFF + W_BYTES;              // fp16 K-extension: col 0 = b2_hi, col 1 = b2_lo
@@ -45,34 +50,49 @@ struct FcombSmem {
   static constexpr int BAR_OFF = AX_OFF + 1024;
   static constexpr int NBARS = 4 + 2 * FC_A1_STAGES + 4;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
-  static constexpr int BZ_CHUNK = 16;                           // samples whose layer-1 bias is staged at a time
-  static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[BZ_CHUNK][64] fp32
-  static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 4 + 1024; }
+  static constexpr int BZ_CHUNK = 64;                           // samples whose layer-1 bias is staged at a time
+  static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[BZ_CHUNK][64] fp16
+  static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 2 + 1024; }
 };
 
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// {hi, lo} -> f16x2 with ReLU, saturating to the largest finite fp16 (lo in the low half)
-__device__ __forceinline__ uint32_t relu_pack_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// relu(a + c) on packed halves in one instruction (fma.relu with b = 1.0)
+__device__ __forceinline__ uint32_t add_relu_f16x2(uint32_t a, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0x3C003C00u), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16: the A operand (128 rows = lanes, K 16-bit elements packed two per
+// 32-bit column, i.e. 8 columns per K = 16 step) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -172,7 +192,6 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   if (warp < 4) {
     // ================================================================ producers
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const int sw = tid & 7;
     uint32_t a_it = 0, t_it = 0;
     int cur_b = -1, cur_chunk = -1;
     // stages bz[s0 .. s0 + BZ_CHUNK) of image b (S <= BZ_CHUNK: once per image; else once per chunk of samples)
@@ -182,8 +201,8 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       const int ns = min(M::BZ_CHUNK, S - s0);
       for (int i = tid; i < ns * (FCT / 4); i += 128) {
         const int s = i / (FCT / 4), j4 = i - s * (FCT / 4);
-        reinterpret_cast<float4*>(bzs)[i] =
-            __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s0 + s) * B + b) * FCT) + j4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s0 + s) * B + b) * FCT) + j4);
+        reinterpret_cast<uint2*>(bzs)[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
       }
       named_bar_sync(1, 128);
       cur_b = b;
@@ -192,20 +211,18 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img;
       if (b != cur_b || cur_chunk != 0) stage_bz(b, 0);
-      // ---- H1 -> registers (kept for all samples), as packed f32x2
+      // ---- H1 -> registers (kept for all samples) as 32 packed f16x2 (saturating)
       mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
-      uint64_t h1[FCT / 2];
-      {
+      uint32_t h1[FCT / 2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld32(lane_addr, v);
+        tmem_ld32(lane_addr + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h1[i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
-        tmem_ld32(lane_addr + 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) h1[16 + i] = (static_cast<uint64_t>(v[2 * i + 1]) << 32) | v[2 * i];
+        for (int i = 0; i < 16; ++i)
+          h1[16 * half + i] = pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
       tc_fence_before();
       __syncwarp();
@@ -213,26 +230,22 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       for (int s = 0; s < S; ++s, ++a_it) {
         if (s / M::BZ_CHUNK != cur_chunk) stage_bz(b, s / M::BZ_CHUNK);
         const uint32_t slot = a_it % FC_A1_STAGES;
-        mbar_wait(a1_empty(slot), ((a_it / FC_A1_STAGES) & 1) ^ 1);
-        // A1_s = relu(H1 + bz_s) as fp16, this thread's 128-byte row, 16-byte chunks XOR-swizzled by (row & 7)
-        const float4* bz4 = reinterpret_cast<const float4*>(bzs + (s % M::BZ_CHUNK) * FCT);
-        uint8_t* row = smem + M::A1_OFF + slot * M::A_BYTES + tid * 128;
+        mbar_wait(a1_empty(slot), ((a_it / FC_A1_STAGES) & 1) ^ 1);  // the MMA that read this slot has completed
+        tc_fence_after();
+        // A1_s = relu(H1 + bz_s): this thread's row of 64 halves = 32 TMEM columns of its lane
+        const uint32_t bz_addr = sbase + M::BZ_OFF + (s % M::BZ_CHUNK) * FCT * 2;
+        uint32_t a[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 ba = bz4[2 * c], bb = bz4[2 * c + 1];
-          float x0, x1, x2, x3, x4, x5, x6, x7;
-          unpack_f32x2(add_f32x2(h1[4 * c + 0], pack_f32x2(ba.x, ba.y)), x0, x1);
-          unpack_f32x2(add_f32x2(h1[4 * c + 1], pack_f32x2(ba.z, ba.w)), x2, x3);
-          unpack_f32x2(add_f32x2(h1[4 * c + 2], pack_f32x2(bb.x, bb.y)), x4, x5);
-          unpack_f32x2(add_f32x2(h1[4 * c + 3], pack_f32x2(bb.z, bb.w)), x6, x7);
-          uint4 o;
-          o.x = relu_pack_f16x2(x0, x1);
-          o.y = relu_pack_f16x2(x2, x3);
-          o.z = relu_pack_f16x2(x4, x5);
-          o.w = relu_pack_f16x2(x6, x7);
-          *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = o;
+          const uint4 bb = lds128(bz_addr + 16 * c);
+          a[4 * c + 0] = add_relu_f16x2(h1[4 * c + 0], bb.x);
+          a[4 * c + 1] = add_relu_f16x2(h1[4 * c + 1], bb.y);
+          a[4 * c + 2] = add_relu_f16x2(h1[4 * c + 2], bb.z);
+          a[4 * c + 3] = add_relu_f16x2(h1[4 * c + 3], bb.w);
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+        tmem_st32(lane_addr + FC_A1_COL + slot * 32, a);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_full(slot));
       }
@@ -343,9 +356,9 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         tc_fence_after();
         if (leader) {
           const uint32_t d = tmem + FCT + hb * FCT;
-          const uint64_t da = umma_desc_k_sw128(sbase + M::A1_OFF + slot * M::A_BYTES);
+          const uint32_t ta = tmem + FC_A1_COL + slot * 32;  // K = 16 halves = 8 columns per MMA
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, da + 2 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_ts(d, ta + 8 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
           umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
           umma_commit(h2_full(hb));
           umma_commit(a1_empty(slot));

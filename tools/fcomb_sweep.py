@@ -12,7 +12,8 @@ w2 = (torch.randn(64, 64, 1, 1, generator=g) / 8).to(dev); b2 = torch.zeros(64, 
 w3 = (torch.randn(1, 64, 1, 1, generator=g)).to(dev); b3 = torch.zeros(1, device=dev)
 print("| S | ms | algorithmic GB/s (140 B/px) | % of 6540 GB/s | algorithmic TFLOP/s | % of 1380 TFLOP/s |")
 print("|---|---|---|---|---|---|")
-for S in (1, 2, 4, 8, 16, 32, 64):
+SS = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 8, 16, 32, 64]
+for S in SS:
     z = torch.randn(S, B, 6, generator=g).to(dev)
     f = lambda: ops.fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, want_weight=False, want_mask=True)
     for _ in range(3):
