@@ -444,6 +444,44 @@ def run_ours(args):
                                             f"per-block standardisation, host image -> device mean-probability image",
                                 "parallelism": f"blocks sharded x{world}"}}
 
+    # weak + strong views of one MitoEM-shape batch on the device (every transform applied: p = 1),
+    # HBM-bound: statistics pass 4 B/px + per view 4 B/px read + 4 B/px noise + 4 B/px write (noise generation by
+    # torch.randn_like is inside the timed region but not in the algorithmic bytes)
+    augment_res = None
+    if not args.no_extras:
+        from probabilistic_domain_adaptation_b200 import augment
+        raw_b = (torch.rand(args.train_batch, 1, args.train_size, args.train_size, generator=g) * 255).to(dev)
+        aug = augment.DualViewAugmenter(augment.weak_view(1.0), augment.mitoem_strong_view(1.0))
+        aug(raw_b)
+        nrep = max(5, args.steps)
+        ms_a, _, _, _ = timed(lambda: aug(raw_b), nrep)
+        px_a = raw_b.numel()
+        augment_res = {"metric": "dual_view_augment_img_per_s", "value": args.train_batch * world * nrep / (ms_a * 1e-3),
+                       "unit": "img/s", "ms_per_batch": ms_a / nrep,
+                       "roofline": {"bound": "hbm", "achieved": px_a * 28.0 * nrep / (ms_a * 1e-3) / 1e9,
+                                    "peak": load_peaks()[0], "unit": "GB/s", "algorithmic_bytes_per_px": 28},
+                       "config": {"workload": f"{args.train_batch}x1x{args.train_size}x{args.train_size}: statistics + "
+                                              "weak view (blur, noise) + strong view (blur, noise, contrast), all applied; "
+                                              "decisions sampled on the host per image inside the timed region"}}
+        # the training batch is 1 M px (29 MB): launch- and host-sampling-bound.  The kernels alone, on 64 images with
+        # pre-sampled decisions (statistics + two views), show the bandwidth they reach
+        big = (torch.rand(64, 1, args.train_size, args.train_size, generator=g) * 255).to(dev)
+        pw, _, kw = augment.sample_view_params(augment.weak_view(1.0), 64)
+        ps, _, ks = augment.sample_view_params(augment.mitoem_strong_view(1.0), 64)
+        pw, ps, nz = pw.to(dev), ps.to(dev), torch.randn_like(big)
+
+        def kernels_only():
+            st = augment.image_stats(big)
+            augment.augment_view(big, pw, kw, noise=nz, stats=st)
+            augment.augment_view(big, ps, ks, noise=nz, stats=st)
+        kernels_only()
+        ms_k, _, _, _ = timed(kernels_only, nrep)
+        augment_res["roofline"].update({"achieved": big.numel() * 28.0 * nrep / (ms_k * 1e-3) / 1e9,
+                                        "measured_on": f"64x1x{args.train_size}x{args.train_size}, decisions and noise "
+                                                       "pre-drawn (3 launches)", "ms": ms_k / nrep})
+        augment_res["roofline"]["frac"] = augment_res["roofline"]["achieved"] / augment_res["roofline"]["peak"]
+        del raw_b, big, nz
+
     train = None
     if args.mode in ("train", "both"):
         del x_dev, eps
@@ -500,6 +538,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "mc_sweep_px_samples_per_s": sweep,
         "tiled_prediction": tiled_res,
+        "augment": augment_res,
         "train": train,
     }
     print(json.dumps(line))

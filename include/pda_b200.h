@@ -121,6 +121,21 @@ int pda_tile_gather_standardize(const float* image, int H, int W, const int32_t*
 int pda_tile_scatter(const float* pred, int T, int th, int tw, const int32_t* rois, const int32_t* inner, float* out,
                      int H, int W, void* stream);
 
+/* On-device weak / strong view augmentation.  Replaces the per-sample CPU transforms that the
+ * DataLoader workers run: get_raw_transform(normalizer=my_standardize_torch, augmentation1=Compose([my_standardize_torch,
+ * RandomApply(GaussianBlur), RandomApply(AdditiveGaussianNoise), RandomApply(RandomContrast)]))
+ * (MitoEM/common.py:50-68, LIVECell/livecell_fm.py:43-67, livecell_adamatch.py:16-38, applied at
+ * prob_utils/my_datasets/my_image_collection_dataset.py:349-357; my_standardize_torch = prob_utils/my_utils/util.py:9-14).
+ * pda_image_stats: stats[b] = (sum, sum of squares) of image b (fp64), n = pixels per image; shared by all views.
+ * pda_augment_view: out[b] = contrast(noise(blur(standardize^k(img[b])))) in one kernel.  params: device float [B][8] =
+ *   (blur kernel size (odd, <= 31; <= 1: no blur), sigma, noise scale (0: none), contrast alpha (1: none), contrast mean,
+ *    k = number of standardisations (0..2), unused, unused) -- the random decisions, drawn on the host in the reference's
+ *   order.  noise: unit-normal field [B][H][W] or NULL.  Blur = torchvision GaussianBlur (reflect padding, separable).
+ *   max_ksize: the largest kernel size in `params` (validated against H, W on the host). */
+int pda_image_stats(const float* img, int B, long long n, double* stats, void* stream);
+int pda_augment_view(const float* img, const float* noise, float* out, int B, int H, int W, const double* stats,
+                     const float* params, float eps, int max_ksize, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Training (backward) entry points.  They replace what torch.autograd runs behind loss.backward() in the step
  * bodies punet_trainer.py:24-36 / mean_teacher_trainer.py:111-119 (cuDNN dgrad/wgrad, ATen elementwise backward).

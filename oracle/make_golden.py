@@ -158,9 +158,37 @@ def dice_case():
     print("dice_score", cases)
 
 
+def augment_case():
+    """Weak / strong views with the reference's own my_standardize_torch (prob_utils/my_utils/util.py:9-14, executed
+    from /root/reference), torchvision's RandomApply / GaussianBlur and the restated torch_em transforms."""
+    import importlib.util
+    from oracle import augment_oracle as ao
+    spec = importlib.util.spec_from_file_location(
+        "ref_util", os.path.join(ref_import.REFERENCE_ROOT, "prob_utils", "my_utils", "util.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    g = torch.Generator().manual_seed(11)
+    yy, xx = torch.meshgrid(torch.arange(72.0), torch.arange(104.0), indexing="ij")
+    base = torch.stack([100 + 60 * torch.sin(xx / (5 + 2 * i)) * torch.cos(yy / (9 - i)) for i in range(3)])[:, None]
+    raw = base + 25.0 * torch.rand(3, 1, 72, 104, generator=g)   # structured image + pixel noise, uint8-like range
+    cases = {}
+    for name, (wk, sk, seed) in {"scripts_seed5": (ao.WEAK, ao.STRONG, 5), "scripts_seed8": (ao.WEAK, ao.STRONG, 8),
+                                 "all_on_seed3": (ao.ALL_ON, ao.ALL_ON, 3)}.items():
+        v1, v2 = ao.dual_views(raw, wk, sk, seed, standardize=ref.my_standardize_torch)
+        cases[name] = {"weak_kw": wk, "strong_kw": sk, "seed": seed, "raw1": v1, "raw2": v2}
+        print("augment", name, float(v1.std()), float(v2.std()))
+    x = raw[0].clone()
+    torch.save({"desc": "dual views of a structured synthetic raw batch (3,1,72,104); my_standardize_torch = the reference's own function",
+                "raw": raw, "standardized0": ref.my_standardize_torch(x), "cases": cases},
+               os.path.join(GOLD, "augment.pt"))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-augment" in sys.argv:
+        return augment_case()
     dice_case()
+    augment_case()
     torch.set_num_threads(os.cpu_count())
     mc_case("mc_64x64_s16", 1, 64, 64, 16, 24.0)
     mc_case("mc_40x72_s4_b2", 2, 40, 72, 4, 24.0)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_tile_gather_standardize": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P],
     "pda_tile_scatter": [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P],
+    "pda_image_stats": [_P, _I, _c.c_longlong, _P, _P],
+    "pda_augment_view": [_P, _P, _P, _I, _I, _I, _P, _P, _F, _I, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -202,14 +202,31 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
       }
     }
   }
+  // block reduction.  With 8 channel groups (cout = 64) a warp holds 4 pixel lanes x 8 groups: fold the pixel lanes with
+  // two shuffles first, so that only 8 lanes per warp touch the shared accumulators (the 32-way conflicting shared
+  // atomics of the direct form cost ten times the accumulation loop itself).
+  const bool fold = (groups == 8);
+  const bool writer = !fold || (threadIdx.x & 31) < 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int co = g * 8 + j;
-    atomicAdd(&red[cout * CIN * 9 + co], accb[j]);
+    float v = accb[j];
+    if (fold) {
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+    }
+    if (writer) atomicAdd(&red[cout * CIN * 9 + co], v);
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(&red[(co * CIN + ci) * 9 + t], acc[ci][t][j]);
+      for (int t = 0; t < 9; ++t) {
+        float a = acc[ci][t][j];
+        if (fold) {
+          a += __shfl_xor_sync(0xffffffffu, a, 8);
+          a += __shfl_xor_sync(0xffffffffu, a, 16);
+        }
+        if (writer) atomicAdd(&red[(co * CIN + ci) * 9 + t], a);
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) atomicAdd(dw + i, red[i]);
