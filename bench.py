@@ -274,6 +274,35 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
                "ms_per_step": ms_src / nsrc,
                "config": {"workload": f"source ELBO step (Dice + KL + L2, Adam) on {Bs}x1x{HW}x{HW} per GPU "
                                       f"(BASELINE config 2, LIVECell shape)", "parallelism": f"dp{world}"}}
+    # BASELINE config 4: joint FixMatch ("AdaMatch", adamatch_trainer.py:62-102) with consensus weighting, data parallel:
+    # source ELBO + weak-view MC pseudo-labels (the model itself) + strong-view target ELBO, one backward, all-reduce, Adam
+    joint = None
+    if not args.no_extras:
+        joint = {}
+        for tag, (Bj, Hj) in {"livecell_2x256": (2, 256), "mitoem_4x512": (4, 512)}.items():
+            xs = torch.randn(Bj, 1, Hj, Hj, generator=g).to(dev)
+            ys = (torch.rand(Bj, 1, Hj, Hj, generator=g) > 0.5).float().to(dev)
+            xt = torch.randn(Bj, 1, Hj, Hj, generator=g)
+            xt1 = (xt + 0.1 * torch.randn(Bj, 1, Hj, Hj, generator=g)).to(dev)
+            xt2 = (xt + 0.25 * torch.randn(Bj, 1, Hj, Hj, generator=g)).to(dev)
+            epsj = torch.randn(S, Bj, 6, generator=torch.Generator().manual_seed(3)).to(dev)
+            # consensus WEIGHTING (--consensus without --masking, livecell_adamatch.py:122,150): the model keeps
+            # consensus_masking=True (= "use consm"), the trainer returns fp32 k/16 weights instead of the int64 mask
+            red3 = GradAllReducer(model)
+            bp3 = steps.default_backprop(opt, red3, model)
+            fnj = lambda: steps.adamatch_step(model, opt, xs, ys, xt1, xt2, n_samples=S, do_consensus_masking=False,  # noqa: E731
+                                              backprop=bp3, eps=epsj)
+            for _ in range(2):
+                fnj()
+            nj = max(3, args.steps // 2)
+            ms_j, launches_j, _ = timed(fnj, nj)
+            red3.remove()
+            joint[tag] = {"metric": "adamatch_joint_train_img_per_s", "value": 2 * Bj * world * nj / (ms_j * 1e-3),
+                          "unit": "img/s (source + target)", "ms_per_step": ms_j / nj,
+                          "launches_per_step": launches_j / nj,
+                          "config": {"workload": f"joint FixMatch step with consensus weighting: {Bj} source + {Bj} target "
+                                                 f"images of 1x{Hj}x{Hj} per GPU, S={S} (BASELINE config 4)",
+                                     "parallelism": f"dp{world}"}}
     if rank != 0:
         return None
     cpu_train = None
@@ -312,6 +341,7 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
         "kernels": per_kernel,
         "cpu_baseline": cpu_train,
         "source_train": src,
+        "joint_fixmatch": joint,
         "model_tflops": TRAIN_FLOP_PER_PX * float(Bt) * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
     }
 
