@@ -40,6 +40,7 @@ def parse():
                     help="infer: MC inference leg only; train: mean-teacher step leg only")
     ap.add_argument("--train-batch", type=int, default=4, help="images per GPU per mean-teacher step (MitoEM: 4)")
     ap.add_argument("--train-size", type=int, default=512)
+    ap.add_argument("--no-graph", action="store_true", help="training legs: time the Python-launched step only")
     ap.add_argument("--no-extras", action="store_true", help="skip the S sweep and the source-training step")
     return ap.parse_args()
 
@@ -205,10 +206,11 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     teacher = copy.deepcopy(model)
     for p in teacher.parameters():
         p.requires_grad = False
-    opt = FusedAdam(model.parameters(), lr=1e-5)
+    opt = FusedAdam(model.parameters(), lr=1e-5, capturable=True)
     reducer = GradAllReducer(model)
     ema = consensus.MomentumUpdater(model, teacher)
     backprop = steps.default_backprop(opt, reducer, model)
+    use_graph = not args.no_graph
     g = torch.Generator().manual_seed(11 + rank)
     x = torch.randn(Bt, 1, HW, HW, generator=g)
     host_x1 = (x + 0.1 * torch.randn(Bt, 1, HW, HW, generator=g)).pin_memory()
@@ -217,9 +219,12 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     eps = torch.randn(S, Bt, 6, generator=torch.Generator().manual_seed(3)).to(dev)
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step_resident():
-        return steps.mean_teacher_step(model, teacher, opt, ema, x1, x2, n_samples=S, do_consensus_masking=True,
+    def step_fn(a, b):
+        return steps.mean_teacher_step(model, teacher, opt, ema, a, b, n_samples=S, do_consensus_masking=True,
                                        backprop=backprop, eps=eps)[0]
+
+    def step_resident():
+        return step_fn(x1, x2)
 
     def step_e2e():
         a = host_x1.to(dev, non_blocking=True)
@@ -250,10 +255,32 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
 
     for _ in range(args.warmup):
         loss = step_resident()
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    # pass 1, launched kernel by kernel from Python: per-kernel CUDA-event profile and launch count
+    ms_launch, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms, ms_graph = ms_launch, None
+    if use_graph:
+        # pass 2: the same step body captured once into a CUDA graph and replayed (steps.GraphedStep): the public
+        # API for fixed-shape training; removes the host from the step
+        gstep = steps.GraphedStep(lambda a, b: step_fn(a, b), (x1, x2), optimizer=opt, warmup=1)
+
+        def step_graph():
+            return gstep(x1, x2)
+
+        def step_e2e_graph():
+            loss = gstep(host_x1, host_x2)   # H2D copies of both views into the static inputs, then the replay
+            host_loss.copy_(loss.detach(), non_blocking=True)
+            return loss
+        for _ in range(args.warmup):
+            loss = step_graph()
+        ms_graph, _, _ = timed(step_graph, args.steps)
+        ms = ms_graph
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e_graph()
+        ms_e2e, _, _ = timed(step_e2e_graph, args.steps)
+    else:
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        ms_e2e, _, _ = timed(step_e2e, args.steps)
     final_loss = float(loss.item())
     reducer.remove()
 
@@ -296,9 +323,18 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
                 fnj()
             nj = max(3, args.steps // 2)
             ms_j, launches_j, _ = timed(fnj, nj)
+            ms_j_launch = ms_j
+            if use_graph:
+                gj = steps.GraphedStep(lambda a, b, c, d: steps.adamatch_step(
+                    model, opt, a, b, c, d, n_samples=S, do_consensus_masking=False, backprop=bp3, eps=epsj)[0],
+                    (xs, ys, xt1, xt2), optimizer=opt, warmup=1)
+                gj(xs, ys, xt1, xt2)
+                ms_j, _, _ = timed(lambda: gj(xs, ys, xt1, xt2), nj)
+                del gj
             red3.remove()
             joint[tag] = {"metric": "adamatch_joint_train_img_per_s", "value": 2 * Bj * world * nj / (ms_j * 1e-3),
                           "unit": "img/s (source + target)", "ms_per_step": ms_j / nj,
+                          "ms_per_step_python_launched": ms_j_launch / nj, "cuda_graph": use_graph,
                           "launches_per_step": launches_j / nj,
                           "config": {"workload": f"joint FixMatch step with consensus weighting: {Bj} source + {Bj} target "
                                                  f"images of 1x{Hj}x{Hj} per GPU, S={S} (BASELINE config 4)",
@@ -334,6 +370,8 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 2 * host_x1.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
+        "cuda_graph": use_graph, "ms_per_step_python_launched": ms_launch / args.steps,
+        "launch_note": "gpu_launches counted in the Python-launched pass; the graphed pass replays the same kernels",
         "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (fwd + dgrad) and wgrad3x3_tc_kernel",
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
@@ -512,6 +550,24 @@ def run_ours(args):
         augment_res["roofline"]["frac"] = augment_res["roofline"]["achieved"] / augment_res["roofline"]["peak"]
         del raw_b, big, nz
 
+    # BASELINE config 1 shape: ONE 256 x 256 image, S = 16 + consensus mask: latency of a single prediction, launched
+    # kernel by kernel from Python and as one CUDA-graph replay (consensus.GraphedMCPredictor)
+    small_res = None
+    if not args.no_extras:
+        xs1 = torch.randn(1, 1, 256, 256, generator=g).to(dev)
+        eps1 = torch.randn(S, 1, 6, generator=g).to(dev)
+        fn1 = lambda: consensus.sample_from_teacher(model, xs1, S, do_consensus_masking=True, eps=eps1)  # noqa: E731
+        fn1()
+        nrep = max(20, args.steps)
+        ms_1, _, _, _ = timed(fn1, nrep)
+        gp = consensus.GraphedMCPredictor(model, xs1, S, do_consensus_masking=True)
+        gp(xs1, eps1)
+        ms_1g, _, _, _ = timed(lambda: gp(xs1, eps1), nrep)
+        small_res = {"metric": "single_image_mc_latency_ms", "python_launched_ms": ms_1 / nrep,
+                     "cuda_graph_ms": ms_1g / nrep, "px_samples_per_s_cuda_graph": 256.0 * 256 * S * nrep / (ms_1g * 1e-3),
+                     "config": {"workload": f"1x1x256x256 (Lung-XRay shape, BASELINE config 1), S={S}, consensus mask"}}
+        del gp
+
     train = None
     if args.mode in ("train", "both"):
         del x_dev, eps
@@ -569,6 +625,7 @@ def run_ours(args):
         "mc_sweep_px_samples_per_s": sweep,
         "tiled_prediction": tiled_res,
         "augment": augment_res,
+        "single_image": small_res,
         "train": train,
     }
     print(json.dumps(line))

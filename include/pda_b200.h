@@ -217,6 +217,13 @@ int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double 
                           double weight_decay, long long step, const float* inv_scale, const float* found_inf,
                           void* stream);
 
+/* The same step with the step count (int64, count BEFORE this update; incremented by the call) and the learning rate
+ * (float) read from DEVICE memory: nothing step-dependent is baked into the launch, so a CUDA graph that captured it can
+ * be replayed (torch.optim.Adam(capturable=True) semantics). */
+int pda_multi_tensor_adam_capturable(const int64_t* table, int n_chunks, const float* lr_dev, double beta1, double beta2,
+                                     double eps, double weight_decay, int64_t* step_dev, const float* inv_scale,
+                                     const float* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

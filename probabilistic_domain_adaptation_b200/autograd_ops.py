@@ -31,11 +31,13 @@ def refresh_packed(module, rot180=True):
     EMA step; `packed_weight` would otherwise repack lazily, one launch per conv and orientation)."""
     import torch.nn as nn
     from . import _lib
-    convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3)
-             and m.in_channels % 64 == 0 and m.weight.is_cuda]
-    if not convs:
-        return
     state = module.__dict__.get("_pda_pack_state")
+    convs = state["convs"] if state is not None else None
+    if convs is None:  # the module tree of these nets is fixed after construction: walk it once
+        convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3)
+                 and m.in_channels % 64 == 0]
+    if not convs or not convs[0].weight.is_cuda:
+        return
     key = tuple((c.weight.data_ptr(), c.weight.device) for c in convs) + (rot180,)
     if state is None or state["key"] != key:
         bufs, rows = [], []
@@ -48,11 +50,11 @@ def refresh_packed(module, rot180=True):
             for start in range(0, 9 * cout * cin, _PACK_CHUNK):
                 rows.append((w.data_ptr(), packed.data_ptr(), 0 if rot is None else rot.data_ptr(), cout, cin, start))
         table = torch.tensor(rows, dtype=torch.int64).to(convs[0].weight.device)
-        state = {"key": key, "bufs": bufs, "table": table}
+        state = {"key": key, "bufs": bufs, "table": table, "convs": convs}
         module.__dict__["_pda_pack_state"] = state
     lib = _lib.load()
     _lib.check(lib.pda_pack_conv3x3_weights_multi(state["table"].data_ptr(), state["table"].shape[0],
-                                                  torch.cuda.current_stream().cuda_stream), "pack_weights_multi")
+                                                  ops._stream()), "pack_weights_multi")
     for c, (packed, rot) in zip(convs, state["bufs"]):
         w = c.weight
         stamp = (w._version, w.data_ptr(), w.device)

@@ -739,8 +739,16 @@ __global__ void fcomb_bwd_finish_kernel(const float* __restrict__ dbz, const flo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adam_kernel(const long long* __restrict__ table, float lr, float beta2, float omb1, float omb2, float eps,
-            float weight_decay, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
+            float weight_decay, float bc1, float bc2_sqrt, const float* __restrict__ inv_scale, const float* __restrict__ found_inf,
+            const float* __restrict__ lr_dev, const long long* __restrict__ step_dev, double beta1_d, double beta2_d) {
   if (found_inf && found_inf[0] != 0.f) return;
+  if (step_dev) {
+    // graph-capturable form: step count and learning rate live on the device (a replayed launch must not bake them in)
+    const double step = (double)(step_dev[0] + 1);
+    bc1 = (float)(1.0 - pow(beta1_d, step));
+    bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, step));
+    lr = lr_dev[0];
+  }
   const long long* e = table + 5LL * blockIdx.x;
   float* p = reinterpret_cast<float*>(e[0]);
   const float* g = reinterpret_cast<const float*>(e[1]);
@@ -779,6 +787,11 @@ adam_kernel(const long long* __restrict__ table, float lr, float beta2, float om
   }
 }
 
+
+__global__ void adam_step_inc_kernel(long long* step_dev, const float* __restrict__ found_inf) {
+  if (found_inf && found_inf[0] != 0.f) return;
+  step_dev[0] += 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Validation metric (my_utils/util.py:17-44, called at punet_trainer.py:78-81): dice = 2 sum(gt * seg) /
@@ -1038,7 +1051,21 @@ int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double 
   PDA_COUNT(1);
   adam_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), (float)lr, (float)beta2,
                                                 (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)bc1,
-                                                (float)sqrt(bc2), inv_scale, found_inf);
+                                                (float)sqrt(bc2), inv_scale, found_inf, nullptr, nullptr, 0.0, 0.0);
+  return LAUNCH_OK();
+}
+
+int pda_multi_tensor_adam_capturable(const int64_t* table, int n_chunks, const float* lr_dev, double beta1, double beta2,
+                                     double eps, double weight_decay, int64_t* step_dev, const float* inv_scale,
+                                     const float* found_inf, void* stream) {
+  if (!table || !lr_dev || !step_dev) return PDA_ERR_ARG;
+  if (n_chunks <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(2);
+  adam_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), 0.f, (float)beta2,
+                                                (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                                                (float)weight_decay, 1.f, 1.f, inv_scale, found_inf, lr_dev,
+                                                reinterpret_cast<const long long*>(step_dev), beta1, beta2);
+  adam_step_inc_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<long long*>(step_dev), found_inf);
   return LAUNCH_OK();
 }
 

@@ -240,6 +240,28 @@ class ProbabilisticUnet(nn.Module):
             self.reconstruction, segm, consm if use_mask else None, dice=bool(self.rl_swap))
         return -(self.reconstruction_loss + self.beta * self.kl)
 
+    def release_graph(self):
+        """Detaches every tensor the stateful protocol caches on the model (values stay readable: loggers read
+        `model.kl`, `model.reconstruction_loss`, ... after the step).  A cached non-leaf tensor keeps the step's whole
+        autograd graph alive -- which is what makes `copy.deepcopy` fail after a forward in the reference
+         and what ties AccumulateGrad nodes to the stream of an earlier step (CUDA-graph capture)."""
+        for name in ("unet_features", "_feat_nhwc", "z_prior_sample", "kl", "reconstruction", "reconstruction_loss",
+                     "mean_reconstruction_loss"):
+            v = self.__dict__.get(name)
+            if torch.is_tensor(v):
+                self.__dict__[name] = v.detach()
+        for name, net in (("prior_latent_space", self.prior), ("posterior_latent_space", self.posterior)):
+            d = self.__dict__.get(name)
+            if d is not None and hasattr(d, "_pda_mls"):
+                mls = d._pda_mls.detach()
+                l = self.latent_dim
+                nd = Independent(Normal(loc=mls[:, :l], scale=torch.exp(mls[:, l:]), validate_args=False), 1,
+                                 validate_args=False)
+                nd._pda_mls = mls
+                self.__dict__[name] = nd
+            if torch.is_tensor(net.mu_log_sigma):
+                net.mu_log_sigma = net.mu_log_sigma.detach()
+
     # ------------------------------------------------------------------ fused Monte-Carlo path
     @torch.no_grad()
     def mc_consensus(self, n_samples=16, eps=None, z=None, testing=False, upper_thres=0.9, lower_thres=0.1,

@@ -28,6 +28,8 @@ def default_backprop(optimizer, reducer=None, model=None):
         optimizer.step()
         if model is not None:
             refresh_packed(model, rot180=True)
+            if hasattr(model, "release_graph"):
+                model.release_graph()  # no cached tensor keeps this step's autograd graph alive (see GraphedStep)
     return backprop
 
 
@@ -45,7 +47,7 @@ def punet_step(model, optimizer, x, y, backprop=None):
     optimizer.zero_grad()
     loss = punet_loss(model, x, y)
     backprop(loss)
-    return loss
+    return loss.detach()  # detached: a live loss keeps the autograd graph (and its AccumulateGrad nodes) alive
 
 
 def mean_teacher_step(model, teacher, optimizer, ema, x1, x2, n_samples=16, do_consensus_masking=False,
@@ -62,7 +64,7 @@ def mean_teacher_step(model, teacher, optimizer, ema, x1, x2, n_samples=16, do_c
     lr = optimizer.param_groups[0]["lr"]
     if lr:  # mean_teacher_trainer.py:126 -- always true for a positive learning rate
         ema.step(momentum)
-    return loss, y, z
+    return loss.detach(), y, z
 
 
 @torch.no_grad()
@@ -105,7 +107,7 @@ def fixmatch_step(model, optimizer, x1, x2, n_samples=16, do_consensus_masking=F
     optimizer.zero_grad()
     loss = punet_loss(model, x2, y, z, use_consm=True)
     backprop(loss)
-    return loss, y, z, ratio
+    return loss.detach(), y, z, ratio
 
 
 def _joint_step(model, pseudo_net, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps):
@@ -118,7 +120,7 @@ def _joint_step(model, pseudo_net, optimizer, xs, ys, xt1, xt2, n_samples, do_co
     target_loss = punet_loss(model, xt2, y, z, use_consm=True)
     loss = (supervised_loss + target_loss) / 2
     backprop(loss)
-    return loss, y, z
+    return loss.detach(), y, z
 
 
 def adamatch_step(model, optimizer, xs, ys, xt1, xt2, n_samples=16, do_consensus_masking=False, backprop=None,
@@ -135,3 +137,51 @@ def adamt_step(model, teacher, optimizer, ema, iteration, xs, ys, xt1, xt2, n_sa
     out = _joint_step(model, teacher, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps)
     ema.step(consensus.adamt_momentum(iteration, momentum))
     return out
+
+
+class GraphedStep:
+    """One whole step body captured into a CUDA graph and replayed: no Python, ctypes, autograd or allocator work per
+    step, which is what bounds the small-batch configurations (LIVECell joint training feeds 2 + 2 images of 256 x 256:
+    ~500 launches for ~4 ms of device work).  The reference has nothing comparable (eager PyTorch, `compile_model=False`
+    in every script); this is the B200-side answer to launch-bound inner loops.
+
+        opt = FusedAdam(model.parameters(), lr=1e-5, capturable=True)
+        reducer = GradAllReducer(model)                       # also for one GPU: keeps p.grad storage fixed
+        bp = default_backprop(opt, reducer, model)
+        step = GraphedStep(lambda x1, x2: mean_teacher_step(model, teacher, opt, ema, x1, x2, backprop=bp)[0],
+                           (x1, x2), optimizer=opt)
+        loss = step(x1, x2)                                   # copies the batch into the static inputs, replays
+
+    Rules (torch.cuda.graph's): fixed shapes; no tensor of an earlier eager step may still hold that step's autograd
+    graph (its AccumulateGrad nodes are tied to the stream they were built on; the step bodies here return detached
+    losses and call `model.release_graph()` for this reason -- pass models stepped otherwise as `modules=`); `fn` must not synchronise with the host (no .item(), no torch.unique ->
+    FixMatch distribution alignment stays eager); host-side scalars are frozen at capture (EMA momentum, beta: constant in
+    every trainer except AdaMT's warm-up) except the Adam step count / learning rate, which FusedAdam(capturable=True)
+    keeps on the device.  Random draws inside `fn` (latent samples) advance per replay (torch's graph-safe generator).
+    The `warmup` eager calls on the first batch are REAL training steps."""
+
+    def __init__(self, fn, example_inputs, optimizer=None, warmup=3, modules=()):
+        self.fn, self.optimizer = fn, optimizer
+        if optimizer is not None and not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedStep needs FusedAdam(capturable=True): a replay must not bake in the step count")
+        self.static_in = [x.clone() for x in example_inputs]
+        for m in modules:
+            m.release_graph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if dst is not src:
+                dst.copy_(src, non_blocking=True)
+        if self.optimizer is not None:
+            self.optimizer.sync_lr()
+        self.graph.replay()
+        return self.static_out
