@@ -267,3 +267,53 @@ def test_graphed_step_matches_eager_steps():
     before = [p.detach().clone() for p in m_g.parameters()]
     step(*batches[0])
     assert all(torch.equal(a, b) for a, b in zip(before, m_g.parameters()))
+
+
+@pytest.mark.gpu
+def test_step_under_torch_em_mixed_precision_protocol():
+    """torch_em's DefaultTrainer runs the student step as `with torch.autocast("cuda"): ...;
+    scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()` (its `_backprop_mixed`; every script
+    leaves mixed_precision on).  The kernels keep their own precision, so autocast must be a no-op for the values and
+    the 2^16 loss scale must pass through the bf16 activation gradients unharmed: the unscaled gradients equal those
+    of the plain step, and torch.optim.Adam + GradScaler take a finite step."""
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, steps
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0, consensus_masking=True, rl_swap=True).to(dev).train()
+    with torch.no_grad():
+        model.fcomb.last_layer.weight.mul_(8.0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 1, 64, 64, generator=g).to(dev)
+    yy, xx = torch.meshgrid(torch.arange(64.0), torch.arange(64.0), indexing="ij")
+    y = ((yy - 32) ** 2 + (xx - 30) ** 2 < 300).float()[None, None].repeat(2, 1, 1, 1).to(dev)
+    consm = (torch.rand(2, 1, 64, 64, generator=g) > 0.3).long().to(dev)
+
+    def grads(amp):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)   # same posterior draw
+        scaler = torch.amp.GradScaler("cuda", enabled=amp)
+        with torch.autocast("cuda", enabled=amp):
+            loss = steps.punet_loss(model, x, y, consm, use_consm=True)
+        assert loss.dtype == torch.float32
+        scaler.scale(loss).backward()
+        s = float(scaler.get_scale()) if amp else 1.0
+        return float(loss), [p.grad.detach().clone() / s for p in model.parameters()], scaler
+
+    l0, g0, _ = grads(False)
+    l1, g1, scaler = grads(True)
+    assert abs(l0 - l1) <= 1e-4 * abs(l0)
+    for (name, _), a, b in zip(model.named_parameters(), g0, g1):
+        assert torch.isfinite(b).all(), name
+        den = float(a.norm()) * float(b.norm())
+        if den > 0:
+            cos = float((a * b).sum()) / den
+            assert cos > 0.999, (name, cos)
+            assert abs(float(a.norm()) - float(b.norm())) <= 0.02 * float(a.norm()), name
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    before = [p.detach().clone() for p in model.parameters()]
+    scaler.step(opt)
+    scaler.update()
+    assert float(scaler.get_scale()) == 65536.0           # no inf / NaN was found: the step was taken
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    assert all(torch.isfinite(p).all() for p in model.parameters())
