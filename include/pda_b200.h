@@ -217,6 +217,14 @@ int pda_multi_tensor_adam(const int64_t* table, int n_chunks, double lr, double 
                           double weight_decay, long long step, const float* inv_scale, const float* found_inf,
                           void* stream);
 
+/* FixMatch distribution alignment (fixmatch_trainer.py:77-84): y_bin = y >= 0.5; target = class frequencies of y_bin
+ * (a single-class batch gives target = [1.0] for both entries, as torch.unique's single count does); ratio = source /
+ * target; out = clip(where(y < 0.5, y * ratio[0], y * ratio[1]), 0, 1).  source_dist: device float[2] = (background,
+ * foreground) frequency of the source domain; scratch: device uint64[1]; ratio: device float[2] (output).  No host
+ * synchronisation (the reference's torch.unique sorts and syncs). */
+int pda_distribution_alignment(const float* y, long long n, const float* source_dist, unsigned long long* scratch,
+                               float* out, float* ratio, void* stream);
+
 /* The same step with the step count (int64, count BEFORE this update; incremented by the call) and the learning rate
  * (float) read from DEVICE memory: nothing step-dependent is baked into the launch, so a CUDA graph that captured it can
  * be replayed (torch.optim.Adam(capturable=True) semantics). */

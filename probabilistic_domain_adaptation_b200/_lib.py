@@ -52,6 +52,7 @@ SIGNATURES = {
     "pda_multi_tensor_l2norm_bwd": [_P, _I, _P, _P, _P, _P],
     "pda_multi_tensor_adam": [_P, _I, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _c.c_longlong,
                               _P, _P, _P],
+    "pda_distribution_alignment": [_P, _c.c_longlong, _P, _P, _P, _P, _P],
     "pda_multi_tensor_adam_capturable": [_P, _I, _P, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P, _P, _P, _P],
     "pda_fcomb_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pda_fcomb_bwd_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -174,13 +174,26 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
       for (int t = 0; t < 9; ++t) acc[ci][t][j] = 0.f;
   }
   const long long npix = (long long)B * H * W;
-  for (long long pix = (long long)blockIdx.x * lanes_px + lpx; pix < npix; pix += (long long)gridDim.x * lanes_px) {
+  const long long pstride = (long long)gridDim.x * lanes_px;
+  long long pix = (long long)blockIdx.x * lanes_px + lpx;
+  // the two 16-byte activation loads of the NEXT pixel are issued before this pixel's 72 / 144 FMAs: with ~200
+  // registers per thread only 8 warps are resident per SM, so the loads in flight per thread decide the bandwidth
+  uint4 q_dz = make_uint4(0, 0, 0, 0), q_y = q_dz;
+  if (pix < npix) {
+    q_dz = __ldg(reinterpret_cast<const uint4*>(dout + pix * cout + g * 8));
+    q_y = __ldg(reinterpret_cast<const uint4*>(out + pix * cout + g * 8));
+  }
+  for (; pix < npix; pix += pstride) {
     const int x = pix % W;
     const int y = (pix / W) % H;
     const long long img_off = (pix / ((long long)W * H)) * H * W;
     float dz[8], yv[8];
-    unpack8f(__ldg(reinterpret_cast<const uint4*>(dout + pix * cout + g * 8)), dz);
-    unpack8f(__ldg(reinterpret_cast<const uint4*>(out + pix * cout + g * 8)), yv);
+    unpack8f(q_dz, dz);
+    unpack8f(q_y, yv);
+    if (pix + pstride < npix) {
+      q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (pix + pstride) * cout + g * 8));
+      q_y = __ldg(reinterpret_cast<const uint4*>(out + (pix + pstride) * cout + g * 8));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dz[j] = yv[j] > 0.f ? dz[j] : 0.f;
@@ -788,6 +801,45 @@ adam_kernel(const long long* __restrict__ table, float lr, float beta2, float om
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// FixMatch distribution alignment (fixmatch_trainer.py:77-84): the foreground / background frequencies of the binarised
+// pseudo-label against the source-domain frequencies.  torch.unique(return_counts=True) (a sort + a host sync in the
+// reference) becomes one counting pass; a batch with a single class yields target = [1.0], exactly what `unique`
+// returning one count does to the reference's broadcast.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+count_fg_kernel(const float* __restrict__ y, long long n, unsigned long long* __restrict__ count) {
+  unsigned int c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += (y[i] >= 0.5f) ? 1u : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(256)
+dist_align_apply_kernel(const float* __restrict__ y, float* __restrict__ out, long long n,
+                        const unsigned long long* __restrict__ count, const float* __restrict__ source,
+                        float* __restrict__ ratio_out) {
+  const unsigned long long n1 = count[0], n0 = (unsigned long long)n - n1;
+  float t0 = 1.f, t1 = 1.f;
+  if (n0 != 0 && n1 != 0) {
+    t0 = (float)(long long)n0 / (float)n;
+    t1 = (float)(long long)n1 / (float)n;
+  }
+  // single class: unique() returns ONE count -> target_distribution = [1.0], broadcast against both source entries
+  const float r0 = source[0] / t0, r1 = source[1] / t1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ratio_out[0] = r0;
+    ratio_out[1] = r1;
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    const float a = (v < 0.5f) ? v * r0 : v * r1;
+    out[i] = fminf(fmaxf(a, 0.f), 1.f);
+  }
+}
+
 __global__ void adam_step_inc_kernel(long long* step_dev, const float* __restrict__ found_inf) {
   if (found_inf && found_inf[0] != 0.f) return;
   step_dev[0] += 1;
@@ -1066,6 +1118,18 @@ int pda_multi_tensor_adam_capturable(const int64_t* table, int n_chunks, const f
                                                 (float)weight_decay, 1.f, 1.f, inv_scale, found_inf, lr_dev,
                                                 reinterpret_cast<const long long*>(step_dev), beta1, beta2);
   adam_step_inc_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<long long*>(step_dev), found_inf);
+  return LAUNCH_OK();
+}
+
+int pda_distribution_alignment(const float* y, long long n, const float* source_dist, unsigned long long* scratch,
+                               float* out, float* ratio, void* stream) {
+  if (!y || !source_dist || !scratch || !out || !ratio) return PDA_ERR_ARG;
+  if (n <= 0) return PDA_ERR_SHAPE;
+  if (cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), ST(stream)) != cudaSuccess) return PDA_ERR_CUDA;
+  const int blocks = grid_cap(n, 256, 148 * 4);
+  PDA_COUNT(2);
+  count_fg_kernel<<<blocks, 256, 0, ST(stream)>>>(y, n, scratch);
+  dist_align_apply_kernel<<<blocks, 256, 0, ST(stream)>>>(y, out, n, scratch, source_dist, ratio);
   return LAUNCH_OK();
 }
 

@@ -85,12 +85,22 @@ def validation_step(model, x, y, n_samples=8):
 
 
 def distribution_alignment(y, source_distribution):
-    """fixmatch_trainer.py:77-84 (tiny: B x H x W compare / unique on the pseudo-label; stays in torch)."""
-    y_binary = torch.where(y >= 0.5, 1, 0)
-    _, target_distribution = torch.unique(y_binary, return_counts=True)
-    target_distribution = target_distribution / target_distribution.sum()
-    ratio = source_distribution / target_distribution
-    return torch.where(y < 0.5, y * ratio[0], y * ratio[1]).clip(0, 1), ratio
+    """fixmatch_trainer.py:77-84 on the device: class frequencies of the binarised pseudo-label (one counting pass instead
+    of torch.unique's sort + host sync), ratio = source / target, rescaled and clipped pseudo-label.  Returns
+    (y_aligned, ratio (2,) device tensor).  `source_distribution`: [background, foreground] frequencies (list or tensor)."""
+    from . import _lib, ops
+    ops._need_cuda(y)
+    y = y.contiguous()
+    if not torch.is_tensor(source_distribution) or not source_distribution.is_cuda:
+        source_distribution = torch.as_tensor(source_distribution, dtype=torch.float32).to(y.device)
+    source_distribution = source_distribution.to(torch.float32).contiguous()
+    out = torch.empty_like(y)
+    ratio = torch.empty(2, dtype=torch.float32, device=y.device)
+    scratch = torch.empty(1, dtype=torch.int64, device=y.device)
+    _lib.check(_lib.load().pda_distribution_alignment(y.data_ptr(), y.numel(), source_distribution.data_ptr(),
+                                                      scratch.data_ptr(), out.data_ptr(), ratio.data_ptr(),
+                                                      ops._stream()), "distribution_alignment")
+    return out, ratio
 
 
 def fixmatch_step(model, optimizer, x1, x2, n_samples=16, do_consensus_masking=False, source_distribution=None,
@@ -154,10 +164,11 @@ class GraphedStep:
 
     Rules (torch.cuda.graph's): fixed shapes; no tensor of an earlier eager step may still hold that step's autograd
     graph (its AccumulateGrad nodes are tied to the stream they were built on; the step bodies here return detached
-    losses and call `model.release_graph()` for this reason -- pass models stepped otherwise as `modules=`); `fn` must not synchronise with the host (no .item(), no torch.unique ->
-    FixMatch distribution alignment stays eager); host-side scalars are frozen at capture (EMA momentum, beta: constant in
-    every trainer except AdaMT's warm-up) except the Adam step count / learning rate, which FusedAdam(capturable=True)
-    keeps on the device.  Random draws inside `fn` (latent samples) advance per replay (torch's graph-safe generator).
+    losses and call `model.release_graph()` for this reason -- pass models stepped otherwise as `modules=`); `fn` must
+    not synchronise with the host (no .item(); FixMatch's distribution alignment runs as a device kernel here for that
+    reason, not through torch.unique); host-side scalars are frozen at capture (EMA momentum, beta: constant in every
+    trainer except AdaMT's warm-up) except the Adam step count / learning rate, which FusedAdam(capturable=True) keeps
+    on the device.  Random draws inside `fn` (latent samples) advance per replay (torch's graph-safe generator).
     The `warmup` eager calls on the first batch are REAL training steps."""
 
     def __init__(self, fn, example_inputs, optimizer=None, warmup=3, modules=()):

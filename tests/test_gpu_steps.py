@@ -22,14 +22,15 @@ def _model(**kw):
     return m.train()
 
 
-def test_fused_adam_matches_torch_adam():
+@pytest.mark.parametrize("capturable", [False, True])
+def test_fused_adam_matches_torch_adam(capturable):
     from probabilistic_domain_adaptation_b200.optim import FusedAdam
     dev = _dev()
     g = torch.Generator().manual_seed(0)
     shapes = [(64, 1, 3, 3), (64,), (128, 64, 3, 3), (12, 512, 1, 1), (70001,)]
     pa = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
     pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
-    oa = FusedAdam(pa, lr=1e-3, weight_decay=0.01)
+    oa = FusedAdam(pa, lr=1e-3, weight_decay=0.01, capturable=capturable)   # capturable: step count / lr on the device
     ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=0.01)
     for it in range(5):
         for a, b in zip(pa, pb):
@@ -317,3 +318,22 @@ def test_step_under_torch_em_mixed_precision_protocol():
     assert float(scaler.get_scale()) == 65536.0           # no inf / NaN was found: the step was taken
     assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+@pytest.mark.gpu
+def test_distribution_alignment_matches_reference_arithmetic():
+    """fixmatch_trainer.py:77-84 through the device kernel vs the oracle's literal torch ops (unique + where + clip),
+    including the single-class batch, where torch.unique returns ONE count and the reference broadcasts it."""
+    from oracle import punet_oracle as po
+    from probabilistic_domain_adaptation_b200 import steps
+    dev = _dev()
+    g = torch.Generator().manual_seed(4)
+    src = torch.tensor([0.8, 0.2])
+    cases = [torch.rand(2, 1, 40, 56, generator=g), torch.rand(1, 1, 33, 17, generator=g) * 0.49,
+             0.5 + 0.5 * torch.rand(3, 1, 8, 8, generator=g), torch.rand(4, 1, 512, 512, generator=g) ** 3]
+    for y in cases:
+        want, ratio_want = po.distribution_alignment(y, src)
+        got, ratio = steps.distribution_alignment(y.to(dev), src.tolist())
+        ratio_want = ratio_want.expand(2) if ratio_want.numel() == 2 else ratio_want
+        assert torch.allclose(ratio.cpu(), ratio_want, rtol=1e-6), (ratio, ratio_want)
+        assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-7)
