@@ -442,7 +442,11 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
   const size_t need = sizeof(float) * (size_t)S * B * FCT;
   if (bz_cap[dev] < need) {
-    if (bz_buf[dev]) cudaFree(bz_buf[dev]);
+    // grow-only, and the outgrown buffer is deliberately NOT freed: a CUDA graph captured earlier may still replay a
+    // launch that writes it (a few KB per growth step; sizes below 1 MB = S * B <= 4096 never grow at all)
+    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap_state) != cudaSuccess) return PDA_ERR_CUDA;
+    if (cap_state != cudaStreamCaptureStatusNone) return PDA_ERR_CUDA;  // run one eager warm-up of this shape first
     const size_t cap = need < (1u << 20) ? (1u << 20) : need;
     if (cudaMalloc(&bz_buf[dev], cap) != cudaSuccess) {
       bz_buf[dev] = nullptr;

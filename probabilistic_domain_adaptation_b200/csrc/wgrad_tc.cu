@@ -3,21 +3,26 @@
 // Replaces the cuDNN wgrad that autograd runs for every nn.Conv2d(k=3) of
 // /root/reference/prob_utils/my_models/unet_blocks.py:19-24 and probabilistic_unet.py:56-61 in backward.
 //
-//   dW[co][tap][ci] = sum over pixels p of  dZ[p][co] * X[p + tap][ci]
+//   dW[co][ky][kx][ci] = sum_{y,x} dZ[y][x][co] * X[y+ky-1][x+kx-1][ci]
+//                      = sum_{y,x'} dZ[y][x'-kx+1][co] * X[y+ky-1][x'][ci]          (x' = x + kx - 1)
 //
 // GEMM view with the reduction over PIXELS as K.  Both operands are read straight from their NHWC tensors by TMA
-// (SWIZZLE_128B) and fed to the MMA as MN-major operands (the channel dimension is contiguous): no transpose is
-// ever materialised.
+// (SWIZZLE_128B) and fed to the MMA as MN-major operands (the channel dimension is contiguous): no transpose is ever
+// materialised.  What the MMA shape has to respect (profiles/r01e_umma_issue_rate.md): an M = 128 x N x K = 16 MMA
+// needs N/2 tensor cycles but (4 KB + N * 32 B) / 128 B/clk of shared-memory operand fetch -- N = 64 tiles are capped at
+// 2/3 of the tensor rate by the operand fetch alone (and the TMA fill shares that port), N >= 128 are not; MN-major
+// operands cost nothing extra.  So the taps go into N, not into M:
 //   work item  = (64 output channels, 64 input channels): all nine taps
-//   pixel tile = 16 rows x 8 px of one image = K 128, as 8 MMAs of K = 16
-//   A (M x K)  = X^T: three column-shifted SLABS [18 rows][8 px][64 ci] (as in the forward conv) hold all nine taps.
-//                M = 128 = a PAIR of taps: the second 64-row block is the first advanced by LBO bytes, which is one
-//                8-px row (next ky) inside a slab or a jump to the next slab.  5 pairs = 9 taps + 1 discarded.
-//   B (N x K)  = dZ^T [64 co]
-//   D          = 5 x (128 x 64) fp32 = 320 TMEM columns, accumulated over the item's pixel tiles.
+//   pixel tile = 16 rows x 8 px of one image = K 128, as 8 K-steps of 16 px (two rows)
+//   B (N x K)  = X^T: ONE slab [18 rows][8 px][64 ci]; the three ky taps of an output row are the slab rows
+//                y, y+1, y+2 = three 64-channel N blocks 1024 B apart  ->  N = 192
+//   A (M x K)  = dZ^T: three column-shifted slabs [16 rows][8 px][64 co] (shift 1 - kx; TMA zero-fills the border).
+//                M = 128 = the kx = 0 and kx = 1 slabs (LBO = slab stride); a second MMA takes kx = 2
+//   D          = [128 (kx, co)][192 (ky, ci)] + an M = 64 accumulator [64 co][192] = 384 TMEM columns (+16: bias sums)
+// Two MMAs per K-step instead of five (plus a 16-column "ones" MMA for the bias gradient on the items of input chunk 0).
 // Persistent stream-K schedule: the (item, pixel tile) steps are split into 148 equal contiguous ranges; a CTA flushes
-// its accumulators with coalesced fp32 atomics into a zero-initialised scratch [cout][9][ctot] whenever its range
-// crosses an item boundary.
+// its accumulators with coalesced fp32 atomics (lanes = output channels) into a zero-initialised scratch
+// [9 taps][ctot][cout] whenever its range crosses an item boundary.
 #include "conv.cuh"
 #include "ptx.cuh"
 
@@ -30,21 +35,23 @@ struct WgradArgs {
   int num_tiles;   // pixel tiles = B * tiles_x * tiles_y
   int n64;         // cout / 64
   int items;       // n64 * (c0 + c1) / 64
-  float* scratch;  // [cout][9][ctot] fp32, zero-initialised by the caller
+  float* scratch;  // [9][ctot][cout] fp32, zero-initialised by the caller
   float* dbias;    // [cout] fp32, zero-initialised, or nullptr: bias gradient = column sums of dZ, from one extra
                    // "ones" MMA on the items of input-channel chunk 0
 };
 
 struct WgradSmem {
-  static constexpr int SLAB = 18 * 1024;             // [18 rows][8 px][64 ch] bf16
-  static constexpr int DZ_BYTES = 16 * 1024;         // [16 rows][8 px][64 co] bf16
-  static constexpr int STAGE_BYTES = 3 * SLAB + DZ_BYTES;  // slabs first: tap pair 4 over-reads 1 KB into the dZ tile
+  static constexpr int DZ_SLAB = 16 * 1024;          // [16 rows][8 px][64 co] bf16
+  static constexpr int X_SLAB = 18 * 1024;           // [18 rows][8 px][64 ci] bf16
+  static constexpr int X_OFF = 3 * DZ_SLAB;
+  static constexpr int STAGE_BYTES = 3 * DZ_SLAB + X_SLAB;
   static constexpr int STAGES = 3;
-  static constexpr int ONES_OFF = STAGES * STAGE_BYTES;  // 1 KB of bf16 ones: an MN-major A block whose rows all alias
+  static constexpr int ONES_OFF = STAGES * STAGE_BYTES;  // 1 KB of bf16 ones: an MN-major B block whose K rows all alias
   static constexpr int BAR_OFF = ONES_OFF + 1024;
   static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 2) * 8;
   static constexpr int DYN_BYTES = SLOT_OFF + 16 + 1024;
-  static constexpr int TMEM_COLS = 512;              // 5 x 64 tap pairs + 64 for the bias column sums
+  static constexpr int TMEM_COLS = 512;              // [0,192) kx 0|1, [192,384) kx 2, [384,400) bias column sums
+  static constexpr int D2_COL = 192, BIAS_COL = 384;
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -111,20 +118,24 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
         const int c = ch << 6;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          if (c < p.c0)
-            tma_load_4d(sa + kx * L::SLAB, &tmX0, full_bar(s), c, x0 + kx - 1, y0 - 1, img);
-          else
-            tma_load_4d(sa + kx * L::SLAB, &tmX1, full_bar(s), c - p.c0, x0 + kx - 1, y0 - 1, img);
-        }
-        tma_load_4d(sa + 3 * L::SLAB, &tmDZ, full_bar(s), nb << 6, x0, y0, img);
+        for (int kx = 0; kx < 3; ++kx)  // dZ shifted by 1 - kx columns (out-of-image columns arrive as zeros)
+          tma_load_4d(sa + kx * L::DZ_SLAB, &tmDZ, full_bar(s), nb << 6, x0 + 1 - kx, y0, img);
+        if (c < p.c0)
+          tma_load_4d(sa + L::X_OFF, &tmX0, full_bar(s), c, x0, y0 - 1, img);
+        else
+          tma_load_4d(sa + L::X_OFF, &tmX1, full_bar(s), c - p.c0, x0, y0 - 1, img);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, /*a_mn_major=*/1, /*b_mn_major=*/1);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 192, /*a_mn_major=*/1, /*b_mn_major=*/1);
+    // the third kx and the bias sums have only 64 useful rows: M = 64 MMAs (same tensor time as M = 128 -- measured --
+    // but half the A-operand fetch and half the multipliers switching).  An M = 64 accumulator keeps rows 16 i .. 16 i + 15
+    // in TMEM lanes 32 i .. 32 i + 15 (profiles/r01e_umma_issue_rate.md)
+    constexpr uint32_t idesc64 = umma_idesc_bf16(64, 192, 1, 1);
+    constexpr uint32_t idesc_bias = umma_idesc_bf16(64, 16, 1, 1);
     uint32_t it = 0, flushes = 0;
     int cur_item = -1;
     for (long long st = s0; st < s1; ++st, ++it) {
@@ -145,25 +156,20 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
       tc_fence_after();
       if (leader) {
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
-        // MN-major SWIZZLE_128B: 64-channel blocks LBO apart, 8-pixel K groups 1024 B apart (SBO)
-        const uint64_t db = umma_desc_mn_sw128(sa + 3 * L::SLAB, 1024, 1024);
-        const uint64_t da0 = umma_desc_mn_sw128(sa, 1024, 1024);                          // (kx0,ky0) (kx0,ky1)
-        const uint64_t da1 = umma_desc_mn_sw128(sa + 2048, L::SLAB - 2048, 1024);         // (kx0,ky2) (kx1,ky0)
-        const uint64_t da2 = umma_desc_mn_sw128(sa + L::SLAB + 1024, 1024, 1024);         // (kx1,ky1) (kx1,ky2)
-        const uint64_t da3 = umma_desc_mn_sw128(sa + 2 * L::SLAB, 1024, 1024);            // (kx2,ky0) (kx2,ky1)
-        const uint64_t da4 = umma_desc_mn_sw128(sa + 2 * L::SLAB + 2048, 1024, 1024);     // (kx2,ky2) (discarded)
-        const uint64_t d1s = umma_desc_mn_sw128(sbase + L::ONES_OFF, 0, 0);               // all-ones rows
+        // MN-major SWIZZLE_128B: 64-channel blocks LBO apart, 8-pixel K groups (one slab row) 1024 B apart (SBO)
+        const uint64_t da01 = umma_desc_mn_sw128(sa, L::DZ_SLAB, 1024);                  // M = (kx 0 | kx 1) x co
+        const uint64_t da2 = umma_desc_mn_sw128(sa + 2 * L::DZ_SLAB, 0, 1024);           // M = 64: kx 2 x co
+        const uint64_t da1 = umma_desc_mn_sw128(sa + L::DZ_SLAB, 0, 1024);               // unshifted dZ (bias sums)
+        const uint64_t db = umma_desc_mn_sw128(sa + L::X_OFF, 1024, 1024);               // N = (ky 0 | 1 | 2) x ci
+        const uint64_t d1s = umma_desc_mn_sw128(sbase + L::ONES_OFF, 0, 0);              // all-ones K rows
         const bool bias_item = p.dbias != nullptr && item / p.n64 == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // 16 pixels per MMA = 2 rows of 8 px = 2048 B: +128 in 16-byte units
           const uint32_t acc = (!first || k != 0) ? 1u : 0u;
-          umma_bf16(tmem + 0, da0 + 128 * k, db + 128 * k, idesc, acc);
-          umma_bf16(tmem + 64, da1 + 128 * k, db + 128 * k, idesc, acc);
-          umma_bf16(tmem + 128, da2 + 128 * k, db + 128 * k, idesc, acc);
-          umma_bf16(tmem + 192, da3 + 128 * k, db + 128 * k, idesc, acc);
-          umma_bf16(tmem + 256, da4 + 128 * k, db + 128 * k, idesc, acc);
-          if (bias_item) umma_bf16(tmem + 320, d1s, db + 128 * k, idesc, acc);  // every row = sum_px dZ[px][co]
+          umma_bf16(tmem, da01 + 128 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + L::D2_COL, da2 + 128 * k, db + 128 * k, idesc64, acc);
+          if (bias_item) umma_bf16(tmem + L::BIAS_COL, da1 + 128 * k, d1s, idesc_bias, acc);  // sum_px dZ[px][co]
         }
         umma_commit(empty_bar(s));
       }
@@ -174,48 +180,45 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ epilogue: accumulator row = (tap of the pair, ci)
+    // ------------------------------------------------------------ epilogue: accumulator row = (kx of the pair, co)
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int h = row >> 6, ci_l = row & 63;
+    const int co_l = (q & 1) * 32 + lane;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t flushes = 0;
     int cur_item = -1;
     auto flush = [&](int item) {
       const int nb = item % p.n64, ch = item / p.n64;
       mbar_wait(acc_full, flushes & 1);
       tc_fence_after();
+      // lanes = consecutive output channels: every atomic instruction of a warp covers one 128-byte line
+      float* base = p.scratch + (static_cast<size_t>(ch) << 6) * p.cout + (nb << 6) + co_l;
+      const size_t tap_stride = static_cast<size_t>(ctot) * p.cout;
 #pragma unroll 1
-      for (int pr = 0; pr < 5; ++pr) {
-        // tap = ky * 3 + kx of this half of pair pr
-        const int lin = 2 * pr + h;             // position in the (kx, ky) slab-major order: lin = kx * 3 + ky
-        const int kx = lin / 3, ky = lin - 3 * kx;
-        const bool live = lin < 9;
-        float* dst = p.scratch + (static_cast<size_t>(nb << 6) * 9 + (ky * 3 + kx)) * ctot + (ch << 6) + ci_l;
+      for (int part = 0; part < 2; ++part) {
+        // part 0: M = 128 accumulator, row = (kx, co) = this thread's lane.  part 1: M = 64 accumulator of kx = 2:
+        // rows 16 q .. 16 q + 15 sit in the first 16 lanes of lane quarter q
+        const int kx = part == 0 ? (q >> 1) : 2;
+        const bool live = part == 0 || lane < 16;
+        float* pbase = part == 0 ? base : base - co_l + 16 * q + lane;
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int c32 = 0; c32 < 6; ++c32) {
+          const int ky = c32 >> 1, ci0 = (c32 & 1) * 32;
           uint32_t v[32];
-          tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + pr * 64 + cb * 32, v);
+          tmem_ld32(lane_addr + part * L::D2_COL + c32 * 32, v);
           tmem_ld_wait();
           if (live) {
+            float* dst = pbase + (ky * 3 + kx) * tap_stride + static_cast<size_t>(ci0) * p.cout;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              atomicAdd(dst + static_cast<size_t>(cb * 32 + j) * 9 * ctot, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + static_cast<size_t>(j) * p.cout, __uint_as_float(v[j]));
           }
         }
       }
-      if (p.dbias != nullptr && ch == 0 && q == 0) {
-        // all 128 rows of the ones-block accumulator are identical: row 0 carries the bias gradient of this co block.
-        // (tcgen05.ld is warp-collective: the whole warp of lane quarter 0 loads, lane 0 publishes)
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tmem + 320 + cb * 32, v);
-          tmem_ld_wait();
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(p.dbias + (nb << 6) + cb * 32 + j, __uint_as_float(v[j]));
-          }
-        }
+      if (p.dbias != nullptr && ch == 0) {
+        // every column of the ones-block accumulator (M = 64 layout) holds sum_px dZ[px][co]
+        uint32_t v[16];
+        tmem_ld16(lane_addr + L::BIAS_COL, v);
+        tmem_ld_wait();
+        if (lane < 16) atomicAdd(p.dbias + (nb << 6) + 16 * q + lane, __uint_as_float(v[0]));
       }
       tc_fence_before();
       __syncwarp();
@@ -238,7 +241,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-// scratch [cout][9][ctot] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0)
+// scratch [9][ctot][cout] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0)
 __global__ void wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot,
                                      int accumulate) {
   const long long n = 9LL * cout * ctot;
@@ -246,7 +249,7 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ scratch, float* _
     const int tap = i % 9;
     const int ci = (i / 9) % ctot;
     const int co = i / (9LL * ctot);
-    const float v = scratch[((long long)co * 9 + tap) * ctot + ci];
+    const float v = scratch[((long long)tap * ctot + ci) * cout + co];
     dw[i] = accumulate ? dw[i] + v : v;
   }
 }
