@@ -20,6 +20,12 @@
 //                M = 128 = the kx = 0 and kx = 1 slabs (LBO = slab stride); a second MMA takes kx = 2
 //   D          = [128 (kx, co)][192 (ky, ci)] + an M = 64 accumulator [64 co][192] = 384 TMEM columns (+16: bias sums)
 // Two MMAs per K-step instead of five (plus a 16-column "ones" MMA for the bias gradient on the items of input chunk 0).
+// Measured with in-kernel cycle counters (round 1e): the MMA warp waits ~130 cycles per step for data and spends ~2130
+// cycles per step issuing against a full MMA queue, i.e. the tensor pipe runs 16 MMAs in 2130 cycles where the tensor
+// rate alone would need 1536.  The shared-memory port explains it: 66 KB of TMA fill + 144 KB of operand fetch per step
+// = 1640 cycles at 128 B/clk (skipping two of the three dZ slab loads: -7 %; skipping the kx = 2 MMA: -21 %).  The X
+// slab is fetched twice (M is capped at 128, the three kx need 192 rows) and the dZ tile is loaded three times (once
+// per column shift): those are the remaining levers.
 // Persistent stream-K schedule: the (item, pixel tile) steps are split into 148 equal contiguous ranges; a CTA flushes
 // its accumulators with coalesced fp32 atomics (lanes = output channels) into a zero-initialised scratch
 // [9 taps][ctot][cout] whenever its range crosses an item boundary.
