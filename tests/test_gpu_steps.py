@@ -337,3 +337,46 @@ def test_distribution_alignment_matches_reference_arithmetic():
         ratio_want = ratio_want.expand(2) if ratio_want.numel() == 2 else ratio_want
         assert torch.allclose(ratio.cpu(), ratio_want, rtol=1e-6), (ratio, ratio_want)
         assert torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_graphed_mc_predictor_matches_eager_path():
+    """consensus.GraphedMCPredictor (one CUDA-graph replay) returns exactly what sample_from_teacher launches kernel by
+    kernel: same mean, same int64 mask for the same latent draws; without `eps` every replay draws fresh samples."""
+    from probabilistic_domain_adaptation_b200 import consensus
+    dev = _dev()
+    model = _model().eval()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 1, 64, 96, generator=g).to(dev)
+    eps = torch.randn(8, 2, 6, generator=g).to(dev)
+    want_mean, want_mask = consensus.sample_from_teacher(model, x, 8, do_consensus_masking=True, eps=eps)
+    gp = consensus.GraphedMCPredictor(model, x, 8, do_consensus_masking=True)
+    for xin in (x, x.clone()):
+        mean, mask = gp(xin, eps)
+        assert torch.equal(mean, want_mean) and torch.equal(mask, want_mask) and mask.dtype == torch.int64
+    a = gp(x)[0].clone()
+    b = gp(x)[0].clone()
+    assert not torch.equal(a, b)                       # fresh latent draws per replay
+    x2 = torch.randn(2, 1, 64, 96, generator=g).to(dev)
+    want2 = consensus.sample_from_teacher(model, x2, 8, do_consensus_masking=True, eps=eps)[0]
+    assert torch.equal(gp(x2, eps)[0], want2)          # new inputs are copied into the static buffer
+
+
+@pytest.mark.gpu
+def test_release_graph_allows_deepcopy_after_a_step():
+    """The reference model cannot be deep-copied after a forward (cached non-leaf tensors); the step
+    bodies here end with release_graph(), after which the cached values are still readable and the model copies."""
+    import copy
+    from probabilistic_domain_adaptation_b200 import steps
+    dev = _dev()
+    model = _model(consensus_masking=True, rl_swap=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1, 64, 64, generator=g).to(dev)
+    y = (torch.rand(2, 1, 64, 64, generator=g) > 0.5).float().to(dev)
+    loss = steps.punet_step(model, opt, x, y, backprop=steps.default_backprop(opt, None, model))
+    assert not loss.requires_grad and torch.isfinite(loss)
+    assert torch.isfinite(model.kl) and not model.kl.requires_grad and model.reconstruction.shape == (2, 1, 64, 64)
+    assert model.posterior_latent_space.base_dist.loc.shape == (2, 6)
+    clone = copy.deepcopy(model)
+    assert sum(p.numel() for p in clone.parameters()) == sum(p.numel() for p in model.parameters())
