@@ -370,15 +370,31 @@ recon_loss_partial_kernel(const float* __restrict__ logits, const float* __restr
   }
 }
 
-__global__ void recon_loss_final_kernel(const double* __restrict__ partial, int nblocks, long long n, int dice,
-                                        float* __restrict__ out, float* __restrict__ stats) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
+// Final reductions over per-block partial sums: ONE warp, lane l owns partials l, l + 32, ... (fixed order), then a
+// fixed shuffle tree -- deterministic, and 1/32 of the dependent-load chain of a single-thread loop (these kernels sit
+// on the critical path of every training step).
+__device__ __forceinline__ void warp_sum3(const double* __restrict__ partial, int nblocks, double& s0, double& s1,
+                                          double& s2) {
+  s0 = s1 = s2 = 0.0;
+  for (int k = threadIdx.x & 31; k < nblocks; k += 32) {
     s0 += partial[3 * k];
     s1 += partial[3 * k + 1];
     s2 += partial[3 * k + 2];
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+}
+
+__global__ void recon_loss_final_kernel(const double* __restrict__ partial, int nblocks, long long n, int dice,
+                                        float* __restrict__ out, float* __restrict__ stats) {
+  if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+  double s0, s1, s2;
+  warp_sum3(partial, nblocks, s0, s1, s2);
+  if (threadIdx.x != 0) return;
   stats[0] = (float)s0;
   stats[1] = (float)s1;
   stats[2] = (float)s2;
@@ -457,14 +473,16 @@ __global__ void __launch_bounds__(256) l2_partial_kernel(const long long* __rest
 
 __global__ void l2_final_kernel(const long long* __restrict__ table, const double* __restrict__ partial, int n_chunks,
                                 int n_tensors, float* __restrict__ norms, float* __restrict__ out) {
-  __shared__ float total;
-  if (threadIdx.x == 0) total = 0.f;
-  __syncthreads();
-  for (int t = threadIdx.x; t < n_tensors; t += blockDim.x) {
+  // one warp per tensor (warps stride over the tensors); lanes stride over ALL chunks and keep those of their tensor:
+  // fixed partition + fixed shuffle tree = deterministic
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < n_tensors; t += nwarps) {
     double s = 0.0;
-    for (int k = 0; k < n_chunks; ++k)
+    for (int k = lane; k < n_chunks; k += 32)
       if ((int)table[4LL * k + 2] == t) s += partial[k];
-    norms[t] = (float)sqrt(s);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) norms[t] = (float)sqrt(s);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -884,13 +902,10 @@ dice_partial_kernel(const float* __restrict__ seg, const float* __restrict__ gt,
 }
 
 __global__ void dice_final_kernel(const double* __restrict__ partial, int nblocks, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
-    s0 += partial[3 * k];
-    s1 += partial[3 * k + 1];
-    s2 += partial[3 * k + 2];
-  }
+  if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+  double s0, s1, s2;
+  warp_sum3(partial, nblocks, s0, s1, s2);
+  if (threadIdx.x != 0) return;
   out[0] = (float)(2.0 * s0 / (s1 + s2 + 1e-7));
 }
 
@@ -1019,7 +1034,7 @@ int pda_multi_tensor_l2norm_fwd(const int64_t* table, int n_chunks, int n_tensor
   if (n_chunks <= 0 || n_tensors <= 0) return PDA_ERR_SHAPE;
   PDA_COUNT(2);
   l2_partial_kernel<<<n_chunks, 256, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), partial);
-  l2_final_kernel<<<1, 128, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), partial, n_chunks, n_tensors,
+  l2_final_kernel<<<1, 1024, 0, ST(stream)>>>(reinterpret_cast<const long long*>(table), partial, n_chunks, n_tensors,
                                              norms, out);
   return LAUNCH_OK();
 }
