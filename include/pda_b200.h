@@ -145,7 +145,7 @@ int pda_augment_view(const float* img, const float* noise, float* out, int B, in
 /* Weight (+bias) gradient of conv3x3: dW[co][ci][ky][kx] = sum_p dZ[p][co] * X[p + tap][ci] on tcgen05 tensor cores
  * (K = pixels; both operands read as MN-major straight from NHWC; persistent stream-K schedule).
  * X = concat(src0, src1) as in the forward.
- * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  scratch: fp32 [cout*9*(c0+c1)].  dw_oihw fp32 OIHW,
+ * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  scratch: fp32 [cout*9*(c0+c1) + cout].  dw_oihw fp32 OIHW,
  * dbias fp32 [cout] (may be NULL).  accumulate != 0 adds to dw/dbias instead of overwriting. */
 int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
                            float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate, void* stream);

@@ -247,10 +247,17 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-// scratch [9][ctot][cout] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0)
+// scratch [9][ctot][cout] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0);
+// the bias sums accumulated behind the scratch go to dbias
 __global__ void wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot,
-                                     int accumulate) {
+                                     int accumulate, float* __restrict__ dbias) {
   const long long n = 9LL * cout * ctot;
+  if (dbias != nullptr && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+      const float v = scratch[n + c];
+      dbias[c] = accumulate ? dbias[c] + v : v;
+    }
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int tap = i % 9;
     const int ci = (i / 9) % ctot;
@@ -309,9 +316,9 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   a.n64 = cout >> 6;
   a.items = a.n64 * (ctot >> 6);
   a.scratch = scratch;
-  a.dbias = dbias;
-  if (dbias && !accumulate && cudaMemsetAsync(dbias, 0, sizeof(float) * cout, stream) != cudaSuccess)
-    return PDA_ERR_CUDA;
+  // the bias sums are accumulated in the cout floats BEHIND the weight scratch (one memset covers both) and handed to
+  // dbias by the scatter kernel
+  a.dbias = dbias ? scratch + 9ull * cout * ctot : nullptr;
   CUtensorMap tX0, tX1, tDZ;
   int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, 8, 18, 64);
   if (r) return r;
@@ -323,7 +330,7 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   }
   r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 8, 16, 64);
   if (r) return r;
-  if (cudaMemsetAsync(scratch, 0, sizeof(float) * 9ull * cout * ctot, stream) != cudaSuccess) return PDA_ERR_CUDA;
+  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (9ull * cout * ctot + cout), stream) != cudaSuccess) return PDA_ERR_CUDA;
   static int configured[64];
   if (dyn_smem_attr_needed(configured, WgradSmem::DYN_BYTES)) {
     if (cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -338,6 +345,6 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   const long long n = 9LL * cout * ctot;
   PDA_COUNT(1);
   wgrad_scatter_kernel<<<(int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256), 256, 0, stream>>>(
-      scratch, dw_oihw, cout, ctot, accumulate);
+      scratch, dw_oihw, cout, ctot, accumulate, dbias);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

@@ -220,7 +220,7 @@ def conv3x3_wgrad(src0, src1, dz, want_bias=True):
     cout = dz.shape[3]
     assert dz.shape[:3] == src0.shape[:3] and dz.is_contiguous() and src0.is_contiguous()
     dev = src0.device
-    scratch = torch.empty(cout * 9 * (c0 + c1), dtype=torch.float32, device=dev)
+    scratch = torch.empty(cout * 9 * (c0 + c1) + cout, dtype=torch.float32, device=dev)
     dw = torch.empty((cout, c0 + c1, 3, 3), dtype=torch.float32, device=dev)
     db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
     with _Timed("wgrad3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
