@@ -110,6 +110,10 @@ int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w
 /* Mean-teacher EMA over many tensors in one launch: t = t*m + p*(1-m)  (mean_teacher_trainer.py:52-55,
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
 int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, void* stream);
+/* The AdaMT form (adamt_trainer.py:40-43): momentum_t = min(1 - 1 / (iteration + 1), momentum) with the iteration count
+ * read from DEVICE memory (int64; incremented by the call), so that a CUDA graph that captured the step can be replayed. */
+int pda_multi_tensor_ema_warmup(const int64_t* table, int n_chunks, double momentum, int64_t* iteration_dev,
+                                void* stream);
 
 /* Tiled prediction driver (the reference calls torch_em.util.prediction.predict_with_halo,
  * punet_predictions.py:41-49, one block at a time from numpy).  rois / inner: device int32 [T][4] = (y0, x0, h, w) in

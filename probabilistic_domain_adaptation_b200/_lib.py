@@ -37,6 +37,7 @@ SIGNATURES = {
     "pda_image_stats": [_P, _I, _c.c_longlong, _P, _P],
     "pda_augment_view": [_P, _P, _P, _I, _I, _I, _P, _P, _F, _I, _P],
     "pda_multi_tensor_ema": [_P, _I, _c.c_double, _P],
+    "pda_multi_tensor_ema_warmup": [_P, _I, _c.c_double, _P, _P],
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear_bwd_bf16": [_P, _P, _I, _I, _I, _I, _P],

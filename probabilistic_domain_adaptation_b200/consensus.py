@@ -68,9 +68,11 @@ class MomentumUpdater:
             self._key = key
 
     @torch.no_grad()
-    def step(self, momentum):
+    def step(self, momentum, iteration_dev=None):
+        """iteration_dev: int64 device scalar -> AdaMT warm-up momentum computed (and the counter advanced) on the device,
+        which keeps a graph-captured AdaMT step replayable."""
         self._refresh()
-        ops.multi_tensor_ema(self._table, momentum)
+        ops.multi_tensor_ema(self._table, momentum, iteration_dev)
         # parameter memory changed behind autograd's back: advance the version counters (packed-weight cache key)
         from .optim import bump_versions
         from .autograd_ops import refresh_packed

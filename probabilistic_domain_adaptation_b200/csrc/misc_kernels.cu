@@ -316,7 +316,15 @@ __global__ void kl_kernel(const float* __restrict__ q, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // multi-tensor EMA: one 256-thread block per chunk of <= 65536 elements
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ema_kernel(const int64_t* __restrict__ table, float m, float om) {
+__global__ void __launch_bounds__(256) ema_kernel(const int64_t* __restrict__ table, float m, float om,
+                                                  const long long* __restrict__ iteration, double cap) {
+  if (iteration != nullptr) {
+    // AdaMT warm-up (adamt_trainer.py:41): min(1 - 1 / (iteration + 1), momentum), evaluated in double like the
+    // reference's python expression, then m and (1 - m) rounded to fp32 like ATen's scalar multiplications
+    const double md = fmin(1.0 - 1.0 / ((double)iteration[0] + 1.0), cap);
+    m = (float)md;
+    om = (float)(1.0 - md);
+  }
   const int64_t* e = table + 3LL * blockIdx.x;
   float* t = reinterpret_cast<float*>(e[0]);
   const float* s = reinterpret_cast<const float*>(e[1]);
@@ -603,7 +611,20 @@ int pda_multi_tensor_ema(const int64_t* table, int n_chunks, double momentum, vo
   if (n_chunks <= 0) return PDA_ERR_SHAPE;
   // the reference multiplies by the python doubles m and (1. - m), each rounded to fp32 by ATen
   PDA_COUNT(1);
-  ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, (float)momentum, (float)(1.0 - momentum));
+  ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, (float)momentum, (float)(1.0 - momentum), nullptr, 0.0);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+__global__ void ema_iteration_inc_kernel(long long* it) { it[0] += 1; }
+
+int pda_multi_tensor_ema_warmup(const int64_t* table, int n_chunks, double momentum, int64_t* iteration_dev,
+                                void* stream) {
+  if (!table || !iteration_dev) return PDA_ERR_ARG;
+  if (n_chunks <= 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(2);
+  ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(table, 0.f, 0.f,
+                                                         reinterpret_cast<const long long*>(iteration_dev), momentum);
+  ema_iteration_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(iteration_dev));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 

@@ -201,9 +201,16 @@ def build_ema_table(teacher_params, student_params):
     return torch.tensor(rows, dtype=torch.int64).to(dev)
 
 
-def multi_tensor_ema(table, momentum):
-    _need_cuda(table)
+def multi_tensor_ema(table, momentum, iteration_dev=None):
+    """iteration_dev (int64 device scalar): AdaMT warm-up momentum min(1 - 1/(it+1), momentum) evaluated on the device;
+    the counter is incremented by the call."""
+    _need_cuda(table, iteration_dev)
     lib = _lib.load()
+    if iteration_dev is not None:
+        assert iteration_dev.dtype == torch.int64 and iteration_dev.numel() == 1
+        _lib.check(lib.pda_multi_tensor_ema_warmup(table.data_ptr(), table.shape[0], float(momentum),
+                                                   iteration_dev.data_ptr(), _stream()), "multi_tensor_ema_warmup")
+        return
     _lib.check(lib.pda_multi_tensor_ema(table.data_ptr(), table.shape[0], float(momentum), _stream()),
                "multi_tensor_ema")
 

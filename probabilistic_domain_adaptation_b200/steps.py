@@ -145,7 +145,10 @@ def adamt_step(model, teacher, optimizer, ema, iteration, xs, ys, xt1, xt2, n_sa
     """Joint mean teacher: source ELBO + teacher pseudo-labelled target ELBO, one backward, warm-up EMA."""
     backprop = backprop or default_backprop(optimizer)
     out = _joint_step(model, teacher, optimizer, xs, ys, xt1, xt2, n_samples, do_consensus_masking, backprop, eps)
-    ema.step(consensus.adamt_momentum(iteration, momentum))
+    if torch.is_tensor(iteration):  # device-side iteration counter (advanced by the kernel): graph-capturable
+        ema.step(momentum, iteration_dev=iteration)
+    else:
+        ema.step(consensus.adamt_momentum(iteration, momentum))
     return out
 
 
@@ -166,9 +169,9 @@ class GraphedStep:
     graph (its AccumulateGrad nodes are tied to the stream they were built on; the step bodies here return detached
     losses and call `model.release_graph()` for this reason -- pass models stepped otherwise as `modules=`); `fn` must
     not synchronise with the host (no .item(); FixMatch's distribution alignment runs as a device kernel here for that
-    reason, not through torch.unique); host-side scalars are frozen at capture (EMA momentum, beta: constant in every
-    trainer except AdaMT's warm-up) except the Adam step count / learning rate, which FusedAdam(capturable=True) keeps
-    on the device.  Random draws inside `fn` (latent samples) advance per replay (torch's graph-safe generator).
+    reason, not through torch.unique); host-side scalars are frozen at capture (beta, a constant EMA momentum) except
+    the Adam step count / learning rate (FusedAdam(capturable=True)) and AdaMT's warm-up momentum (pass the iteration
+    to adamt_step as an int64 device tensor), which live on the device.  Random draws inside `fn` (latent samples) advance per replay (torch's graph-safe generator).
     The `warmup` eager calls on the first batch are REAL training steps."""
 
     def __init__(self, fn, example_inputs, optimizer=None, warmup=3, modules=()):

@@ -380,3 +380,62 @@ def test_release_graph_allows_deepcopy_after_a_step():
     assert model.posterior_latent_space.base_dist.loc.shape == (2, 6)
     clone = copy.deepcopy(model)
     assert sum(p.numel() for p in clone.parameters()) == sum(p.numel() for p in model.parameters())
+
+
+@pytest.mark.gpu
+def test_every_step_body_can_be_graph_captured():
+    """FixMatch (with distribution alignment), AdaMatch and AdaMT (device-side warm-up momentum) step bodies replay from
+    a CUDA graph: finite losses, parameters move, AdaMT's teacher follows the reference's warm-up schedule."""
+    import copy
+    from probabilistic_domain_adaptation_b200 import consensus, steps
+    from probabilistic_domain_adaptation_b200.optim import FusedAdam
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer
+    dev = _dev()
+    g = torch.Generator().manual_seed(1)
+    xs, xt1, xt2 = [torch.randn(2, 1, 64, 64, generator=g).to(dev) for _ in range(3)]
+    ys = (torch.rand(2, 1, 64, 64, generator=g) > 0.5).float().to(dev)
+    src = torch.tensor([0.7, 0.3], device=dev)
+
+    def setup():
+        model = _model(consensus_masking=True, rl_swap=True)
+        opt = FusedAdam(model.parameters(), lr=1e-4, capturable=True)
+        bp = steps.default_backprop(opt, GradAllReducer(model), model)
+        return model, opt, bp
+
+    # FixMatch with distribution alignment (no torch.unique on this path)
+    model, opt, bp = setup()
+    fm = steps.GraphedStep(lambda a, b: steps.fixmatch_step(model, opt, a, b, n_samples=4, source_distribution=src,
+                                                            backprop=bp)[0], (xt1, xt2), optimizer=opt, warmup=1)
+    before = [p.detach().clone() for p in model.parameters()]
+    losses = [float(fm(xt1, xt2)) for _ in range(3)]
+    assert all(l == l and abs(l) < 1e9 for l in losses)
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+    # AdaMatch
+    model, opt, bp = setup()
+    am = steps.GraphedStep(lambda a, b, c, d: steps.adamatch_step(model, opt, a, b, c, d, n_samples=4, backprop=bp)[0],
+                           (xs, ys, xt1, xt2), optimizer=opt, warmup=1)
+    assert all(torch.isfinite(am(xs, ys, xt1, xt2)) for _ in range(2))
+
+    # AdaMT: iteration counter on the device; momentum_t = min(1 - 1/(t+1), 0.999)
+    model, opt, bp = setup()
+    teacher = copy.deepcopy(model)
+    for p in teacher.parameters():
+        p.requires_grad = False
+    ema = consensus.MomentumUpdater(model, teacher)
+    it_dev = torch.zeros((), dtype=torch.int64, device=dev)
+    t0 = [p.detach().clone() for p in teacher.parameters()]
+    at = steps.GraphedStep(lambda a, b, c, d: steps.adamt_step(model, teacher, opt, ema, it_dev, a, b, c, d, n_samples=4,
+                                                               backprop=bp)[0],
+                           (xs, ys, xt1, xt2), optimizer=opt, warmup=1)
+    # the eager warm-up step ran with iteration 0: momentum 0 -> teacher == student (adamt_trainer.py:41)
+    assert int(it_dev) == 1
+    student_prev = [p.detach().clone() for p in model.parameters()]
+    teacher_prev = [p.detach().clone() for p in teacher.parameters()]
+    assert any(not torch.equal(a, b) for a, b in zip(t0, teacher_prev))
+    at(xs, ys, xt1, xt2)                                  # replay = iteration 1: momentum 1/2
+    assert int(it_dev) == 2
+    for tp, tn, sn in zip(teacher_prev, teacher.parameters(), model.parameters()):
+        want = tp * 0.5 + sn.detach() * 0.5
+        assert torch.allclose(tn, want, rtol=1e-6, atol=1e-8)
+    del student_prev
