@@ -40,6 +40,7 @@ def parse():
                     help="infer: MC inference leg only; train: mean-teacher step leg only")
     ap.add_argument("--train-batch", type=int, default=4, help="images per GPU per mean-teacher step (MitoEM: 4)")
     ap.add_argument("--train-size", type=int, default=512)
+    ap.add_argument("--bucket-mb", type=float, default=25.0, help="gradient all-reduce bucket size (training legs)")
     ap.add_argument("--no-graph", action="store_true", help="training legs: time the Python-launched step only")
     ap.add_argument("--no-extras", action="store_true", help="skip the S sweep and the source-training step")
     return ap.parse_args()
@@ -207,7 +208,7 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     for p in teacher.parameters():
         p.requires_grad = False
     opt = FusedAdam(model.parameters(), lr=1e-5, capturable=True)
-    reducer = GradAllReducer(model)
+    reducer = GradAllReducer(model, bucket_mb=args.bucket_mb)
     ema = consensus.MomentumUpdater(model, teacher)
     backprop = steps.default_backprop(opt, reducer, model)
     use_graph = not args.no_graph
