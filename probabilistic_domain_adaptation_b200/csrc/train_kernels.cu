@@ -99,8 +99,24 @@ relu_pool_bwd_kernel(const uint4* __restrict__ dfull, const uint4* __restrict__ 
 // backward of F.interpolate(bilinear, x2, align_corners=True) (unet_blocks.py:51), gather form:
 // every input pixel sums the output-gradient pixels whose footprint contains it (deterministic).
 // ------------------------------------------------------------------------------------------------
+// weight with which output coordinate Q (of 2n) contributes to input coordinate q (of n): the forward's own arithmetic
+__device__ __forceinline__ float up_weight(int Q, int q, int n, float r) {
+  if (Q < 0 || Q > 2 * n - 1) return 0.f;
+  const float s = r * (float)Q;
+  const int q1 = (int)s;
+  const int qp = (q1 < n - 1) ? 1 : 0;
+  const float l1 = s - q1, l0 = 1.f - l1;
+  float wgt = 0.f;
+  if (q1 == q) wgt += l0;
+  if (q1 + qp == q) wgt += l1;
+  return wgt;
+}
+
+// The six candidate columns' weights depend only on the thread's x: computed once per thread; the six row weights once
+// per row; the image index comes from blockIdx.z.  (The first version re-derived every weight for each of the 36
+// candidates of every pixel and divided by h per row: instruction-bound at 25 % of the HBM roofline.)
 __global__ void __launch_bounds__(256)
-upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int B, int h, int w, int c_shift) {
+upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, int h, int w, int c_shift) {
   const int Ho = 2 * h, Wo = 2 * w;
   const unsigned C8 = 1u << c_shift;
   const float rh = (Ho > 1) ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
@@ -109,41 +125,32 @@ upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, i
   if (xc >= (unsigned)w * C8) return;
   const int x = xc >> c_shift;
   const unsigned c = xc & (C8 - 1);
-  const int X0 = max(0, 2 * x - 2), X1 = min(Wo - 1, 2 * x + 3);
-  for (unsigned r = blockIdx.y; r < (unsigned)B * h; r += gridDim.y) {
-    const unsigned b = r / (unsigned)h;
-    const int y = r - b * h;
+  float wx[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) wx[k] = up_weight(2 * x - 2 + k, x, w, rw);
+  const uint4* gimg = dout + (((size_t)blockIdx.z * Ho * Wo) << c_shift) + c;
+  uint4* dimg = din + (((size_t)blockIdx.z * h * w) << c_shift);
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // candidate output rows / columns: source coordinate rh*Y lies in (y-1, y+1)
-    const int Y0 = max(0, 2 * y - 2), Y1 = min(Ho - 1, 2 * y + 3);
-    for (int Y = Y0; Y <= Y1; ++Y) {
-      const float sy = rh * Y;
-      const int y1 = (int)sy;
-      const int yp = (y1 < h - 1) ? 1 : 0;
-      const float ly1 = sy - y1, ly0 = 1.f - ly1;
-      float wy = 0.f;
-      if (y1 == y) wy += ly0;
-      if (y1 + yp == y) wy += ly1;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const int Y = 2 * y - 2 + a;
+      const float wy = up_weight(Y, y, h, rh);
       if (wy == 0.f) continue;
-      for (int X = X0; X <= X1; ++X) {
-        const float sx = rw * X;
-        const int x1 = (int)sx;
-        const int xp = (x1 < w - 1) ? 1 : 0;
-        const float lx1 = sx - x1, lx0 = 1.f - lx1;
-        float wx = 0.f;
-        if (x1 == x) wx += lx0;
-        if (x1 + xp == x) wx += lx1;
-        if (wx == 0.f) continue;
+      const uint4* grow = gimg + (((size_t)Y * Wo) << c_shift);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (wx[k] == 0.f) continue;
         float g[8];
-        unpack8f(__ldg(dout + ((((size_t)b * Ho + Y) * Wo + X) << c_shift) + c), g);
-        const float wgt = wy * wx;
+        unpack8f(__ldg(grow + ((size_t)(2 * x - 2 + k) << c_shift)), g);
+        const float wgt = wy * wx[k];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, g[i], acc[i]);
       }
     }
-    din[((size_t)r * w << c_shift) + xc] = pack8f(acc);
+    dimg[((size_t)y * w << c_shift) + xc] = pack8f(acc);
   }
 }
 
@@ -154,8 +161,7 @@ upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ din, i
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const __nv_bfloat16* __restrict__ out,
-                      const __nv_bfloat16* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db, int B,
-                      int H, int W, int cout) {
+                      const __nv_bfloat16* __restrict__ dout, float* __restrict__ part, int B, int H, int W, int cout) {
   extern __shared__ float red[];  // [cout * CIN * 9 + cout]
   const int groups = cout >> 3;
   const int g = threadIdx.x % groups;
@@ -173,26 +179,30 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[ci][t][j] = 0.f;
   }
-  const long long npix = (long long)B * H * W;
-  const long long pstride = (long long)gridDim.x * lanes_px;
-  long long pix = (long long)blockIdx.x * lanes_px + lpx;
+  // 32-bit pixel index (the host checks B * H * W * cout < 2^31): the three 64-bit divisions per pixel of the first
+  // version cost more instructions than the 72 FMAs they fed
+  const unsigned npix = (unsigned)B * H * W;
+  const unsigned pstride = gridDim.x * lanes_px;
+  const unsigned HW = (unsigned)H * W;
+  unsigned pix = blockIdx.x * lanes_px + lpx;
   // the two 16-byte activation loads of the NEXT pixel are issued before this pixel's 72 / 144 FMAs: with ~200
   // registers per thread only 8 warps are resident per SM, so the loads in flight per thread decide the bandwidth
   uint4 q_dz = make_uint4(0, 0, 0, 0), q_y = q_dz;
   if (pix < npix) {
-    q_dz = __ldg(reinterpret_cast<const uint4*>(dout + pix * cout + g * 8));
-    q_y = __ldg(reinterpret_cast<const uint4*>(out + pix * cout + g * 8));
+    q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)pix * cout + g * 8));
+    q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)pix * cout + g * 8));
   }
   for (; pix < npix; pix += pstride) {
-    const int x = pix % W;
-    const int y = (pix / W) % H;
-    const long long img_off = (pix / ((long long)W * H)) * H * W;
+    const unsigned img = pix / HW, rem = pix - img * HW;
+    const int y = rem / (unsigned)W;
+    const int x = rem - y * W;
+    const unsigned img_off = img * HW;
     float dz[8], yv[8];
     unpack8f(q_dz, dz);
     unpack8f(q_y, yv);
     if (pix + pstride < npix) {
-      q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (pix + pstride) * cout + g * 8));
-      q_y = __ldg(reinterpret_cast<const uint4*>(out + (pix + pstride) * cout + g * 8));
+      q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)(pix + pstride) * cout + g * 8));
+      q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)(pix + pstride) * cout + g * 8));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -208,7 +218,7 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int xx = x + kx - 1;
-          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (long long)yy * W + xx) : 0.f;
+          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + (unsigned)(yy * W + xx)) : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[ci][ky * 3 + kx][j] = fmaf(v, dz[j], acc[ci][ky * 3 + kx][j]);
         }
@@ -242,8 +252,28 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
       }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) atomicAdd(dw + i, red[i]);
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(db + i, red[cout * CIN * 9 + i]);
+  // per-block totals go to part[block][nred]; a second kernel sums the blocks in a fixed order.  (Global atomics from
+  // ~300 blocks onto the same 640 / 1216 addresses serialise in L2: ~45 us of a 160 us launch, and not deterministic.)
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) part[(size_t)blockIdx.x * nred + i] = red[i];
+}
+
+// dw[i] (i < nw) and db[i - nw] = sum over blocks of part[block][i]
+__global__ void __launch_bounds__(256)
+conv_first_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int nw, int nred, float* __restrict__ dw,
+                             float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nred) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int k = 0;
+  for (; k + 3 < nblocks; k += 4) {
+    s0 += part[(size_t)k * nred + i];
+    s1 += part[(size_t)(k + 1) * nred + i];
+    s2 += part[(size_t)(k + 2) * nred + i];
+    s3 += part[(size_t)(k + 3) * nred + i];
+  }
+  for (; k < nblocks; ++k) s0 += part[(size_t)k * nred + i];
+  const float v = (s0 + s1) + (s2 + s3);
+  if (i < nw) dw[i] = v; else db[i - nw] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -940,8 +970,11 @@ int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, 
   const long long total = (long long)B * h * w * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  upsample2x_bwd_kernel<<<row_grid((long long)w * (C / 8), (long long)B * h), 256, 0, ST(stream)>>>(
-      static_cast<const uint4*>(dout), static_cast<uint4*>(din), B, h, w, c8_shift(C));
+  if (B > 65535) return PDA_ERR_SHAPE;
+  dim3 grid = row_grid((long long)w * (C / 8), h, (148 * 8 + B - 1) / B);
+  grid.z = B;
+  upsample2x_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const uint4*>(dout), static_cast<uint4*>(din), h, w,
+                                                     c8_shift(C));
   return LAUNCH_OK();
 }
 
@@ -950,20 +983,41 @@ int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, con
   if (!x0 || !out || !dout || !dw || !db) return PDA_ERR_ARG;
   const int groups = cout >> 3;
   if (cout <= 0 || (cout & 7) || 256 % groups) return PDA_ERR_SHAPE;
+  if ((long long)B * H * W * cout >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   const int cin = x1 ? 2 : 1;
   cudaStream_t st = ST(stream);
-  if (cudaMemsetAsync(dw, 0, sizeof(float) * cout * cin * 9, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(db, 0, sizeof(float) * cout, st) != cudaSuccess) return PDA_ERR_CUDA;
-  const size_t smem = sizeof(float) * (cout * cin * 9 + cout);
+  const int nw = cout * cin * 9, nred = nw + cout;
+  const size_t smem = sizeof(float) * nred;
   const long long total = (long long)B * H * W * groups;
   const int grid = grid_cap(total, 256, 148 * 2);
-  PDA_COUNT(1);
+  // per-device grow-only scratch for the per-block partial sums (like the fcomb bias scratch: shared by the launches of
+  // this process on the device, never freed because a captured CUDA graph may still replay a launch that uses it)
+  static float* part_buf[64];
+  static size_t part_cap[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
+  const size_t need = sizeof(float) * (size_t)grid * nred;
+  if (part_cap[dev] < need) {
+    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap_state) != cudaSuccess || cap_state != cudaStreamCaptureStatusNone)
+      return PDA_ERR_CUDA;  // run one eager warm-up of this shape before capturing
+    const size_t cap = need < (4u << 20) ? (4u << 20) : need;
+    if (cudaMalloc(&part_buf[dev], cap) != cudaSuccess) {
+      part_buf[dev] = nullptr;
+      part_cap[dev] = 0;
+      return PDA_ERR_CUDA;
+    }
+    part_cap[dev] = cap;
+  }
+  float* part = part_buf[dev];
+  PDA_COUNT(2);
   if (x1)
     conv_first_bwd_kernel<2><<<grid, 256, smem, st>>>(x0, x1, static_cast<const __nv_bfloat16*>(out),
-                                                      static_cast<const __nv_bfloat16*>(dout), dw, db, B, H, W, cout);
+                                                      static_cast<const __nv_bfloat16*>(dout), part, B, H, W, cout);
   else
     conv_first_bwd_kernel<1><<<grid, 256, smem, st>>>(x0, x1, static_cast<const __nv_bfloat16*>(out),
-                                                      static_cast<const __nv_bfloat16*>(dout), dw, db, B, H, W, cout);
+                                                      static_cast<const __nv_bfloat16*>(dout), part, B, H, W, cout);
+  conv_first_bwd_reduce_kernel<<<(nred + 255) / 256, 256, 0, st>>>(part, grid, nw, nred, dw, db);
   return LAUNCH_OK();
 }
 
