@@ -248,22 +248,40 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
 }
 
 // scratch [9][ctot][cout] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0);
-// the bias sums accumulated behind the scratch go to dbias
-__global__ void wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot,
-                                     int accumulate, float* __restrict__ dbias) {
-  const long long n = 9LL * cout * ctot;
+// the bias sums accumulated behind the scratch go to dbias.
+// A 32 (ci) x 32 (co) tile with all nine taps goes through shared memory: reads are coalesced along co, and for one co
+// the 32 ci x 9 taps are 288 CONTIGUOUS floats of dW (grid: ctot / 32 x cout / 32; both are multiples of 64).
+__global__ void __launch_bounds__(256)
+wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot, int accumulate,
+                     float* __restrict__ dbias) {
+  __shared__ float tile[9][32][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (dbias != nullptr && blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < cout; c += blockDim.x) {
-      const float v = scratch[n + c];
-      dbias[c] = accumulate ? dbias[c] + v : v;
+    if (threadIdx.x < 32) {
+      const float v = scratch[9ull * cout * ctot + co0 + threadIdx.x];
+      dbias[co0 + threadIdx.x] = accumulate ? dbias[co0 + threadIdx.x] + v : v;
     }
   }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int tap = i % 9;
-    const int ci = (i / 9) % ctot;
-    const int co = i / (9LL * ctot);
-    const float v = scratch[((long long)tap * ctot + ci) * cout + co];
-    dw[i] = accumulate ? dw[i] + v : v;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci_l = warp + 8 * k;
+      tile[tap][ci_l][lane] = scratch[(static_cast<size_t>(tap) * ctot + ci0 + ci_l) * cout + co0 + lane];
+    }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co_l = warp + 8 * k;
+    float* dst = dw + (static_cast<size_t>(co0 + co_l) * ctot + ci0) * 9;
+#pragma unroll
+    for (int e0 = 0; e0 < 288; e0 += 32) {
+      const int e = e0 + lane;
+      const int ci_l = e / 9, tap = e - 9 * ci_l;
+      const float v = tile[tap][ci_l][co_l];
+      dst[e] = accumulate ? dst[e] + v : v;
+    }
   }
 }
 
@@ -342,9 +360,7 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   PDA_COUNT(1);
   wgrad3x3_tc_kernel<<<grid, 192, WgradSmem::DYN_BYTES, stream>>>(tX0, tX1, tDZ, a);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
-  const long long n = 9LL * cout * ctot;
   PDA_COUNT(1);
-  wgrad_scatter_kernel<<<(int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256), 256, 0, stream>>>(
-      scratch, dw_oihw, cout, ctot, accumulate, dbias);
+  wgrad_scatter_kernel<<<dim3(ctot / 32, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, cout, ctot, accumulate, dbias);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
