@@ -63,6 +63,20 @@ __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __re
 // 18 (36) input loads and 18 (36) 128-bit shared-memory weight reads feed 288 (576) FMAs; the 8 threads of a pixel
 // write one contiguous 128-byte line.  All index math is 32-bit, one division per 4 pixels.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ w,
@@ -86,11 +100,13 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
     const unsigned row = q / quads_per_row;        // = b * H + y
     const int xq = (int)(q - row * quads_per_row) << 2;
     const int y = (int)(row % (unsigned)H);
-    float acc[4][8];
+    // accumulators as packed fp32 pairs: the kernel is bound by the FMA pipe (9 x 64 FMAs per pixel = 0.13 ms for
+    // 4 x 1024^2 at 64 FMA/clk/SM), and one FFMA2 retires two of them (bit-identical to the scalar FMAs)
+    uint64_t acc2[4][4];
 #pragma unroll
     for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[px][j] = bsm[g * 8 + j];
+      for (int j = 0; j < 4; ++j) acc2[px][j] = pack_f32x2(bsm[g * 8 + 2 * j], bsm[g * 8 + 2 * j + 1]);
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
       const float* plane = (ci == 0 ? x0 : x1) + (size_t)(row - y) * W;  // start of image b
@@ -109,11 +125,14 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
         for (int kx = 0; kx < 3; ++kx) {
           const float4 wa = *reinterpret_cast<const float4*>(wsm + (ci * 9 + ky * 3 + kx) * cout + g * 8);
           const float4 wb = *reinterpret_cast<const float4*>(wsm + (ci * 9 + ky * 3 + kx) * cout + g * 8 + 4);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          const uint64_t w2[4] = {pack_f32x2(wa.x, wa.y), pack_f32x2(wa.z, wa.w), pack_f32x2(wb.x, wb.y),
+                                  pack_f32x2(wb.z, wb.w)};
 #pragma unroll
-          for (int px = 0; px < 4; ++px)
+          for (int px = 0; px < 4; ++px) {
+            const uint64_t v2 = pack_f32x2(in[px + kx], in[px + kx]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(in[px + kx], wv[j], acc[px][j]);
+            for (int j = 0; j < 4; ++j) acc2[px][j] = fma_f32x2(v2, w2[j], acc2[px][j]);
+          }
         }
       }
     }
@@ -121,7 +140,9 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (xq + px < W) {
-        float* a = acc[px];
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack_f32x2(acc2[px][j], a[2 * j], a[2 * j + 1]);
         if (relu) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
