@@ -94,11 +94,17 @@ int pda_kl_diag_gauss(const float* mu_logsigma_q, const float* mu_logsigma_p, fl
  *   w1 [64][64+L] (first 64 input channels = features, last L = z), b1[64], w2[64][64], b2[64], w3[64], b3[1]: fp32.
  * Outputs (any may be NULL): mean_prob [B][P] fp32 = sum_s sigmoid(logit_s) / S;
  *   cons_weight [B][P] fp32 = #{s: p_s >= upper or p_s <= lower} / S;  cons_mask [B][P] int64 = (count == S);
- *   logits / probs [S][B][P] fp32 (per-sample, for sample()/reconstruct() and the parity tests). */
+ *   logits / probs [S][B][P] fp32 (per-sample, for sample()/reconstruct() and the parity tests).
+ * scratch: caller-allocated fp32 [pda_fcomb_scratch_floats(S, B)], private to this call (no state is shared between
+ *   launches, streams or CUDA graphs).  Word 0 is the fp16 RANGE FLAG (int): the hidden layer runs in packed fp16;
+ *   when |F.W1f| or |b1 + W1z.z| reaches 32000 anywhere in the batch the flag is raised on the device and the same
+ *   call re-computes every output with the exact fp32 kernel below (no host synchronisation).  Pass the same scratch
+ *   to pda_fcomb_bwd so that the backward follows the path the forward took. */
+long long pda_fcomb_scratch_floats(int S, int B);
 int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
                            float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
-                           float* logits, float* probs, void* stream);
+                           float* logits, float* probs, float* scratch, void* stream);
 
 /* Same contract in exact-order fp32 on CUDA cores (no bf16 rounding of weights / hidden activations): the
  * numerics baseline of the tensor-core kernel above.  ~20x slower; selected explicitly by the caller only. */
@@ -163,9 +169,11 @@ int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, 
 /* Backward of the bilinear x2 upsample (unet_blocks.py:51): dout (2h,2w) -> din (h,w), NHWC bf16. */
 int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream);
 
-/* First layer (cin 1 or 2) weight/bias gradient; out = forward output (for the ReLU mask), dout its gradient. */
+/* First layer (cin 1 or 2) weight/bias gradient; out = forward output (for the ReLU mask), dout its gradient.
+ * scratch: caller-allocated fp32 [pda_conv3x3_first_bwd_scratch_floats(...)] for the per-block partial sums. */
+long long pda_conv3x3_first_bwd_scratch_floats(int B, int H, int W, int cout, int cin);
 int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,
-                          int B, int H, int W, int cout, void* stream);
+                          int B, int H, int W, int cout, float* scratch, void* stream);
 
 /* Gaussian head: spatial mean [B][C] from the forward's stage-1 scratch, and the backward to the encoder output. */
 int pda_gauss_head_mean(const float* scratch, float* mean, int B, int P, int C, void* stream);
@@ -201,10 +209,14 @@ int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const f
                                 void* grad_base, void* stream);
 
 /* Fcomb backward for one latent sample z [B][L]: dlogit [B][P] -> dfeat [B][P][64] bf16, parameter grads, dz [B][L].
- * Five chained tcgen05 GEMMs per 128-pixel tile (bf16 operands, fp32 accumulate).  scratch: fp32 [64*64 + 2*B*64]. */
+ * Five chained tcgen05 GEMMs per 128-pixel tile (bf16 operands, fp32 accumulate).  scratch: fp32 [64*64 + 2*B*64].
+ * fwd_range_flag: word 0 of the scratch the forward call (pda_fcomb_mc_consensus, S = 1) used, or NULL.  When the
+ *   forward raised its fp16 range flag, the tensor-core kernel steps aside and the exact fp32 kernel computes the
+ *   gradients of the function that was actually evaluated (decided on the device). */
 int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
-                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream);
+                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, const int* fwd_range_flag,
+                  void* stream);
 
 /* Same contract in exact-order fp32 on CUDA cores: the numerics baseline of the tensor-core kernel above (~10x
  * slower; explicit opt-in only).  scratch: fp32 [64*64 + B*64]. */

@@ -255,6 +255,24 @@ def sample_from_teacher(sd, x, eps, do_consensus_masking=False, **kw):
     return consensus_from_probs(probs, do_consensus_masking=do_consensus_masking) + (logits,)
 
 
+def pseudo_labels_from_probs(probs, upper_threshold=0.9, lower_threshold=0.1):
+    """punet_predictions.py:113-124 on a stack of probabilities (S, 1, 1, H, W): the mean over the samples and the
+    consensus MASK, computed per sample with numpy on the host exactly as there (`>=` / `<=` on float32 arrays against
+    Python floats, bool `+` = OR, sum / S == 1).  Returns (mypred float32 (H, W), consensus_mask uint8 (H, W))."""
+    import numpy as np
+    n = probs.shape[0]
+    samples = list(probs)
+    mypred = torch.stack(samples, dim=0).sum(dim=0) / n                      # :113
+    mypred = mypred.detach().cpu().numpy().squeeze()                         # :114
+    masks = []
+    for sample in samples:                                                   # :116-120
+        sample = sample.detach().cpu().numpy().squeeze()
+        masks.append((sample >= upper_threshold) + (sample <= lower_threshold))
+    consensus_mask = np.stack(masks, axis=0).sum(axis=0) / n                 # :123
+    consensus_mask = np.where(consensus_mask == 1, 1, 0)                     # :124
+    return mypred, consensus_mask.astype("uint8")                            # :135
+
+
 def momentum_update(teacher_sd, student_sd, momentum=0.999):
     """mean_teacher_trainer.py:52-55: t = t * m + p * (1 - m), per tensor, fp32."""
     return {k: teacher_sd[k] * momentum + student_sd[k] * (1.0 - momentum) for k in teacher_sd}

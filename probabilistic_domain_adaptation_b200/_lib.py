@@ -30,7 +30,8 @@ SIGNATURES = {
     "pda_gauss_head": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_latent_samples": [_P, _P, _P, _I, _I, _I, _P],
     "pda_kl_diag_gauss": [_P, _P, _P, _I, _I, _P],
-    "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
+    "pda_fcomb_scratch_floats": [_I, _I],
+    "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     "pda_tile_gather_standardize": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P],
     "pda_tile_scatter": [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P],
@@ -41,7 +42,8 @@ SIGNATURES = {
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear_bwd_bf16": [_P, _P, _I, _I, _I, _I, _P],
-    "pda_conv3x3_first_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "pda_conv3x3_first_bwd_scratch_floats": [_I, _I, _I, _I, _I],
+    "pda_conv3x3_first_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "pda_gauss_head_mean": [_P, _P, _I, _I, _I, _P],
     "pda_gauss_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_kl_diag_gauss_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
@@ -55,10 +57,11 @@ SIGNATURES = {
                               _P, _P, _P],
     "pda_distribution_alignment": [_P, _c.c_longlong, _P, _P, _P, _P, _P],
     "pda_multi_tensor_adam_capturable": [_P, _I, _P, _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P, _P, _P, _P],
-    "pda_fcomb_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pda_fcomb_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pda_fcomb_bwd_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
-_RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None}
+_RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None,
+             "pda_fcomb_scratch_floats": _c.c_longlong, "pda_conv3x3_first_bwd_scratch_floats": _c.c_longlong}
 
 _lib = None
 

@@ -25,7 +25,8 @@ NVCC_FLAGS = [
 def _digest():
     h = hashlib.sha256()
     root = os.path.dirname(PKG)
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(root, "include", "pda_b200.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(root, "include", "pda_b200.h"))
     for f in files:
         with open(f, "rb") as fh:
             h.update(f.encode())

@@ -34,7 +34,13 @@ int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long 
 
 int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, const float* dlogit, int B, int P, int L, void* dfeat, float* dw1f, float* dw2,
-                 float* db2, float* dw3, float* db3, float* dbz, float* bz, cudaStream_t st);
+                 float* db2, float* dw3, float* db3, float* dbz, float* bz, const int* skip_flag, cudaStream_t st);
+
+// exact fp32 Fcomb + consensus (csrc/fcomb.cu); run_flag != nullptr: only runs when *run_flag != 0 (device-side)
+int fcomb_mc_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* w3, const float* b3, int B, int P, int S, int latent, float upper, float lower,
+                  float* mean_prob, float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
+                  const int* run_flag, cudaStream_t stream);
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,

@@ -40,13 +40,11 @@ struct FbSmem {
   static constexpr int BAR = ONES + 1024;         // 2 x (mbarF, mbarM)
   static constexpr int SLOT = BAR + 4 * 8;
   static constexpr int BZ = SLOT + 16;            // [2][64] fp32
-  static constexpr int RED = BZ + 2 * 64 * 4;     // dW3 reduction [64] + db3 [1]
-  static constexpr int TOTAL = RED + 65 * 4;
+  static constexpr int RED = BZ + 2 * 64 * 4;     // dW3 reduction [64] + db3 [1] (padded to 68 floats)
+  static constexpr int W3 = RED + 68 * 4;         // last layer w3[64] fp32 (per-launch copy: no process-wide state)
+  static constexpr int TOTAL = W3 + 64 * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
-
-// last Fcomb layer (w3[64]) as constant-bank operands; refreshed by every launch (stream-ordered D2D copy)
-__constant__ float c_fb_w3[FB_C];
 
 __device__ __forceinline__ uint32_t fb_pack2(float lo, float hi) { return pack_bf16x2(lo, hi); }
 
@@ -90,11 +88,14 @@ __device__ __forceinline__ void fb_named_bar(int id) { asm volatile("bar.sync %0
 __global__ void __launch_bounds__(256, 1)
 fcomb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ bzg,
                     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ b2,
+                    const float* __restrict__ w3, const int* __restrict__ skip_flag,
                     const float* __restrict__ dlogit, int P, int L, int B, int tiles_per_img, int num_tiles,
                     __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw1f, float* __restrict__ dw2,
                     float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3,
                     float* __restrict__ dbz) {
   using M = FbSmem;
+  // the forward took the fp32 path (fp16 range flag): the fp32 backward kernel produces the gradients instead
+  if (skip_flag != nullptr && *skip_flag != 0) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -106,6 +107,7 @@ fcomb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __rest
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + M::SLOT);
   float* bzs = reinterpret_cast<float*>(smem + M::BZ) + 64 * wg;
   float* red = reinterpret_cast<float*>(smem + M::RED);
+  const float4* w3s = reinterpret_cast<const float4*>(smem + M::W3);
   uint8_t* tiles = smem + wg * M::WG_BYTES;
   const uint32_t tiles_u32 = sbase + wg * M::WG_BYTES;
   const int kin = FB_C + L;
@@ -141,6 +143,7 @@ fcomb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __rest
     *reinterpret_cast<uint4*>(smem + M::ONES + tid * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   }
   if (tid < 65) red[tid] = 0.f;
+  if (tid >= 128 && tid < 128 + FB_C) reinterpret_cast<float*>(smem + M::W3)[tid - 128] = w3[tid - 128];
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -285,12 +288,14 @@ fcomb_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __rest
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float x[8];
+        const float4 wa = w3s[half * 8 + 2 * c], wb = w3s[half * 8 + 2 * c + 1];  // warp-wide broadcast reads
+        const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int j = half * 32 + 8 * c + e;
           const float h2 = __uint_as_float(v[8 * c + e]);
           acc3[j] = fmaf(g, fmaxf(h2, 0.f), acc3[j]);
-          x[e] = h2 > 0.f ? g * c_fb_w3[j] : 0.f;
+          x[e] = h2 > 0.f ? g * w8[e] : 0.f;
         }
         *reinterpret_cast<uint4*>(rowDH2 + (((half * 4 + c) ^ sw) << 4)) =
             make_uint4(fb_pack2(x[0], x[1]), fb_pack2(x[2], x[3]), fb_pack2(x[4], x[5]), fb_pack2(x[6], x[7]));
@@ -410,7 +415,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // Launches the tensor-core backward.  bz: fp32 [B][64] scratch.  The accumulation targets must be zero-initialised.
 int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
                  const float* b2, const float* w3, const float* dlogit, int B, int P, int L, void* dfeat, float* dw1f,
-                 float* dw2, float* db2, float* dw3, float* db3, float* dbz, float* bz, cudaStream_t st) {
+                 float* dw2, float* db2, float* dw3, float* db3, float* dbz, float* bz, const int* skip_flag,
+                 cudaStream_t st) {
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   if (!enc) return PDA_ERR_DRIVER;
   CUtensorMap tm;
@@ -422,8 +428,6 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PDA_ERR_TENSORMAP;
-  if (cudaMemcpyToSymbolAsync(c_fb_w3, w3, sizeof(float) * FB_C, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-    return PDA_ERR_CUDA;
   static int configured[64];
   if (dyn_smem_attr_needed(configured, FbSmem::DYN_BYTES)) {
     if (cudaFuncSetAttribute(fcomb_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::DYN_BYTES) !=
@@ -436,7 +440,7 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
   const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
   PDA_COUNT(2);
   fb_bz_kernel<<<(B * FB_C + 255) / 256, 256, 0, st>>>(z, w1, b1, bz, B, L);
-  fcomb_bwd_tc_kernel<<<grid, 256, FbSmem::DYN_BYTES, st>>>(tm, bz, w1, w2, b2, dlogit, P, L, B, tiles_per_img,
+  fcomb_bwd_tc_kernel<<<grid, 256, FbSmem::DYN_BYTES, st>>>(tm, bz, w1, w2, b2, w3, skip_flag, dlogit, P, L, B, tiles_per_img,
                                                             (int)num_tiles, static_cast<__nv_bfloat16*>(dfeat), dw1f,
                                                             dw2, db2, dw3, db3, dbz);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;

@@ -15,7 +15,7 @@
 // bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat (fcomb_bz_kernel).
 //
 // Warp-specialised persistent CTA (2 per SM): warps 0-3 = producers (own H1 in registers, write the A1 ring),
-// warps 4-7 = epilogue (TMEM -> relu -> w3 dot with w3 as constant-bank operands -> sigmoid / counters),
+// warps 4-7 = epilogue (TMEM -> relu -> w3 dot with w3 held in registers -> sigmoid / counters),
 // warp 8 = control (TMA of the feature tile, all tcgen05.mma).  Three mbarrier pipelines (F tile, A1 ring of 2 and
 // H2 accumulator ring of 2, both in TMEM) let the three roles run concurrently; nothing but the outputs leaves the SM.
 // Measured (profiles/r01e_fcomb_variants.md): 1.62 ms -> 0.99 ms at 4 x 1024^2 px, S = 16 against the version that
@@ -34,9 +34,15 @@ constexpr int FC_A1_STAGES = 2;
 constexpr int FC_A1_COL = 3 * FCT;
 constexpr int FC_THREADS = 288;
 
-// last Fcomb layer as constant-bank operands of the epilogue FFMAs: w3[64], b3.  Refreshed (stream-ordered D2D copy)
-// by every launch; launches that use DIFFERENT weights must therefore not overlap on different streams.
-__constant__ float c_fcomb_w3[FCT + 4];
+// |H1| and |bz| below this bound cannot overflow the packed-fp16 add relu(H1 + bz) (2 x 32000 < 65504); a launch that
+// sees a larger value raises the overflow flag and the caller's stream re-runs the batch through the exact fp32 kernel
+constexpr float FC_F16_SAFE = 32000.f;
+
+// last layer w3[64]: the first FC_W3_REG entries live in the epilogue threads' registers, the rest is read from shared
+// memory as warp-wide broadcast LDS.128 (the 96-register cap of 2 CTAs/SM does not leave room for all 64: 48 is the most ptxas allocates without spilling)
+#ifndef FC_W3_REG
+#define FC_W3_REG 48
+#endif
 
 struct FcombSmem {
   static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 x 2 B
@@ -51,7 +57,8 @@ struct FcombSmem {
   static constexpr int NBARS = 4 + 2 * FC_A1_STAGES + 4;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BZ_CHUNK = 64;                           // samples whose layer-1 bias is staged at a time
-  static constexpr int BZ_OFF = SLOT_OFF + 16;                  // bz[BZ_CHUNK][64] fp16
+  static constexpr int W3_OFF = SLOT_OFF + 16;                  // w3[64] fp32 (per-launch copy)
+  static constexpr int BZ_OFF = W3_OFF + FCT * 4;               // bz[BZ_CHUNK][64] fp16
   static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 2 + 1024; }
 };
 
@@ -124,7 +131,8 @@ __device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo
 
 __global__ void __launch_bounds__(FC_THREADS, 2)
 fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ bzg, const float* __restrict__ w1,
-                const float* __restrict__ w2, const float* __restrict__ b2, int P, int S, int L, int B,
+                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                const float* __restrict__ b3, int* __restrict__ oflag, int P, int S, int L, int B,
                 int tiles_per_img, int num_tiles, float upper, float lower, float* __restrict__ mean_prob,
                 float* __restrict__ cons_weight, int64_t* __restrict__ cons_mask, float* __restrict__ logits,
                 float* __restrict__ probs) {
@@ -177,6 +185,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     }
     *reinterpret_cast<uint4*>(smem + M::W2X_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
+  if (tid >= 64 && tid < 64 + FCT) reinterpret_cast<float*>(smem + M::W3_OFF)[tid - 64] = w3[tid - 64];
   if (tid < 64) {
     const int n = tid >> 3, c = tid & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -215,16 +224,21 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
       uint32_t h1[FCT / 2];
+      float hmax = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
         tmem_ld32(lane_addr + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 16; ++i) {
           h1[16 * half + i] = pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          hmax = fmaxf(hmax, fmaxf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
+        }
       }
       tc_fence_before();
+      // fp16 range guard (once per tile): "not below the bound" also catches NaN
+      if (__any_sync(0xffffffffu, !(hmax < FC_F16_SAFE)) && lane == 0) atomicOr(oflag, 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(h1_empty);
       for (int s = 0; s < S; ++s, ++a_it) {
@@ -256,6 +270,16 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     const int prow = q * 32 + lane;  // pixel row of this thread inside the tile
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t e_it = 0;
+    // last layer (w3[64], b3) lives in registers for the whole kernel: per-launch state only (an earlier version kept
+    // it in a __constant__ bank shared by every launch of the process, which let concurrent streams race)
+    float w3r[FC_W3_REG > 0 ? FC_W3_REG : 4];
+#pragma unroll
+    for (int i = 0; i < FC_W3_REG / 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(w3) + i);
+      w3r[4 * i] = t.x; w3r[4 * i + 1] = t.y; w3r[4 * i + 2] = t.z; w3r[4 * i + 3] = t.w;
+    }
+    const float b3r = __ldg(b3);
+    const uint32_t w3s_addr = sbase + M::W3_OFF;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int pix = (tile - b * tiles_per_img) * FC_TILE + prow;
@@ -267,24 +291,32 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         const uint32_t hb = e_it & 1;
         mbar_wait(h2_full(hb), (e_it >> 1) & 1);
         tc_fence_after();
-        float l0 = c_fcomb_w3[FCT], l1 = 0.f, l2 = 0.f, l3 = 0.f;  // b3 + four independent chains
+        float l0 = b3r, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // b3 + four independent chains
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + FCT + hb * FCT + half * 32, v);
+        for (int part = 0; part < 4; ++part) {
+          uint32_t v[16];
+          tmem_ld16(lane_addr + FCT + hb * FCT + part * 16, v);
           tmem_ld_wait();
-          if (half == 1) {
-            // both halves are in registers: the accumulator buffer can be overwritten
+          if (part == 3) {
+            // all four quarters are in registers: the accumulator buffer can be overwritten
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(h2_empty(hb));
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            l0 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 0], fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), l0);
-            l1 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 1], fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), l1);
-            l2 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 2], fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), l2);
-            l3 = fmaf(c_fcomb_w3[half * 32 + 4 * i + 3], fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), l3);
+          for (int i = 0; i < 4; ++i) {
+            const int j = part * 16 + 4 * i;
+            float wa, wb, wc, wd;
+            if (j < FC_W3_REG) {
+              wa = w3r[j]; wb = w3r[j + 1]; wc = w3r[j + 2]; wd = w3r[j + 3];
+            } else {
+              const uint4 t = lds128(w3s_addr + 4 * j);
+              wa = __uint_as_float(t.x); wb = __uint_as_float(t.y); wc = __uint_as_float(t.z); wd = __uint_as_float(t.w);
+            }
+            l0 = fmaf(wa, fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), l0);
+            l1 = fmaf(wb, fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), l1);
+            l2 = fmaf(wc, fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), l2);
+            l3 = fmaf(wd, fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), l3);
           }
         }
         const float logit = (l0 + l1) + (l2 + l3);
@@ -376,15 +408,22 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   if (warp == 8) tmem_dealloc(tmem, FC_TMEM_COLS);
 }
 
-// bz[s][b][j] = b1[j] + sum_d W1[j][64 + d] * z[s][b][d]: the per-(sample, image) bias that replaces the tiled-z concat
-__global__ void fcomb_bz_kernel(const float* __restrict__ z, const float* __restrict__ w1, const float* __restrict__ b1,
-                                float* __restrict__ bz, int SB, int L) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= SB * FCT) return;
-  const int sb = i / FCT, j = i - sb * FCT;
-  float acc = b1[j];
-  for (int d = 0; d < L; ++d) acc = fmaf(w1[j * (FCT + L) + FCT + d], z[sb * L + d], acc);
-  bz[i] = acc;
+// bz[s][b][j] = b1[j] + sum_d W1[j][64 + d] * z[s][b][d]: the per-(sample, image) bias that replaces the tiled-z concat.
+// ONE block, so that the same launch can also (re)initialise the overflow flag: *oflag = any |bz| outside the fp16-safe
+// range (no separate memset; the tensor-core kernel ORs its own H1 range check into it afterwards).
+__global__ void __launch_bounds__(1024)
+fcomb_bz_kernel(const float* __restrict__ z, const float* __restrict__ w1, const float* __restrict__ b1,
+                float* __restrict__ bz, int SB, int L, int* __restrict__ oflag) {
+  int over = 0;
+  for (int i = threadIdx.x; i < SB * FCT; i += blockDim.x) {
+    const int sb = i / FCT, j = i - sb * FCT;
+    float acc = b1[j];
+    for (int d = 0; d < L; ++d) acc = fmaf(w1[j * (FCT + L) + FCT + d], z[sb * L + d], acc);
+    bz[i] = acc;
+    over |= !(fabsf(acc) < FC_F16_SAFE);
+  }
+  over = __syncthreads_or(over);
+  if (threadIdx.x == 0) *oflag = over ? 1 : 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -395,13 +434,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 using namespace pda;
 
+// scratch (fp32 words, caller-allocated per call -> no state shared between launches / streams / graphs):
+// [0] overflow flag (int), [4 ..) bz[S][B][64]
+extern "C" long long pda_fcomb_scratch_floats(int S, int B) { return 4 + (long long)S * B * FCT; }
+
 extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1,
                                       const float* w2, const float* b2, const float* w3, const float* b3, int B, int P,
                                       int S, int latent, float upper, float lower, float* mean_prob,
                                       float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
-                                      void* stream) {
-  if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) return PDA_ERR_ARG;
+                                      float* scratch, void* stream) {
+  if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !scratch) return PDA_ERR_ARG;
   if (B <= 0 || P <= 0 || S <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  if (S > 640) return PDA_ERR_SHAPE;  // the fp32 range-guard fallback stages bz[S][64] fp32 in shared memory
   const int smem = FcombSmem::bytes(S);
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
   if (!enc) return PDA_ERR_DRIVER;
@@ -415,11 +459,6 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PDA_ERR_TENSORMAP;
   cudaStream_t st = (cudaStream_t)stream;
-  // last layer -> constant bank (stream-ordered device-to-device copies)
-  if (cudaMemcpyToSymbolAsync(c_fcomb_w3, w3, sizeof(float) * FCT, 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
-      cudaMemcpyToSymbolAsync(c_fcomb_w3, b3, sizeof(float), sizeof(float) * FCT, cudaMemcpyDeviceToDevice, st) !=
-          cudaSuccess)
-    return PDA_ERR_CUDA;
   static int configured[64];
   if (dyn_smem_attr_needed(configured, smem)) {
     if (cudaFuncSetAttribute(fcomb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -427,38 +466,23 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   }
   const int tiles_per_img = (P + FC_TILE - 1) / FC_TILE;
   const long long num_tiles = (long long)tiles_per_img * B;
-  if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
+  if (num_tiles > 0x7fffffffLL || (long long)S * B * FCT > 0x7fffffffLL) return PDA_ERR_SHAPE;
   // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise)
-  // (2 CTAs of 288 threads x 96 registers and 2 x 256 TMEM columns fit; shared memory decides)
+  // (2 CTAs of 288 threads and 2 x 256 TMEM columns fit; shared memory decides)
   int per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm < 1) return PDA_ERR_SHAPE;
   if (per_sm > 2) per_sm = 2;
   const int grid = (int)(num_tiles < 148 * per_sm ? num_tiles : 148 * per_sm);
-  // per-device grow-only scratch for bz[S][B][64] (no allocator call on the hot path; like the constant-bank copy of
-  // w3 it is shared by all launches of this process on the device: launches on different streams must not overlap)
-  static float* bz_buf[64];
-  static size_t bz_cap[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
-  const size_t need = sizeof(float) * (size_t)S * B * FCT;
-  if (bz_cap[dev] < need) {
-    // grow-only, and the outgrown buffer is deliberately NOT freed: a CUDA graph captured earlier may still replay a
-    // launch that writes it (a few KB per growth step; sizes below 1 MB = S * B <= 4096 never grow at all)
-    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cap_state) != cudaSuccess) return PDA_ERR_CUDA;
-    if (cap_state != cudaStreamCaptureStatusNone) return PDA_ERR_CUDA;  // run one eager warm-up of this shape first
-    const size_t cap = need < (1u << 20) ? (1u << 20) : need;
-    if (cudaMalloc(&bz_buf[dev], cap) != cudaSuccess) {
-      bz_buf[dev] = nullptr;
-      bz_cap[dev] = 0;
-      return PDA_ERR_CUDA;
-    }
-    bz_cap[dev] = cap;
-  }
-  float* bz = bz_buf[dev];
+  int* oflag = reinterpret_cast<int*>(scratch);
+  float* bz = scratch + 4;
   PDA_COUNT(2);
-  fcomb_bz_kernel<<<(S * B * FCT + 255) / 256, 256, 0, st>>>(z, w1, b1, bz, S * B, latent);
-  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, P, S, latent, B, tiles_per_img, (int)num_tiles,
-                                                  upper, lower, mean_prob, cons_weight, cons_mask, logits, probs);
-  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+  fcomb_bz_kernel<<<1, 1024, 0, st>>>(z, w1, b1, bz, S * B, latent, oflag);
+  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, w3, b3, oflag, P, S, latent, B, tiles_per_img,
+                                                  (int)num_tiles, upper, lower, mean_prob, cons_weight, cons_mask,
+                                                  logits, probs);
+  if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
+  // fp16 range guard: when the flag is up, the exact fp32 kernel overwrites every output of this call (device-side
+  // decision, no host synchronisation; its blocks exit at once otherwise)
+  return fcomb_mc_fp32(feat, z, w1, b1, w2, b2, w3, b3, B, P, S, latent, upper, lower, mean_prob, cons_weight,
+                       cons_mask, logits, probs, oflag, st);
 }

@@ -561,7 +561,10 @@ fcomb_bwd_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict
                  const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                  const float* __restrict__ w3, const float* __restrict__ dlogit, int P, int L, int B, int tiles_per_img,
                  int num_tiles, __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dw1f, float* __restrict__ dw2,
-                 float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3, float* __restrict__ dbz) {
+                 float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3, float* __restrict__ dbz,
+                 const int* __restrict__ run_flag) {
+  // run_flag != nullptr: fallback of the tensor-core backward, runs only when the forward raised its fp16 range flag
+  if (run_flag != nullptr && *run_flag == 0) return;
   extern __shared__ __align__(16) float sm[];
   float* w1s = sm;                       // [64][64]
   float* w2s = w1s + FB * FB;            // [64][64]
@@ -978,9 +981,18 @@ int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, 
   return LAUNCH_OK();
 }
 
+static int first_bwd_grid(int B, int H, int W, int cout) {
+  return grid_cap((long long)B * H * W * (cout >> 3), 256, 148 * 2);
+}
+
+long long pda_conv3x3_first_bwd_scratch_floats(int B, int H, int W, int cout, int cin) {
+  if (B <= 0 || H <= 0 || W <= 0 || cout <= 0 || cin <= 0) return 0;
+  return (long long)first_bwd_grid(B, H, W, cout) * (cout * cin * 9 + cout);
+}
+
 int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,
-                          int B, int H, int W, int cout, void* stream) {
-  if (!x0 || !out || !dout || !dw || !db) return PDA_ERR_ARG;
+                          int B, int H, int W, int cout, float* scratch, void* stream) {
+  if (!x0 || !out || !dout || !dw || !db || !scratch) return PDA_ERR_ARG;
   const int groups = cout >> 3;
   if (cout <= 0 || (cout & 7) || 256 % groups) return PDA_ERR_SHAPE;
   if ((long long)B * H * W * cout >= 0x7fffffffLL) return PDA_ERR_SHAPE;
@@ -988,28 +1000,9 @@ int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, con
   cudaStream_t st = ST(stream);
   const int nw = cout * cin * 9, nred = nw + cout;
   const size_t smem = sizeof(float) * nred;
-  const long long total = (long long)B * H * W * groups;
-  const int grid = grid_cap(total, 256, 148 * 2);
-  // per-device grow-only scratch for the per-block partial sums (like the fcomb bias scratch: shared by the launches of
-  // this process on the device, never freed because a captured CUDA graph may still replay a launch that uses it)
-  static float* part_buf[64];
-  static size_t part_cap[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
-  const size_t need = sizeof(float) * (size_t)grid * nred;
-  if (part_cap[dev] < need) {
-    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cap_state) != cudaSuccess || cap_state != cudaStreamCaptureStatusNone)
-      return PDA_ERR_CUDA;  // run one eager warm-up of this shape before capturing
-    const size_t cap = need < (4u << 20) ? (4u << 20) : need;
-    if (cudaMalloc(&part_buf[dev], cap) != cudaSuccess) {
-      part_buf[dev] = nullptr;
-      part_cap[dev] = 0;
-      return PDA_ERR_CUDA;
-    }
-    part_cap[dev] = cap;
-  }
-  float* part = part_buf[dev];
+  const int grid = first_bwd_grid(B, H, W, cout);
+  // per-block partial sums live in the caller's per-call scratch (no state shared between launches or streams)
+  float* part = scratch;
   PDA_COUNT(2);
   if (x1)
     conv_first_bwd_kernel<2><<<grid, 256, smem, st>>>(x0, x1, static_cast<const __nv_bfloat16*>(out),
@@ -1103,26 +1096,74 @@ int pda_multi_tensor_l2norm_bwd(const int64_t* grad_table, int n_chunks, const f
   return LAUNCH_OK();
 }
 
+// zero-fills up to five fp32 buffers in ONE launch (the accumulation targets of the Fcomb backward)
+struct ZeroList {
+  float* p[5];
+  int n[5];
+};
+__global__ void __launch_bounds__(256) zero_list_kernel(ZeroList zl) {
+  float* p = zl.p[blockIdx.y];
+  const int n = zl.n[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+static int fcomb_bwd_fp32_launch(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
+                                 const float* b2, const float* w3, const float* dlogit, int B, int P, int latent,
+                                 void* dfeat, float* dw1f, float* dw2, float* db2, float* dw3, float* db3, float* dbz,
+                                 const int* run_flag, cudaStream_t st) {
+  const int smem = sizeof(float) * (2 * FB * FB + 4 * 128 * FB_LD + 320);
+  static int configured[64];
+  if (dyn_smem_attr_needed(configured, smem)) {
+    if (cudaFuncSetAttribute(fcomb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return PDA_ERR_CUDA;
+  }
+  const int tiles_per_img = (P + 127) / 128;
+  const long long num_tiles = (long long)tiles_per_img * B;
+  if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
+  const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
+  PDA_COUNT(1);
+  fcomb_bwd_kernel<<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2, b2, w3, dlogit, P,
+                                            latent, B, tiles_per_img, (int)num_tiles,
+                                            static_cast<__nv_bfloat16*>(dfeat), dw1f, dw2, db2, dw3, db3, dbz,
+                                            run_flag);
+  return LAUNCH_OK();
+}
+
+static int fcomb_bwd_zero(float* scratch, int B, float* dw2, float* db2, float* dw3, float* db3, cudaStream_t st) {
+  ZeroList zl;
+  zl.p[0] = scratch; zl.n[0] = FB * FB + B * FB;
+  zl.p[1] = dw2;     zl.n[1] = FB * FB;
+  zl.p[2] = db2;     zl.n[2] = FB;
+  zl.p[3] = dw3;     zl.n[3] = FB;
+  zl.p[4] = db3;     zl.n[4] = 1;
+  PDA_COUNT(1);
+  zero_list_kernel<<<dim3((FB * FB + B * FB + 255) / 256, 5), 256, 0, st>>>(zl);
+  return LAUNCH_OK();
+}
+
 int pda_fcomb_bwd(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* dlogit, int B, int P, int latent, void* dfeat, float* dw1, float* db1,
-                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, void* stream) {
+                  float* dw2, float* db2, float* dw3, float* db3, float* dz, float* scratch, const int* fwd_range_flag,
+                  void* stream) {
   // scratch: fp32, at least 64*64 + 2*B*64 elements (dW1f accumulator, per-image column sums, per-image layer-1 bias)
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !dlogit || !dfeat || !dw1 || !db1 || !dw2 || !db2 || !dw3 ||
       !db3 || !dz || !scratch)
     return PDA_ERR_ARG;
-  if (B <= 0 || P <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  if (B <= 0 || P <= 0 || latent <= 0 || B > (1 << 20)) return PDA_ERR_SHAPE;
   cudaStream_t st = ST(stream);
   float* dw1f = scratch;
   float* dbz = scratch + FB * FB;
   float* bz = dbz + (size_t)B * FB;
-  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (FB * FB + (size_t)B * FB), st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(dw2, 0, sizeof(float) * FB * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(db2, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(dw3, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(db3, 0, sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
-  const int r = fcomb_bwd_tc(feat, z, w1, b1, w2, b2, w3, dlogit, B, P, latent, dfeat, dw1f, dw2, db2, dw3, db3, dbz,
-                             bz, st);
+  int r = fcomb_bwd_zero(scratch, B, dw2, db2, dw3, db3, st);
   if (r) return r;
+  r = fcomb_bwd_tc(feat, z, w1, b1, w2, b2, w3, dlogit, B, P, latent, dfeat, dw1f, dw2, db2, dw3, db3, dbz, bz,
+                   fwd_range_flag, st);
+  if (r) return r;
+  if (fwd_range_flag != nullptr) {
+    r = fcomb_bwd_fp32_launch(feat, z, w1, b1, w2, b2, w3, dlogit, B, P, latent, dfeat, dw1f, dw2, db2, dw3, db3, dbz,
+                              fwd_range_flag, st);
+    if (r) return r;
+  }
   PDA_COUNT(1);
   fcomb_bwd_finish_kernel<<<1, 256, 0, st>>>(dbz, dw1f, w1, z, dw1, db1, dz, B, latent);
   return LAUNCH_OK();
@@ -1135,29 +1176,16 @@ int pda_fcomb_bwd_fp32(const void* feat, const float* z, const float* w1, const 
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !dlogit || !dfeat || !dw1 || !db1 || !dw2 || !db2 || !dw3 ||
       !db3 || !dz || !scratch)
     return PDA_ERR_ARG;
-  if (B <= 0 || P <= 0 || latent <= 0) return PDA_ERR_SHAPE;
+  if (B <= 0 || P <= 0 || latent <= 0 || B > (1 << 20)) return PDA_ERR_SHAPE;
   cudaStream_t st = ST(stream);
   float* dw1f = scratch;
   float* dbz = scratch + FB * FB;
-  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (FB * FB + (size_t)B * FB), st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(dw2, 0, sizeof(float) * FB * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(db2, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(dw3, 0, sizeof(float) * FB, st) != cudaSuccess) return PDA_ERR_CUDA;
-  if (cudaMemsetAsync(db3, 0, sizeof(float), st) != cudaSuccess) return PDA_ERR_CUDA;
-  const int smem = sizeof(float) * (2 * FB * FB + 4 * 128 * FB_LD + 320);
-  static int configured[64];
-  if (dyn_smem_attr_needed(configured, smem)) {
-    if (cudaFuncSetAttribute(fcomb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return PDA_ERR_CUDA;
-  }
-  const int tiles_per_img = (P + 127) / 128;
-  const long long num_tiles = (long long)tiles_per_img * B;
-  if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
-  const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
-  PDA_COUNT(2);
-  fcomb_bwd_kernel<<<grid, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2, b2, w3, dlogit, P,
-                                            latent, B, tiles_per_img, (int)num_tiles,
-                                            static_cast<__nv_bfloat16*>(dfeat), dw1f, dw2, db2, dw3, db3, dbz);
+  int r = fcomb_bwd_zero(scratch, B, dw2, db2, dw3, db3, st);
+  if (r) return r;
+  r = fcomb_bwd_fp32_launch(feat, z, w1, b1, w2, b2, w3, dlogit, B, P, latent, dfeat, dw1f, dw2, db2, dw3, db3, dbz,
+                            nullptr, st);
+  if (r) return r;
+  PDA_COUNT(1);
   fcomb_bwd_finish_kernel<<<1, 256, 0, st>>>(dbz, dw1f, w1, z, dw1, db1, dz, B, latent);
   return LAUNCH_OK();
 }

@@ -162,7 +162,9 @@ def kl_diag_gauss(mls_q, mls_p):
 
 def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, want_mean=True, want_weight=True,
                        want_mask=False, want_logits=False, want_probs=False, precision="bf16"):
-    """feat (B,H,W,64) bf16; z (S,B,L) fp32.  Returns dict of (B,1,H,W) / (S,B,1,H,W) tensors."""
+    """feat (B,H,W,64) bf16; z (S,B,L) fp32.  Returns dict of (B,1,H,W) / (S,B,1,H,W) tensors.
+    "range_flag" (precision "bf16" only): the call's scratch; element 0 is the int32 fp16-range flag that the kernel
+    raises (and acts on, by re-running the batch in fp32 on the device) -- `fcomb_bwd` takes it as `fwd_flag`."""
     _need_cuda(feat, z, w1)
     lib = _lib.load()
     B, H, W, C = feat.shape
@@ -176,13 +178,19 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
     logits = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_logits else None
     probs = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_probs else None
     z = z.contiguous().float()
-    fn = lib.pda_fcomb_mc_consensus if precision == "bf16" else lib.pda_fcomb_mc_consensus_fp32
+    scratch = None
+    args = (feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            w3.data_ptr(), b3.data_ptr(), B, P, S, L, float(upper), float(lower), _ptr(mean), _ptr(weight),
+            _ptr(mask), _ptr(logits), _ptr(probs))
     with _Timed("fcomb_mc", float(B * P)):
-        rc = fn(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-                w3.data_ptr(), b3.data_ptr(), B, P, S, L, float(upper), float(lower), _ptr(mean), _ptr(weight),
-                _ptr(mask), _ptr(logits), _ptr(probs), _stream())
+        if precision == "bf16":
+            # per-call scratch from torch's caching allocator: nothing is shared between launches, streams or graphs
+            scratch = torch.empty(lib.pda_fcomb_scratch_floats(S, B), dtype=torch.float32, device=dev)
+            rc = lib.pda_fcomb_mc_consensus(*args, scratch.data_ptr(), _stream())
+        else:
+            rc = lib.pda_fcomb_mc_consensus_fp32(*args, _stream())
     _lib.check(rc, "fcomb_mc_consensus")
-    return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs}
+    return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs, "range_flag": scratch}
 
 
 _EMA_CHUNK = 16384  # elements per 256-thread block of the multi-tensor kernels (<= 65536)
@@ -269,8 +277,11 @@ def conv3x3_first_bwd(x0, x1, out, dout):
     cin = 1 if x1 is None else 2
     dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=out.device)
     db = torch.empty((cout,), dtype=torch.float32, device=out.device)
+    scratch = torch.empty(lib.pda_conv3x3_first_bwd_scratch_floats(B, H, W, cout, cin), dtype=torch.float32,
+                          device=out.device)
     _lib.check(lib.pda_conv3x3_first_bwd(x0.data_ptr(), _ptr(x1), out.data_ptr(), dout.data_ptr(), dw.data_ptr(),
-                                         db.data_ptr(), B, H, W, cout, _stream()), "conv3x3_first_bwd")
+                                         db.data_ptr(), B, H, W, cout, scratch.data_ptr(), _stream()),
+               "conv3x3_first_bwd")
     return dw, db
 
 
@@ -391,9 +402,10 @@ def multi_tensor_l2norm_bwd(table, norms, gout, total):
     return flat
 
 
-def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit, precision="bf16"):
+def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit, precision="bf16", fwd_flag=None):
     """Backward of Fcomb for one latent sample: feat (B,H,W,64) bf16, z (B,L), dlogit (B,1,H,W) fp32.
-    precision "bf16": tensor-core kernel; "fp32": the exact CUDA-core baseline."""
+    precision "bf16": tensor-core kernel; "fp32": the exact CUDA-core baseline.  fwd_flag: the "range_flag" tensor of
+    the forward call -- when the forward fell back to fp32 (fp16 range guard) the backward does the same, on the device."""
     _need_cuda(feat, z, w1, dlogit)
     lib = _lib.load()
     B, H, W, C = feat.shape
@@ -408,12 +420,14 @@ def fcomb_bwd(feat, z, w1, b1, w2, b2, w3, dlogit, precision="bf16"):
     scratch = torch.empty(64 * 64 + 2 * B * 64, dtype=torch.float32, device=dev)
     z = z.contiguous().float()
     dlogit = dlogit.contiguous().float()
-    fn = lib.pda_fcomb_bwd if precision == "bf16" else lib.pda_fcomb_bwd_fp32
+    args = (feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(),
+            dlogit.data_ptr(), B, H * W, L, dfeat.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
+            db2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), dz.data_ptr(), scratch.data_ptr())
     with _Timed("fcomb_bwd", float(B * H * W)):
-        rc = fn(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                               b2.data_ptr(), w3.data_ptr(), dlogit.data_ptr(), B, H * W, L, dfeat.data_ptr(),
-                               dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(),
-                               db3.data_ptr(), dz.data_ptr(), scratch.data_ptr(), _stream())
+        if precision == "bf16":
+            rc = lib.pda_fcomb_bwd(*args, _ptr(fwd_flag), _stream())
+        else:
+            rc = lib.pda_fcomb_bwd_fp32(*args, _stream())
     _lib.check(rc, "fcomb_bwd")
     return dfeat, dw1, db1, dw2, db2, dw3, db3, dz
 

@@ -35,6 +35,12 @@ class FusedAdam(torch.optim.Optimizer):
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == key:
             return cached[1]
+        if torch.cuda.is_current_stream_capturing():
+            # building the table needs a host -> device copy, which is illegal under stream capture
+            raise _lib.PdaError(
+                "FusedAdam: parameter / gradient storage changed inside a CUDA-graph capture.  Keep p.grad storage "
+                "fixed (attach a parallel.GradAllReducer, or zero gradients in place with zero_grad(set_to_none="
+                "False)) and run one eager step before capturing")
         rows = []
         for p in params:
             st = self.state[p]

@@ -9,8 +9,12 @@ Before the script starts, `install()`
     (every script and trainer, e.g. LIVECell/livecell_mt.py:8, prob_utils/my_trainer/mean_teacher_trainer.py:12) binds
     the sm_100a implementation -- the reference's own my_models package is never imported;
   * puts the fused helpers on the reference's trainer classes in place (`sample_from_teacher`, `sample_from_weak_model`,
-    `sample_from_model`, `_momentum_update`: INTEGRATION.md section 2); their step bodies, loggers and checkpoints stay
-    reference code on torch_em.
+    `sample_from_model`, `_momentum_update`, `PUNetTrainer._sample`: INTEGRATION.md section 2); their step bodies,
+    loggers and checkpoints stay reference code on torch_em;
+  * replaces `prob_utils.my_predictions.punet_prediction` / `punet_pseudo_prediction` (punet_predictions.py:15-63,
+    66-136: what every `--predict` / `--get_pseudo_labels` runs) by `predictions.py`: same signatures and files, the
+    per-image work goes through `tiled.predict_with_halo` / `consensus.punet_pseudo_labels` (one fused
+    Fcomb + consensus launch per block batch instead of S `sample()` calls per block).
 It is the zero-edit alternative to the two `__init__.py` edits described in INTEGRATION.md.
 """
 import importlib
@@ -42,6 +46,11 @@ def patch_trainers(trainer_module):
     name from prob_utils.my_trainer).  Returns the names of the classes that were patched."""
     from . import trainer_mixins
     done = []
+    punet_cls = getattr(trainer_module, "PUNetTrainer", None)
+    if punet_cls is not None:
+        from . import predictions
+        punet_cls._sample = predictions.punet_trainer_sample      # punet_trainer.py:15-17
+        done.append("PUNetTrainer")
     for cls_name, mixin_name in _MIXINS.items():
         cls = getattr(trainer_module, cls_name, None)
         if cls is None:
@@ -55,6 +64,21 @@ def patch_trainers(trainer_module):
                     continue                                     # class-level defaults never shadow the reference's
                 setattr(cls, name, attr)
         done.append(cls_name)
+    return done
+
+
+def patch_predictions(pred_module):
+    """Binds predictions.punet_prediction / punet_pseudo_prediction into prob_utils.my_predictions (and its
+    punet_predictions sub-module, for callers that import from there).  Returns the patched names."""
+    from . import predictions
+    done = []
+    sub = sys.modules.get(pred_module.__name__ + ".punet_predictions")
+    for name in ("punet_prediction", "punet_pseudo_prediction"):
+        if hasattr(pred_module, name) or (sub is not None and hasattr(sub, name)):
+            setattr(pred_module, name, getattr(predictions, name))
+            if sub is not None:
+                setattr(sub, name, getattr(predictions, name))
+            done.append(name)
     return done
 
 
@@ -73,6 +97,10 @@ def install(reference_root=None, patch=True):
             patched = patch_trainers(importlib.import_module("prob_utils.my_trainer"))
         except ImportError as e:                                 # e.g. torch_em missing: prediction-only environments
             warnings.warn(f"prob_utils.my_trainer not importable ({e}); trainers left unpatched")
+        try:
+            patched += patch_predictions(importlib.import_module("prob_utils.my_predictions"))
+        except ImportError as e:                                 # imageio / torch_em missing
+            warnings.warn(f"prob_utils.my_predictions not importable ({e}); prediction functions left unpatched")
     return patched
 
 

@@ -178,6 +178,8 @@ class GraphedStep:
         self.fn, self.optimizer = fn, optimizer
         if optimizer is not None and not getattr(optimizer, "capturable", False):
             raise ValueError("GraphedStep needs FusedAdam(capturable=True): a replay must not bake in the step count")
+        # (a step body whose optimizer.zero_grad() drops the gradients needs a GradAllReducer -- it keeps p.grad storage
+        # fixed; FusedAdam raises a PdaError naming this if its pointer table would have to be rebuilt under capture)
         self.static_in = [x.clone() for x in example_inputs]
         for m in modules:
             m.release_graph()

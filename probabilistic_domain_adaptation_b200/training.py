@@ -256,7 +256,7 @@ class L2NormSumFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cache, *params):
-        key = tuple(p.data_ptr() for p in params)
+        key = tuple((p.data_ptr(), p.numel()) for p in params)
         if cache.get("key") != key:
             cache["fwd"], cache["bwd"], cache["offsets"], cache["total"] = ops.build_l2_tables(
                 [p.detach() for p in params])
@@ -276,12 +276,20 @@ class L2NormSumFn(torch.autograd.Function):
         return (None, *grads)
 
 
-_L2_CACHES = {}
+_L2_CACHES = {}   # (storage pointer, numel) of every tensor -> pointer tables; bounded (oldest entry evicted)
+_L2_CACHE_LIMIT = 32
 
 
 def l2_norm_sum(params):
     params = list(params)
-    cache = _L2_CACHES.setdefault(tuple(id(p) for p in params), {})
+    # keyed by what the tables actually contain (pointers and sizes), not by object identity: a recycled id() can
+    # never resurrect a stale table, and models that were freed do not pin entries for ever
+    ckey = tuple((p.data_ptr(), p.numel()) for p in params)
+    cache = _L2_CACHES.get(ckey)
+    if cache is None:
+        if len(_L2_CACHES) >= _L2_CACHE_LIMIT:
+            _L2_CACHES.pop(next(iter(_L2_CACHES)))
+        cache = _L2_CACHES[ckey] = {}
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return L2NormSumFn.apply(cache, *params)
     with torch.no_grad():
@@ -302,13 +310,15 @@ class FcombTrainFn(torch.autograd.Function):
         out = ops.fcomb_mc_consensus(feat, z[None].detach(), w1.detach(), b1.detach(), w2.detach(), b2.detach(),
                                      w3.detach(), b3.detach(), want_mean=False, want_weight=False, want_logits=True)
         ctx.save_for_backward(feat, z, w1, b1, w2, b2, w3)
+        ctx.range_flag = out["range_flag"]  # fp16 range flag of the forward: the backward follows the same path
         return out["logits"][0]
 
     @staticmethod
     def backward(ctx, g):
         feat, z, w1, b1, w2, b2, w3 = ctx.saved_tensors
         dfeat, dw1, db1, dw2, db2, dw3, db3, dz = ops.fcomb_bwd(feat, z.detach(), w1.detach(), b1.detach(),
-                                                                w2.detach(), b2.detach(), w3.detach(), g)
+                                                                w2.detach(), b2.detach(), w3.detach(), g,
+                                                                fwd_flag=ctx.range_flag)
         return dfeat, dz, dw1, db1, dw2, db2, dw3, db3
 
 
