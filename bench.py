@@ -155,6 +155,54 @@ def cpu_reference_train_step(batch, size, samples):
     return batch / dt, dt, cores
 
 
+def eager_gpu_baseline(dev, T, HW, S, steps=3, warmup=1):
+    """The same inference workload through EAGER PyTorch on the same B200 (cuDNN / cuBLAS / ATen kernels): the oracle
+    port is the reference's arithmetic op for op (the reference's GPU path IS eager PyTorch).
+    fp32 with cuDNN's default TF32 convolutions, and under bf16 autocast.  A reported baseline (GPU vs GPU), measured
+    inside the default run so that the driver's record carries it; never part of the product path."""
+    import torch
+    from oracle import punet_oracle as po
+    sd = {k: v.to(dev) for k, v in po.make_state_dict(0, last_layer_gain=8.0).items()}
+    x, _, eps, _ = po.synthetic_inputs(T, HW, HW, s=S)
+    x, eps = x.to(dev), eps.to(dev)
+
+    def run(autocast):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return po.sample_from_teacher(sd, x, eps, do_consensus_masking=True)
+
+    out = {}
+    for name, ac in (("eager_fp32_tf32", False), ("eager_autocast_bf16", True)):
+        for _ in range(warmup):
+            run(ac)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            run(ac)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "value": float(T) * HW * HW * S / (ms * 1e-3), "unit": "px*samples/s"}
+    out["sample"] = f"{T} tiles 1x{HW}x{HW}, S={S}, {steps} timed steps after {warmup} warm-up, device-resident"
+    out["what"] = "oracle port of the reference run as eager PyTorch on cuda:0 (cuDNN conv, ATen elementwise)"
+    del sd, x, eps
+    torch.cuda.empty_cache()
+    return out
+
+
+def load_traffic_profile(T, HW, S):
+    """DRAM bytes per launch of the dominant kernels from the ncu capture of THIS workload, written by
+    tools/ncu_traffic_summary.py into profiles/dram_traffic.json (which names the build it was taken on)."""
+    path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        prof = json.load(fh)
+    if prof.get("workload") != {"tiles": T, "tile": HW, "samples": S}:
+        return None
+    return prof
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -580,12 +628,18 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # DRAM traffic per launch from the ncu capture of this exact workload (profiles/r01c_conv_dram_traffic.md):
-    # 31 conv launches move 15.16 GB per step against 16.55 GB algorithmic (activations in + out + weights; the L2
-    # absorbs part of the weight / bridge re-reads), the fcomb launch 579 MB against 587 MB.
-    default_wl = (T, HW, S) == (4, 1024, 16)
-    conv_traffic = 489.2e6 if default_wl else None
-    conv_traffic_alg = 533.8e6 if default_wl else None
+    # DRAM traffic per launch: read from the ncu capture of this exact workload (profiles/dram_traffic.json, produced by
+    # tools/gpu_traffic.sh + tools/ncu_traffic_summary.py on the build named inside); null for any other workload
+    tprof = load_traffic_profile(T, HW, S)
+    conv_traffic = tprof["conv3x3_tc"]["dram_bytes_per_launch"] if tprof else None
+    conv_traffic_alg = tprof["conv3x3_tc"]["algorithmic_bytes_per_launch"] if tprof else None
+    fcomb_traffic = tprof["fcomb_tc"]["dram_bytes_per_launch"] if tprof else None
+
+    eager = None
+    if world == 1 and not args.no_cpu_baseline and not args.no_extras:
+        eager = eager_gpu_baseline(dev, T, HW, S)
+        eager["speedup_vs_eager_fp32_tf32"] = eager["eager_fp32_tf32"]["ms_per_step"] / (ms / args.steps)
+        eager["speedup_vs_eager_autocast_bf16"] = eager["eager_autocast_bf16"]["ms_per_step"] / (ms / args.steps)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -612,17 +666,24 @@ def run_ours(args):
                      "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": conv_traffic,
                      "traffic_algorithmic": conv_traffic_alg,
-                     "traffic_source": "profiles/r01c_conv_dram_traffic.md (ncu dram__bytes_read+write, mean per launch)",
+                     "traffic_source": (f"profiles/dram_traffic.json ({tprof['build']}; ncu dram__bytes_read+write, mean "
+                                        f"per launch)" if tprof else None),
                      "launches": n_conv, "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms},
         "roofline_fcomb": {"bound": "hbm (north star) / tensor + CUDA-core epilogue (actual)", "achieved": fc_gbs, "peak": hbm_peak,
                            "unit": "GB/s", "frac": fc_gbs / hbm_peak, "algorithmic_bytes_per_px": 140,
-                           "traffic": 579.2e6 if default_wl else None,
+                           "traffic": fcomb_traffic,
                            "tensor_frac": fc_tf / tf_peak,
                            "achieved_tflops": fc_tf, "kernel_ms_per_step": fc_ms / args.steps,
                            "share_of_step": fc_ms / ms},
         "model_tflops": FLOP_PER_PX_FORWARD * T * HW * HW * world * args.steps / (ms * 1e-3) / 1e12,
         "cpu_baseline": cpu,
+        "eager_gpu_baseline": eager,
+        "train_scaling": (None if train is None else
+                          {"metric": train["metric"], "value": train["value"], "unit": train["unit"], "n_gpus": world,
+                           "ms_per_step": train["ms_per_step"], "scaling": "weak",
+                           "collective": "one NCCL gradient all-reduce per step (109 MB fp32)" if world > 1 else None,
+                           "workload": train["config"]["workload"]}),
         "mc_sweep_px_samples_per_s": sweep,
         "tiled_prediction": tiled_res,
         "augment": augment_res,

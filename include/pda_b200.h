@@ -36,19 +36,29 @@ const char* pda_error_string(int code);
 long long pda_launch_count(void);
 void pda_reset_launch_count(void);
 
-/* Weights of nn.Conv2d(cin, cout, 3): OIHW fp32 -> [cout][tap = ky*3+kx][cin] bf16 (K-major GEMM B operand).
- * With rot180 != 0 the taps are reversed and cin/cout swapped ([cin][8-tap][cout]): the dgrad operand. */
-int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, void* stream);
+/* ACTIVATION FORMAT.  Feature maps are NHWC 16-bit tensors in one of two storage formats, selected per call by
+ * `act_f16`: 0 = bf16 (the training path: activation gradients need the fp32 exponent range), 1 = fp16 (the no-grad /
+ * Monte-Carlo inference path: 11 mantissa bits instead of 8 cut the rounding error of the 21-layer trunk by 8x, which is
+ * what brings sampled logits within the 1e-2 tolerance at full image sizes; fp16 is also the dtype the reference's own
+ * student forward runs in under torch_em's autocast).  Tensor-core operands match the activations (bf16 x bf16 or
+ * fp16 x fp16), accumulation is always fp32.  fp16 stores saturate at +-65504 (never inf); kernels that can produce
+ * large values take `range_flag` (device int, may be NULL) and set it to 1 when a value exceeded the range. */
 
-/* Same for many convs in one launch (after an optimizer or EMA step).  table: device int64 [n_chunks][6] =
- * (w_oihw ptr, packed ptr, rot180-packed ptr or 0, cout, cin, first output element of the chunk); chunks of 16384. */
+/* Weights of nn.Conv2d(cin, cout, 3): OIHW fp32 -> [cout][tap = ky*3+kx][cin] 16-bit (K-major GEMM B operand), bf16 or
+ * fp16 (f16 != 0).  With rot180 != 0 the taps are reversed and cin/cout swapped ([cin][8-tap][cout]): the dgrad operand. */
+int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, int f16,
+                             void* stream);
+
+/* Same for many convs in one launch (after an optimizer or EMA step).  table: device int64 [n_chunks][7] =
+ * (w_oihw ptr, bf16 packed ptr or 0, bf16 rot180-packed ptr or 0, fp16 packed ptr or 0, cout, cin, first output element
+ * of the chunk); chunks of 16384. */
 int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* stream);
 
 /* First layer of every net (cin = 1, or 2 for the posterior whose input is cat(patch, segm),
  * probabilistic_unet.py:118): x0/x1 are fp32 [B][H][W] planes (x1 may be NULL), w is OIHW fp32.
- * Replaces unet_blocks.py:19-20 / probabilistic_unet.py:56-57 for block 0.  out: NHWC bf16. */
+ * Replaces unet_blocks.py:19-20 / probabilistic_unet.py:56-57 for block 0.  out: NHWC bf16 / fp16 (act_f16). */
 int pda_conv3x3_first(const float* x0, const float* x1, const float* w_oihw, const float* bias, void* out, int B,
-                      int H, int W, int cout, int relu, void* stream);
+                      int H, int W, int cout, int relu, int act_f16, void* stream);
 
 /* conv3x3(pad 1) + bias (+ReLU) (+ 2x2 average pool) on tcgen05 tensor cores.
  * Input = channel concat of src0 (c0 ch) and src1 (c1 ch, may be NULL/0) -- the torch.cat of
@@ -56,29 +66,35 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w_oihw, con
  * Replaces unet_blocks.py:17-24 (DownConvBlock) and probabilistic_unet.py:53-61 (Encoder).
  * relu_mask (NHWC bf16 [B][H][W][cout], may be NULL): outputs are zeroed where relu_mask <= 0 -- the ReLU backward of
  * the layer that produced this conv's input, fused into the epilogue when the kernel runs as dgrad.
- * bn_tile: 0 = auto, else 64/128 output channels per CTA. */
-int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
-                     void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
-                     int bn_tile, void* stream);
+ * bn_tile: 0 = auto, else 64/128 output channels per CTA.  act_f16 / range_flag: see ACTIVATION FORMAT above (inputs,
+ * packed weights and outputs share the format). */
+int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                   void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
+                   int bn_tile, int act_f16, int* range_flag, void* stream);
 
-/* Same contract on plain CUDA cores (one thread per output element).  Cross-check kernel for the
+/* Kernel selection for pda_conv3x3_tc: 0 = one CTA per 128-pixel tile (csrc/conv3x3_tc.cu), 1 = CTA pairs issuing
+ * M = 256 tcgen05.mma.cta_group::2 with the weight tile split across the pair (csrc/conv3x3_tc2.cu).  mode < 0 only
+ * queries.  Returns the previous mode.  Results are bit-identical between the two. */
+int pda_set_conv_pair(int mode);
+
+/* Same contract (bf16 only) on plain CUDA cores (one thread per output element).  Cross-check kernel for the
  * parity tests; the product path never selects it implicitly. */
 int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                           const float* bias, void* out, void* out_pool, int B, int H, int W, int cout, int relu,
                           void* stream);
 
-/* nn.AvgPool2d(2, 2, 0, ceil_mode=True) for even H, W (unet_blocks.py:17).  NHWC bf16. */
-int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream);
+/* nn.AvgPool2d(2, 2, 0, ceil_mode=True) for even H, W (unet_blocks.py:17).  NHWC bf16 / fp16. */
+int pda_avgpool2(const void* in, void* out, int B, int H, int W, int C, int act_f16, void* stream);
 
-/* F.interpolate(mode='bilinear', scale_factor=2, align_corners=True) (unet_blocks.py:51). NHWC bf16 (h,w)->(2h,2w) */
-int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w, int C, void* stream);
+/* F.interpolate(mode='bilinear', scale_factor=2, align_corners=True) (unet_blocks.py:51). NHWC (h,w)->(2h,2w) */
+int pda_upsample2x_bilinear(const void* in, void* out, int B, int h, int w, int C, int act_f16, void* stream);
 
 /* AxisAlignedConvGaussian head (probabilistic_unet.py:126-137): mean over H then W of the encoder output
- * enc [B][P][C] bf16, then the 1x1 conv C -> 2*latent (w_head [2L][C] fp32, b_head [2L]).
+ * enc [B][P][C] bf16 / fp16, then the 1x1 conv C -> 2*latent (w_head [2L][C] fp32, b_head [2L]).
  * scratch: fp32, at least B * pda_gauss_head_scratch_rows(P) * C elements.  out: [B][2L] fp32 = (mu | log_sigma). */
 int pda_gauss_head_scratch_rows(int P);
 int pda_gauss_head(const void* enc, const float* w_head, const float* b_head, float* scratch, float* mu_logsigma,
-                   int B, int P, int C, int latent, void* stream);
+                   int B, int P, int C, int latent, int act_f16, void* stream);
 
 /* z[s][b][:] = mu[b] + exp(log_sigma[b]) * eps[s][b]  (Normal.rsample, probabilistic_unet.py:302/349). */
 int pda_latent_samples(const float* mu_logsigma, const float* eps, float* z, int S, int B, int latent, void* stream);
@@ -90,7 +106,7 @@ int pda_kl_diag_gauss(const float* mu_logsigma_q, const float* mu_logsigma_p, fl
 /* Fused Fcomb + sigmoid + cross-sample mean + consensus for S latent samples.
  * Replaces S x Fcomb.forward (probabilistic_unet.py:200-214: tile, cat, 3 x conv1x1) and the consensus
  * arithmetic of mean_teacher_trainer.py:74-86 (+ 3 copies) / punet_predictions.py:31-32,117-124.
- *   feat [B][P][64] bf16, z [S][B][L] fp32,
+ *   feat [B][P][64] bf16 / fp16 (feat_f16), z [S][B][L] fp32,
  *   w1 [64][64+L] (first 64 input channels = features, last L = z), b1[64], w2[64][64], b2[64], w3[64], b3[1]: fp32.
  * Outputs (any may be NULL): mean_prob [B][P] fp32 = sum_s sigmoid(logit_s) / S;
  *   cons_weight [B][P] fp32 = #{s: p_s >= upper or p_s <= lower} / S;  cons_mask [B][P] int64 = (count == S);
@@ -104,14 +120,14 @@ long long pda_fcomb_scratch_floats(int S, int B);
 int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
                            float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
-                           float* logits, float* probs, float* scratch, void* stream);
+                           float* logits, float* probs, float* scratch, int feat_f16, void* stream);
 
 /* Same contract in exact-order fp32 on CUDA cores (no bf16 rounding of weights / hidden activations): the
  * numerics baseline of the tensor-core kernel above.  ~20x slower; selected explicitly by the caller only. */
 int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2,
                                 const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
                                 float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
-                                float* logits, float* probs, void* stream);
+                                float* logits, float* probs, int feat_f16, void* stream);
 
 /* Mean-teacher EMA over many tensors in one launch: t = t*m + p*(1-m)  (mean_teacher_trainer.py:52-55,
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */
@@ -149,7 +165,7 @@ int pda_augment_view(const float* img, const float* noise, float* out, int B, in
 /* ---------------------------------------------------------------------------------------------------------
  * Training (backward) entry points.  They replace what torch.autograd runs behind loss.backward() in the step
  * bodies punet_trainer.py:24-36 / mean_teacher_trainer.py:111-119 (cuDNN dgrad/wgrad, ATen elementwise backward).
- * dgrad of conv3x3 is pda_conv3x3_bf16 itself, called with the rot180-packed weights and relu = 0.
+ * dgrad of conv3x3 is pda_conv3x3_tc itself, called with the rot180-packed weights and relu = 0.
  * --------------------------------------------------------------------------------------------------------- */
 
 /* Weight (+bias) gradient of conv3x3: dW[co][ci][ky][kx] = sum_p dZ[p][co] * X[p + tap][ci] on tcgen05 tensor cores

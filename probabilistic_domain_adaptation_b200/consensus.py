@@ -77,7 +77,7 @@ class MomentumUpdater:
         from .optim import bump_versions
         from .autograd_ops import refresh_packed
         bump_versions(self.teacher.parameters())
-        refresh_packed(self.teacher, rot180=False)  # the teacher only runs forward
+        refresh_packed(self.teacher, rot180=False, bf16=False, f16=True)  # the teacher only runs the no-grad forward
 
 
 def adamt_momentum(iteration, momentum=0.999):

@@ -25,6 +25,9 @@ struct ConvArgs {
   __nv_bfloat16* out_pool;  // NHWC [B][H/2][W/2][cout] (2x2 average of the post-ReLU fp32 values) or nullptr
   const __nv_bfloat16* mask;  // NHWC [B][H][W][cout] or nullptr: outputs are zeroed where mask <= 0 (ReLU backward
                               // of the layer that produced this conv's input, fused into the dgrad epilogue)
+  int act_f16;                // activations / weights / outputs are fp16 (no-grad path) instead of bf16
+  int* range_flag;            // fp16 only, may be nullptr: set to 1 when an output exceeds the fp16 range (the store
+                              // saturates at +-65504)
 };
 
 void* get_encode_tiled();  // cuTensorMapEncodeTiled driver entry point (or nullptr)
@@ -40,11 +43,18 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
 int fcomb_mc_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* b3, int B, int P, int S, int latent, float upper, float lower,
                   float* mean_prob, float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
-                  const int* run_flag, cudaStream_t stream);
+                  const int* run_flag, int feat_f16, cudaStream_t stream);
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
-               cudaStream_t stream);
+               int act_f16, int* range_flag, cudaStream_t stream);
+
+int conv_pair_mode(int set);  // csrc/conv3x3_tc.cu
+
+// CTA-pair (cta_group::2) variant, csrc/conv3x3_tc2.cu
+int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
+                void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
+                int act_f16, int* range_flag, cudaStream_t stream);
 
 // log2(C / 8) for C = 8 * 2^k (the NHWC kernels address 16-byte channel chunks with shifts), else -1
 static inline int c8_shift(int C) {

@@ -11,6 +11,12 @@
 //   M tile = 128 output pixels = a tile_h x tile_w spatial patch of one image (tile_w in {8, 16})
 //   N tile = BN output channels, K step = 64 input channels of one tap (one 128-byte swizzle row).
 // Activations: NHWC bf16.  Weights: packed [Cout][9][Ctot] bf16 (K-major).
+#include <stdlib.h>
+
+#ifndef PDA_CONV_PAIR_DEFAULT
+#define PDA_CONV_PAIR_DEFAULT 1
+#endif
+
 #include "conv.cuh"
 #include "ptx.cuh"
 
@@ -53,7 +59,7 @@ struct ConvCfg {
 
 constexpr int CONV_THREADS = 320;
 
-template <int BN, int MT, bool RES>
+template <int BN, int MT, bool RES, bool F16>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -167,7 +173,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform control, elected lane issues)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    // operands: bf16 x bf16, or fp16 x fp16 on the fp16-activation (no-grad) path; fp32 accumulate either way
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     uint32_t it = 0;
@@ -289,6 +296,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             float tv = __uint_as_float(v[j]) + bias_s[n0 + g * 64 + cb * 32 + j];
             f[j] = p.relu ? fmaxf(tv, 0.f) : tv;
           }
+          if (F16) {
+            // fp16 range guard: the stores below saturate at +-65504; a value beyond that raises the caller's flag
+            float vmax = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, fabsf(f[j]));
+            if (p.range_flag != nullptr && __any_sync(0xffffffffu, !(vmax <= F16_MAX)) && lane == 0)
+              atomicOr(p.range_flag, 1);
+          }
           if (p.mask) {
             // bf16 mask values are post-ReLU activations (>= 0): "> 0" <=> magnitude bits non-zero and sign clear
 #pragma unroll
@@ -306,10 +321,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
-              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              o.x = pack_act2<F16>(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_act2<F16>(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_act2<F16>(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_act2<F16>(f[8 * j + 6], f[8 * j + 7]);
               *reinterpret_cast<uint4*>(stage + lane * 128 + (((cb * 4 + j) ^ sw) << 4)) = o;
             }
           }
@@ -328,10 +343,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 o;
-                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                o.x = pack_act2<F16>(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_act2<F16>(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_act2<F16>(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_act2<F16>(f[8 * j + 6], f[8 * j + 7]);
                 dst[j] = o;
               }
             }
@@ -406,13 +421,24 @@ int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long 
   return r == CUDA_SUCCESS ? PDA_OK : PDA_ERR_TENSORMAP;
 }
 
-template <int BN, int MT, bool RES>
-static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                       const ConvArgs& args, cudaStream_t stream) {
+// 1: conv3x3 launches use the CTA-pair (cta_group::2) kernel; initial value from PDA_CONV_PAIR, changed at run time
+// through pda_set_conv_pair (A/B measurements, tests).  set < 0: query only.
+int conv_pair_mode(int set) {
+  static std::atomic<int> mode{[] {
+    const char* e = getenv("PDA_CONV_PAIR");
+    return e ? atoi(e) : PDA_CONV_PAIR_DEFAULT;
+  }()};
+  if (set >= 0) return mode.exchange(set);
+  return mode.load();
+}
+
+template <int BN, int MT, bool RES, bool F16>
+static int launch_conv_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                           const ConvArgs& args, cudaStream_t stream) {
   using L = ConvCfg<BN, MT, RES>;
   static int configured[64];
   if (dyn_smem_attr_needed(configured, L::DYN_BYTES)) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MT, RES>,
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, MT, RES, F16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return PDA_ERR_CUDA;
   }
@@ -420,16 +446,32 @@ static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   if (units > 0x7fffffffLL) return PDA_ERR_SHAPE;
   const int grid = (int)(units < 148 ? units : 148);
   PDA_COUNT(1);
-  conv3x3_tc_kernel<BN, MT, RES><<<grid, CONV_THREADS, L::DYN_BYTES, stream>>>(a0, a1, b, o, args);
+  conv3x3_tc_kernel<BN, MT, RES, F16><<<grid, CONV_THREADS, L::DYN_BYTES, stream>>>(a0, a1, b, o, args);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+template <int BN, int MT, bool RES>
+static int launch_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                       const ConvArgs& args, cudaStream_t stream) {
+  return args.act_f16 ? launch_conv_fmt<BN, MT, RES, true>(a0, a1, b, o, args, stream)
+                      : launch_conv_fmt<BN, MT, RES, false>(a0, a1, b, o, args, stream);
 }
 
 int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
-               cudaStream_t stream) {
+               int act_f16, int* range_flag, cudaStream_t stream) {
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
     return PDA_ERR_SHAPE;
   if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
+  {
+    // CTA-pair kernel (csrc/conv3x3_tc2.cu) for every launch with at least two pixel tiles
+    const int pair_mode = conv_pair_mode(-1);
+    const int th = ((H > 16 && !(bn_override == 256 || (bn_override == 0 && cout % 256 == 0))) ? 32 : 16);
+    const long long mtiles = (long long)((W + 7) / 8) * ((H + th - 1) / th) * B;
+    if (pair_mode && mtiles >= 2)
+      return conv3x3_tc2(src0, c0, src1, c1, wpacked, bias, out, out_pool, mask, B, H, W, cout, relu, bn_override,
+                         act_f16, range_flag, stream);
+  }
   // N = 256 halves the shared-memory bytes per MAC of the B operand (N = 128 tiles sit exactly at the 128 B/clk
   // shared-memory port limit); its 2 x 256 accumulator columns leave room for one M-tile per unit only
   int bn = (bn_override == 64 || bn_override == 128 || bn_override == 256)
@@ -447,6 +489,8 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   a.out = static_cast<__nv_bfloat16*>(out);
   a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
   a.mask = static_cast<const __nv_bfloat16*>(mask);
+  a.act_f16 = act_f16;
+  a.range_flag = act_f16 ? range_flag : nullptr;
   CUtensorMap tA0, tA1, tB;
   int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);
   if (r) return r;

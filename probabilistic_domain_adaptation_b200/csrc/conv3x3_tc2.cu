@@ -1,0 +1,548 @@
+// CTA-pair (cta_group::2) variant of the implicit-GEMM conv3x3 of conv3x3_tc.cu.
+//
+// Why: an M = 128 x N x K = 16 tcgen05.mma needs N/2 tensor cycles but fetches 4 KB (A) + N * 32 B (B) of operands
+// through a shared-memory port that delivers 128 B/clk per SM (profiles/r01e_umma_issue_rate.md): N = 64 tiles are capped
+// at 2/3 of the tensor rate, N = 128 tiles are exactly balanced -- and the TMA fill shares the port.  Two CTAs of one
+// cluster (the two SMs of a TPC) issue ONE M = 256 MMA instead: each SM multiplies its own 128 pixels (its own A slabs)
+// with the SAME weight tile, of which each CTA holds only half the rows (N/2) -- per SM the B fetch and the B fill are
+// halved (N = 64: 40 instead of 48 port cycles per 32 tensor cycles; N = 128: 48 per 64: tensor-bound).
+//
+// Same work decomposition, slabs, tap reuse, epilogue and outputs as conv3x3_tc_kernel; what changes is the plumbing:
+//   * cluster of 2 CTAs; a pair-unit = two adjacent pixel tiles x one block of BN output channels
+//   * both CTAs run their TMA producer (own A slabs, own half of the weight tile); the transaction bytes of both land on
+//     the LEADER's (rank 0) full barriers (cp.async.bulk.tensor ... .cta_group::2 with the barrier address mapped to rank
+//     0); the leader's producer alone arrives on them, announcing the bytes of both CTAs
+//   * only the leader's MMA warp issues tcgen05.mma.cta_group::2; its commits are multicast to the barriers of both CTAs
+//     (smem slot release, accumulator-full)
+//   * each CTA's epilogue drains its own TMEM (its 128 rows of the M = 256 accumulator); the peer's epilogue warps
+//     release the accumulator buffer with remote arrives on the leader's barrier
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace pda {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// (default semantics, as a local arrive: the explicit .release.cluster form costs a MEMBAR.ALL + ERRBAR per arrive, which
+// also waits for the warp's outstanding global stores; the TMEM reads this arrive publishes are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion bytes may be signalled on a barrier of the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem, N/2 rows in each CTA]; issued by the leader
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (count 1) on the barrier at this shared-memory offset in BOTH CTAs once all earlier MMAs of this thread are done
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int BN, int MT, bool RES>
+struct Conv2Cfg {
+  static constexpr int SLAB_ROWS = 16 * MT + 2;
+  static constexpr int A_BYTES = SLAB_ROWS * 1024;     // one slab: SLAB_ROWS x (8 px x 128 B)
+  static constexpr int BH = BN / 2;                    // weight rows held by one CTA of the pair
+  static constexpr int B_BYTES = BH * 128;             // this CTA's half of one (tap, chunk) weight tile
+  static constexpr int A_STAGES = 4;
+  static constexpr int B_STAGES = RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6));
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = A_STAGES * A_BYTES;
+  static constexpr int STG_OFF = B_OFF + B_STAGES * B_BYTES;   // 8 epilogue warps x 4 KB output staging
+  static constexpr int BAR_OFF = STG_OFF + 8 * 4096;
+  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
+  static constexpr int BIAS_OFF = SLOT_OFF + 16;
+  static constexpr int MAX_COUT = 512;
+  static constexpr int TOTAL = BIAS_OFF + MAX_COUT * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
+  static_assert(B_BYTES % 1024 == 0, "weight half-tile must be whole swizzle atoms");
+};
+
+constexpr int CONV2_THREADS = 320;
+
+template <int BN, int MT, bool RES, bool F16>
+__global__ void __launch_bounds__(CONV2_THREADS, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                   const ConvArgs p) {
+  using L = Conv2Cfg<BN, MT, RES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (L::A_STAGES + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + L::B_STAGES + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::SLOT_OFF);
+  float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();     // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int ctot = p.c0 + p.c1;
+  const int chunks = ctot >> 6;
+  const int n_blocks = p.cout / BN;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int mtiles = tiles_per_img * p.B;
+  const int mpairs = (mtiles + 1) >> 1;
+  const int units = mpairs * n_blocks;         // pair-units
+
+  if (threadIdx.x == 0) {
+    // full barriers are only used in the leader: ONE arrival per phase (the leader's arrive.expect_tx, which announces
+    // the bytes of BOTH CTAs); the peer's TMA loads just complete their bytes on it.  Bytes of the peer that land before
+    // the leader's expect_tx leave the transaction count negative while the arrival is still pending: no early phase
+    // flip.  (A remote arrive of the peer's producer per stage -- mbarrier.arrive.release.cluster = MEMBAR + ERRBAR --
+    // serialised its loop to one stage per ~1000 cycles: measured, the whole kernel ran at half speed.)
+    for (int s = 0; s < L::A_STAGES; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < L::B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 16);  // one arrive per epilogue warp of BOTH CTAs (leader's barrier)
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.cout; i += CONV2_THREADS - 64) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone signals them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's pixel tile of pair-unit u (the peer of an odd tile count re-computes the last tile and discards it)
+  auto unit_tile = [&](int u, int& nb, int& img, int& ty, int& tx, bool& ghost) {
+    nb = u % n_blocks;
+    int mtile = 2 * (u / n_blocks) + (int)rank;
+    ghost = mtile >= mtiles;
+    if (ghost) mtile = mtiles - 1;
+    img = mtile / tiles_per_img;
+    const int t = mtile - img * tiles_per_img;
+    ty = t / p.tiles_x;
+    tx = t - ty * p.tiles_x;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    const bool leader_lane = elect_one();
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    if (RES) {
+      // this CTA's half of the whole weight matrix of the (single) n-block: 9 taps x 1 chunk, loaded once
+      const uint32_t bar = mapa_shared(b_full(0), 0);
+      if (leader_lane) {
+        if (rank == 0) mbar_expect_tx(b_full(0), 2 * 9 * L::B_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d_pair(sbase + L::B_OFF + tap * L::B_BYTES, &tmB, bar, tap * ctot, (int)rank * L::BH);
+      }
+      __syncwarp();
+    }
+    for (int u = pair; u < units; u += npairs) {
+      int nb, img, ty, tx;
+      bool ghost;
+      unit_tile(u, nb, img, ty, tx, ghost);
+      const int x0 = tx * 8, y0 = ty * (16 * MT);
+      const int n0 = nb * BN + (int)rank * L::BH;
+      for (int ch = 0; ch < chunks; ++ch) {
+        const int c = ch << 6;
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(a_empty(as), aph ^ 1);
+          if (leader_lane) {
+            const uint32_t bar = mapa_shared(a_full(as), 0);
+            if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_BYTES);
+            const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
+            if (c < p.c0)
+              tma_load_4d_pair(dst, &tmA0, bar, c, x0 + kx - 1, y0 - 1, img);
+            else
+              tma_load_4d_pair(dst, &tmA1, bar, c - p.c0, x0 + kx - 1, y0 - 1, img);
+          }
+          __syncwarp();
+          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+          if (!RES) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(b_empty(bs), bph ^ 1);
+              if (leader_lane) {
+                const uint32_t bar = mapa_shared(b_full(bs), 0);
+                if (rank == 0) mbar_expect_tx(b_full(bs), 2 * L::B_BYTES);
+                tma_load_2d_pair(sbase + L::B_OFF + bs * L::B_BYTES, &tmB, bar, (ky * 3 + kx) * ctot + c, n0);
+              }
+              __syncwarp();
+              if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: the leader CTA only
+    if (rank == 0) {
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, BN) : umma_idesc_bf16(256, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      uint32_t it = 0;
+      if (RES) {
+        mbar_wait(b_full(0), 0);
+        tc_fence_after();
+      }
+      for (int u = pair; u < units; u += npairs, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(acc_empty(buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + buf * (MT * BN);
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(a_full(as), aph);
+            tc_fence_after();
+            const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              uint32_t sb;
+              if (RES) {
+                sb = sbase + L::B_OFF + (ky * 3 + kx) * L::B_BYTES;
+              } else {
+                mbar_wait(b_full(bs), bph);
+                tc_fence_after();
+                sb = sbase + L::B_OFF + bs * L::B_BYTES;
+              }
+              if (leader_lane) {
+                const uint64_t db = umma_desc_k_sw128(sb);
+                const uint32_t acc = (ch | kx | ky) != 0 ? 1u : 0u;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t da = umma_desc_k_sw128(sa + (16 * mt + ky) * 1024);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_pair(dcol + mt * BN, da + 2 * k, db + 2 * k, idesc, (acc | k) != 0 ? 1u : 0u);
+                }
+                if (!RES) umma_commit_pair(b_empty(bs));
+              }
+              __syncwarp();
+              if (!RES) {
+                if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
+              }
+            }
+            if (leader_lane) umma_commit_pair(a_empty(as));
+            __syncwarp();
+            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+          }
+        }
+        if (leader_lane) umma_commit_pair(acc_full(buf));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: 8 warps, one output pixel per thread
+    constexpr int NG = BN / 64;            // 64-channel groups per accumulator
+    constexpr int NSUB = MT * NG;          // [128 px x 64 ch] sub-tiles per unit
+    const int ew = warp - 2;               // 0..7
+    const int wg = ew >> 2;                // warpgroup: takes the sub-tiles with index % 2 == wg
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int lty = row >> 3, ltx = row & 7;
+    const int Hp = p.H >> 1, Wp = p.W >> 1;
+    uint8_t* stage = smem + L::STG_OFF + ew * 4096;
+    const uint32_t stage_u32 = sbase + L::STG_OFF + ew * 4096;
+    const int sw = lane & 7;
+    uint32_t it = 0;
+    for (int u = pair; u < units; u += npairs, ++it) {
+      int nb, img, ty, tx;
+      bool ghost;
+      unit_tile(u, nb, img, ty, tx, ghost);
+      const int n0 = nb * BN;
+      const int x = tx * 8 + ltx;
+      const uint32_t buf = it & 1;
+      const uint32_t acc_empty_leader = mapa_shared(acc_empty(buf), 0);
+      mbar_wait(acc_full(buf), (it >> 1) & 1);
+      tc_fence_after();
+      if (wg >= NSUB) {  // nothing to read for this warpgroup (MT = 1, BN = 64)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+      }
+#pragma unroll 1
+      for (int sub = wg; sub < NSUB; sub += 2) {
+        const int mt = sub / NG, g = sub - mt * NG;
+        const int y = ty * (16 * MT) + mt * 16 + lty;
+        const bool valid = !ghost && (y < p.H) && (x < p.W);
+        const bool pool_owner = valid && !(lty & 1) && !(ltx & 1);
+        __nv_bfloat16* pool_px =
+            p.out_pool
+                ? p.out_pool + ((static_cast<size_t>(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.cout + n0 + g * 64
+                : nullptr;
+        if (p.out) {
+          // the previous TMA store of this warp has finished reading the staging box
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (MT * BN) + mt * BN + g * 64 + cb * 32,
+                    v);
+          uint4 mk[4];
+          if (p.mask) {  // issued before the TMEM wait so that both latencies overlap
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask + ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0 + g * 64 + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mk[j] = valid ? __ldg(mp + j) : make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          if (cb == 1 && sub + 2 >= NSUB) {
+            // last TMEM read of this warp for this unit: hand the accumulator buffer back to the (leader's) MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float tv = __uint_as_float(v[j]) + bias_s[n0 + g * 64 + cb * 32 + j];
+            f[j] = p.relu ? fmaxf(tv, 0.f) : tv;
+          }
+          if (F16) {
+            float vmax = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, fabsf(f[j]));
+            if (p.range_flag != nullptr && __any_sync(0xffffffffu, valid && !(vmax <= F16_MAX)) && lane == 0)
+              atomicOr(p.range_flag, 1);
+          }
+          if (p.mask) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                if (h == 0u || h >= 0x8000u) f[8 * j + e] = 0.f;
+              }
+            }
+          }
+          if (p.out) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_act2<F16>(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_act2<F16>(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_act2<F16>(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_act2<F16>(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((cb * 4 + j) ^ sw) << 4)) = o;
+            }
+          }
+          if (pool_px) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float tv = valid ? f[j] : 0.f;
+              tv += __shfl_xor_sync(0xffffffffu, tv, 1);
+              tv += __shfl_xor_sync(0xffffffffu, tv, 8);
+              f[j] = 0.25f * tv;
+            }
+            if (pool_owner) {
+              uint4* dst = reinterpret_cast<uint4*>(pool_px + cb * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_act2<F16>(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_act2<F16>(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_act2<F16>(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_act2<F16>(f[8 * j + 6], f[8 * j + 7]);
+                dst[j] = o;
+              }
+            }
+          }
+        }
+        if (p.out) {
+          fence_proxy_async_smem();  // staging written by the generic proxy, read by the TMA engine
+          __syncwarp();
+          if (lane == 0 && !ghost) {
+            tma_store_4d(&tmOut, stage_u32, n0 + g * 64, tx * 8, ty * (16 * MT) + mt * 16 + q * 4, img);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
+  }
+
+  // both CTAs are done with each other's shared memory / barriers and with their tensor memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, int MT, bool RES, bool F16>
+static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                            const ConvArgs& args, cudaStream_t stream) {
+  using L = Conv2Cfg<BN, MT, RES>;
+  auto kern = conv3x3_tc2_kernel<BN, MT, RES, F16>;
+  static int configured[64];
+  static int max_clusters[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PDA_ERR_CUDA;
+  if (dyn_smem_attr_needed(configured, L::DYN_BYTES)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess)
+      return PDA_ERR_CUDA;
+    max_clusters[dev] = 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(CONV2_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0) {
+    // how many CTA pairs can be resident at once (74 on a full B200: one per TPC)
+    cfg.gridDim = dim3(148);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) return PDA_ERR_CUDA;
+    max_clusters[dev] = n > 74 ? 74 : n;
+    if (getenv("PDA_DEBUG")) fprintf(stderr, "[pda] conv3x3_tc2<%d,%d,%d,%d>: max active clusters %d\n", BN, MT, (int)RES, (int)F16, n);
+  }
+  const long long mtiles = (long long)args.tiles_x * args.tiles_y * args.B;
+  const long long units = ((mtiles + 1) / 2) * (args.cout / BN);
+  if (units > 0x3fffffffLL) return PDA_ERR_SHAPE;
+  const int pairs = (int)(units < max_clusters[dev] ? units : max_clusters[dev]);
+  cfg.gridDim = dim3(2 * pairs);
+  PDA_COUNT(1);
+  if (cudaLaunchKernelEx(&cfg, kern, a0, a1, b, o, args) != cudaSuccess) return PDA_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+}
+
+template <int BN, int MT, bool RES>
+static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                        const ConvArgs& args, cudaStream_t stream) {
+  return args.act_f16 ? launch_conv2_fmt<BN, MT, RES, true>(a0, a1, b, o, args, stream)
+                      : launch_conv2_fmt<BN, MT, RES, false>(a0, a1, b, o, args, stream);
+}
+
+// same contract as conv3x3_tc (csrc/conv3x3_tc.cu); selected by it for shapes with at least two pixel tiles
+int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
+                void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
+                int act_f16, int* range_flag, cudaStream_t stream) {
+  if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
+    return PDA_ERR_SHAPE;
+  if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
+  int bn = (bn_override == 64 || bn_override == 128 || bn_override == 256)
+               ? bn_override
+               : ((cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : 64);
+  if (cout % bn) return PDA_ERR_SHAPE;
+  const int mt = (H > 16 && bn != 256) ? 2 : 1;
+  ConvArgs a;
+  a.B = B; a.H = H; a.W = W; a.c0 = c0; a.c1 = c1; a.cout = cout; a.relu = relu;
+  a.tile_w = 8;
+  a.tile_h = 16 * mt;
+  a.tiles_x = (W + 7) / 8;
+  a.tiles_y = (H + a.tile_h - 1) / a.tile_h;
+  a.bias = bias;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
+  a.mask = static_cast<const __nv_bfloat16*>(mask);
+  a.act_f16 = act_f16;
+  a.range_flag = act_f16 ? range_flag : nullptr;
+  CUtensorMap tA0, tA1, tB;
+  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);
+  if (r) return r;
+  if (c1 > 0) {
+    r = make_act_tensor_map(&tA1, src1, B, H, W, c1, 8, a.tile_h + 2, 64);
+    if (r) return r;
+  } else {
+    tA1 = tA0;
+  }
+  r = make_mat_tensor_map(&tB, wpacked, 9LL * (c0 + c1), cout, 64, bn / 2);  // one CTA loads half the rows
+  if (r) return r;
+  CUtensorMap tO = tA0;  // unused when out == nullptr
+  if (out) {
+    r = make_act_tensor_map(&tO, out, B, H, W, cout, 8, 4, 64);
+    if (r) return r;
+  }
+  const bool resident = (bn == 64 && cout == 64 && c0 + c1 == 64 && mt == 2);
+  if (mt == 2) {
+    if (bn == 128) return launch_conv2<128, 2, false>(tA0, tA1, tB, tO, a, stream);
+    return resident ? launch_conv2<64, 2, true>(tA0, tA1, tB, tO, a, stream)
+                    : launch_conv2<64, 2, false>(tA0, tA1, tB, tO, a, stream);
+  }
+  if (bn == 256) return launch_conv2<256, 1, false>(tA0, tA1, tB, tO, a, stream);
+  if (bn == 128) return launch_conv2<128, 1, false>(tA0, tA1, tB, tO, a, stream);
+  return launch_conv2<64, 1, false>(tA0, tA1, tB, tO, a, stream);
+}
+
+}  // namespace pda

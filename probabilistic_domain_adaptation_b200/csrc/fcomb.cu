@@ -23,7 +23,7 @@ fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
                 const float* __restrict__ w3, const float* __restrict__ b3, int P, int S, int L, int B, float upper,
                 float lower, float* __restrict__ mean_prob, float* __restrict__ cons_weight,
                 int64_t* __restrict__ cons_mask, float* __restrict__ logits, float* __restrict__ probs,
-                const int* __restrict__ run_flag, int blocks_per_img, int num_blocks) {
+                const int* __restrict__ run_flag, int blocks_per_img, int num_blocks, int feat_f16) {
   // run_flag != nullptr: this launch is the fp16-overflow fallback of the tensor-core kernel and only runs when the
   // flag is up (csrc/fcomb_tc.cu)
   if (run_flag != nullptr && *run_flag == 0) return;
@@ -68,10 +68,10 @@ fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < FC / 8; ++k) {
       const uint4 v = __ldg(src + k);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 t = __bfloat1622float2(h[i]);
+        const float2 t = feat_f16 ? unpack_act2<true>(w4[i]) : unpack_act2<false>(w4[i]);
         f[8 * k + 2 * i] = t.x;
         f[8 * k + 2 * i + 1] = t.y;
       }
@@ -131,7 +131,7 @@ fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
 int fcomb_mc_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* b3, int B, int P, int S, int latent, float upper, float lower,
                   float* mean_prob, float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
-                  const int* run_flag, cudaStream_t stream) {
+                  const int* run_flag, int feat_f16, cudaStream_t stream) {
   const size_t smem = (size_t)(2 * FC * FC + 2 * FC + S * FC) * sizeof(float);
   if (smem > 200 * 1024) return PDA_ERR_SHAPE;
   static int configured[64];
@@ -149,7 +149,7 @@ int fcomb_mc_fp32(const void* feat, const float* z, const float* w1, const float
   PDA_COUNT(1);
   fcomb_mc_kernel<<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(feat), z, w1, b1, w2, b2, w3, b3, P,
                                                S, latent, B, upper, lower, mean_prob, cons_weight, cons_mask, logits,
-                                               probs, run_flag, blocks_per_img, (int)num_blocks);
+                                               probs, run_flag, blocks_per_img, (int)num_blocks, feat_f16);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
@@ -161,9 +161,9 @@ extern "C" int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, con
                                       const float* w2, const float* b2, const float* w3, const float* b3, int B, int P,
                                       int S, int latent, float upper, float lower, float* mean_prob,
                                       float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
-                                      void* stream) {
+                                      int feat_f16, void* stream) {
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) return PDA_ERR_ARG;
   if (B <= 0 || P <= 0 || S <= 0 || latent <= 0) return PDA_ERR_SHAPE;
   return fcomb_mc_fp32(feat, z, w1, b1, w2, b2, w3, b3, B, P, S, latent, upper, lower, mean_prob, cons_weight,
-                       cons_mask, logits, probs, nullptr, (cudaStream_t)stream);
+                       cons_mask, logits, probs, nullptr, feat_f16, (cudaStream_t)stream);
 }

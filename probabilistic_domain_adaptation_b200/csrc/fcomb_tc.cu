@@ -39,9 +39,9 @@ constexpr int FC_THREADS = 288;
 constexpr float FC_F16_SAFE = 32000.f;
 
 // last layer w3[64]: the first FC_W3_REG entries live in the epilogue threads' registers, the rest is read from shared
-// memory as warp-wide broadcast LDS.128 (the 96-register cap of 2 CTAs/SM does not leave room for all 64: 48 is the most ptxas allocates without spilling)
+// memory as warp-wide broadcast LDS.128 (measured at 4 x 1024^2, S = 16: all 64 from shared memory 1.03 ms, 48 in registers 1.08 ms, 64 in registers -- which spills under the 96-register cap of 2 CTAs/SM -- 1.10 ms; profiles/r02_fcomb_w3_variants.md)
 #ifndef FC_W3_REG
-#define FC_W3_REG 48
+#define FC_W3_REG 0
 #endif
 
 struct FcombSmem {
@@ -106,8 +106,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // fp32 [64][ld] weights (first 64 columns) -> K-major SWIZZLE_128B operand tiles in shared memory:
-// bf16 hi + bf16 lo (w ~= hi + lo) when dst_lo != nullptr, else a single fp16 tile.
-__device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo, const float* __restrict__ w, int ld) {
+// hi + lo (w ~= hi + lo; bf16 pair, or fp16 pair when f16) when dst_lo != nullptr, else a single fp16 tile.
+__device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo, const float* __restrict__ w, int ld,
+                                                   bool f16 = false) {
   for (int i = threadIdx.x; i < FCT * 8; i += blockDim.x) {
     const int n = i >> 3, c = i & 7;  // row n, 16-byte chunk c (8 k-values)
     const float* src = w + n * ld + c * 8;
@@ -115,7 +116,11 @@ __device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float a = src[2 * j], b = src[2 * j + 1];
-      if (dst_lo) {
+      if (dst_lo && f16) {
+        const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+        hi[j] = pack_f16x2(a, b);
+        lo[j] = pack_f16x2(a - ah, b - bh);
+      } else if (dst_lo) {
         const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
         hi[j] = pack_bf16x2(a, b);
         lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
@@ -132,7 +137,7 @@ __device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo
 __global__ void __launch_bounds__(FC_THREADS, 2)
 fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ bzg, const float* __restrict__ w1,
                 const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
-                const float* __restrict__ b3, int* __restrict__ oflag, int P, int S, int L, int B,
+                const float* __restrict__ b3, int* __restrict__ oflag, int feat_f16, int P, int S, int L, int B,
                 int tiles_per_img, int num_tiles, float upper, float lower, float* __restrict__ mean_prob,
                 float* __restrict__ cons_weight, int64_t* __restrict__ cons_mask, float* __restrict__ logits,
                 float* __restrict__ probs) {
@@ -171,7 +176,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), FC_TMEM_COLS);
     tmem_relinquish();
   }
-  stage_weight_sw128(smem + M::W1_OFF, smem + M::W1L_OFF, w1, kin);
+  stage_weight_sw128(smem + M::W1_OFF, smem + M::W1L_OFF, w1, kin, feat_f16 != 0);  // same format as the features
   stage_weight_sw128(smem + M::W2_OFF, nullptr, w2, FCT);
   // K-extension tiles: B rows n carry (b2_hi, b2_lo) in k = 0, 1; the A rows carry (1, 1).  Only the first 16 k
   // (two 16-byte chunks) of each 128-byte row are read by the K = 16 MMA.
@@ -338,7 +343,8 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     // ================================================================ control: TMA + every tcgen05.mma
     // warp-uniform control flow (addresses / descriptors stay in uniform registers); one elected lane issues
     const bool leader = elect_one();
-    constexpr uint32_t idesc1 = umma_idesc_bf16(128, FCT);  // F (bf16) x W1 hi/lo (bf16)
+    // F x W1 hi/lo: bf16 x bf16, or fp16 x fp16 when the trunk ran with fp16 activations
+    const uint32_t idesc1 = feat_f16 ? umma_idesc_f16(128, FCT) : umma_idesc_bf16(128, FCT);
     constexpr uint32_t idesc2 = umma_idesc_f16(128, FCT);   // A1 (fp16) x W2 (fp16)
     const uint64_t dW1 = umma_desc_k_sw128(sbase + M::W1_OFF);
     const uint64_t dW1L = umma_desc_k_sw128(sbase + M::W1L_OFF);
@@ -442,7 +448,7 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
                                       const float* w2, const float* b2, const float* w3, const float* b3, int B, int P,
                                       int S, int latent, float upper, float lower, float* mean_prob,
                                       float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
-                                      float* scratch, void* stream) {
+                                      float* scratch, int feat_f16, void* stream) {
   if (!feat || !z || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !scratch) return PDA_ERR_ARG;
   if (B <= 0 || P <= 0 || S <= 0 || latent <= 0) return PDA_ERR_SHAPE;
   if (S > 640) return PDA_ERR_SHAPE;  // the fp32 range-guard fallback stages bz[S][64] fp32 in shared memory
@@ -477,12 +483,12 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   float* bz = scratch + 4;
   PDA_COUNT(2);
   fcomb_bz_kernel<<<1, 1024, 0, st>>>(z, w1, b1, bz, S * B, latent, oflag);
-  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, w3, b3, oflag, P, S, latent, B, tiles_per_img,
+  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, w3, b3, oflag, feat_f16, P, S, latent, B, tiles_per_img,
                                                   (int)num_tiles, upper, lower, mean_prob, cons_weight, cons_mask,
                                                   logits, probs);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
   // fp16 range guard: when the flag is up, the exact fp32 kernel overwrites every output of this call (device-side
   // decision, no host synchronisation; its blocks exit at once otherwise)
   return fcomb_mc_fp32(feat, z, w1, b1, w2, b2, w3, b3, B, P, S, latent, upper, lower, mean_prob, cons_weight,
-                       cons_mask, logits, probs, oflag, st);
+                       cons_mask, logits, probs, oflag, feat_f16, st);
 }

@@ -11,8 +11,13 @@ namespace pda {
 // ------------------------------------------------------------------------------------------------
 // OIHW fp32 -> [cout][tap][cin] bf16   (rot180: [cin][8-tap][cout], the dgrad operand)
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int cout, int cin,
-                              int rot180) {
+__device__ __forceinline__ uint16_t w16(float v, int f16) {
+  // 16-bit weight operand: bf16, or fp16 (saturating) for the fp16-activation inference path
+  return f16 ? (uint16_t)(pack_f16x2_sat(v, 0.f) & 0xffffu) : (uint16_t)(pack_bf16x2(v, 0.f) & 0xffffu);
+}
+
+__global__ void pack_w_kernel(const float* __restrict__ w, uint16_t* __restrict__ o, int cout, int cin,
+                              int rot180, int f16) {
   const long long n = 9LL * cout * cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     // i indexes the OUTPUT so writes are coalesced
@@ -20,39 +25,43 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
       const int ci = i % cin;
       const int tap = (i / cin) % 9;
       const int co = i / (9LL * cin);
-      o[i] = __float2bfloat16(w[((long long)co * cin + ci) * 9 + tap]);
+      o[i] = w16(w[((long long)co * cin + ci) * 9 + tap], f16);
     } else {
       const int co = i % cout;
       const int tap = (i / cout) % 9;
       const int ci = i / (9LL * cout);
-      o[i] = __float2bfloat16(w[((long long)co * cin + ci) * 9 + (8 - tap)]);
+      o[i] = w16(w[((long long)co * cin + ci) * 9 + (8 - tap)], f16);
     }
   }
 }
 
-// multi-tensor variant: one launch refreshes the bf16 operands of many convs after an optimizer / EMA step.
-// table rows: (w_ptr, packed_ptr, rot_ptr or 0, cout, cin, first output element of this chunk); chunk = 16384 outputs
+// multi-tensor variant: one launch refreshes the 16-bit operands of many convs after an optimizer / EMA step.
+// table rows: (w_ptr, bf16 packed_ptr or 0, bf16 rot_ptr or 0, fp16 packed_ptr or 0, cout, cin, first output element of
+// this chunk); chunk = 16384 outputs
 __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __restrict__ table) {
-  const long long* e = table + 6LL * blockIdx.x;
+  const long long* e = table + 7LL * blockIdx.x;
   const float* w = reinterpret_cast<const float*>(e[0]);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e[1]);
-  __nv_bfloat16* orot = reinterpret_cast<__nv_bfloat16*>(e[2]);
-  const int cout = (int)e[3], cin = (int)e[4];
-  const int start = (int)e[5];
+  uint16_t* o = reinterpret_cast<uint16_t*>(e[1]);
+  uint16_t* orot = reinterpret_cast<uint16_t*>(e[2]);
+  uint16_t* oh = reinterpret_cast<uint16_t*>(e[3]);
+  const int cout = (int)e[4], cin = (int)e[5];
+  const int start = (int)e[6];
   const int n = 9 * cout * cin;
   const int end = min(n, start + 16384);
   for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
-    {
+    if (o || oh) {
       const int ci = i % cin;
       const int tap = (i / cin) % 9;
       const int co = i / (9 * cin);
-      o[i] = __float2bfloat16(w[(co * cin + ci) * 9 + tap]);
+      const float v = w[(co * cin + ci) * 9 + tap];
+      if (o) o[i] = w16(v, 0);
+      if (oh) oh[i] = w16(v, 1);
     }
     if (orot) {
       const int co = i % cout;
       const int tap = (i / cout) % 9;
       const int ci = i / (9 * cout);
-      orot[i] = __float2bfloat16(w[(co * cin + ci) * 9 + (8 - tap)]);
+      orot[i] = w16(w[(co * cin + ci) * 9 + (8 - tap)], 0);
     }
   }
 }
@@ -77,7 +86,7 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   return r;
 }
 
-template <int CIN>
+template <int CIN, bool F16>
 __global__ void __launch_bounds__(256)
 conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ w,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int cout,
@@ -148,10 +157,10 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
           for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
         }
         uint4 o;
-        o.x = pack_bf16x2(a[0], a[1]);
-        o.y = pack_bf16x2(a[2], a[3]);
-        o.z = pack_bf16x2(a[4], a[5]);
-        o.w = pack_bf16x2(a[6], a[7]);
+        o.x = pack_act2<F16>(a[0], a[1]);
+        o.y = pack_act2<F16>(a[2], a[3]);
+        o.z = pack_act2<F16>(a[4], a[5]);
+        o.w = pack_act2<F16>(a[6], a[7]);
         *reinterpret_cast<uint4*>(orow + (size_t)px * cout) = o;
       }
     }
@@ -161,27 +170,30 @@ conv_first_kernel(const float* __restrict__ x0, const float* __restrict__ x1, co
 // ------------------------------------------------------------------------------------------------
 // 2x2 average pool, NHWC bf16, 8 channels (16 B) per thread
 // ------------------------------------------------------------------------------------------------
+template <bool F16 = false>
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
+    const float2 t = unpack_act2<F16>(w4[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
+template <bool F16 = false>
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]);
-  o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]);
-  o.w = pack_bf16x2(f[6], f[7]);
+  o.x = pack_act2<F16>(f[0], f[1]);
+  o.y = pack_act2<F16>(f[2], f[3]);
+  o.z = pack_act2<F16>(f[4], f[5]);
+  o.w = pack_act2<F16>(f[6], f[7]);
   return o;
 }
 
 // The NHWC elementwise kernels use a 2-D decomposition: blockIdx.x / threadIdx.x cover (x, 16-byte channel chunk) of
 // one output row, blockIdx.y strides over the B * H output rows: one 32-bit division per row instead of three 64-bit
 // ones per element.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int c_shift) {
   const unsigned Ho = H >> 1, Wo = W >> 1;
@@ -193,17 +205,17 @@ avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, in
     const unsigned b = r / Ho, y = r - b * Ho;
     const size_t base = ((((size_t)b * H + 2 * y) * W + 2 * x) << c_shift) + c;
     float a[8], s[8];
-    unpack8(__ldg(in + base), s);
-    unpack8(__ldg(in + base + C8), a);
+    unpack8<F16>(__ldg(in + base), s);
+    unpack8<F16>(__ldg(in + base + C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += a[i];
-    unpack8(__ldg(in + base + (size_t)W * C8), a);
+    unpack8<F16>(__ldg(in + base + (size_t)W * C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += a[i];
-    unpack8(__ldg(in + base + (size_t)W * C8 + C8), a);
+    unpack8<F16>(__ldg(in + base + (size_t)W * C8 + C8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = (s[i] + a[i]) * 0.25f;
-    out[((size_t)r * Wo << c_shift) + xc] = pack8(s);
+    out[((size_t)r * Wo << c_shift) + xc] = pack8<F16>(s);
   }
 }
 
@@ -217,9 +229,8 @@ avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, in
 // was instruction-bound (ncu: ALU pipe 61 %, issue slots 73 %, 38 % of the HBM roofline).  The first row / column pair
 // (both outputs start in the same input row / column) takes the plain four-neighbour path.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
-  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-}
+template <bool F16>
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return unpack_act2<F16>(w); }
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int k) {
   return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
 }
@@ -228,20 +239,22 @@ __device__ __forceinline__ void set_word(uint4& v, int k, uint32_t w) {
 }
 
 // one output pixel from its four neighbours (the arithmetic of the reference, channel pair by channel pair)
+template <bool F16>
 __device__ __forceinline__ uint4 bilerp4(const uint4& q00, const uint4& q01, const uint4& q10, const uint4& q11,
                                          float lx0, float lx1, float l0, float l1) {
   uint4 o;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float2 a = bf2_to_f2(word_of(q00, k)), b = bf2_to_f2(word_of(q01, k));
-    const float2 c = bf2_to_f2(word_of(q10, k)), d = bf2_to_f2(word_of(q11, k));
+    const float2 a = bf2_to_f2<F16>(word_of(q00, k)), b = bf2_to_f2<F16>(word_of(q01, k));
+    const float2 c = bf2_to_f2<F16>(word_of(q10, k)), d = bf2_to_f2<F16>(word_of(q11, k));
     const float ox = l0 * (lx0 * a.x + lx1 * b.x) + l1 * (lx0 * c.x + lx1 * d.x);
     const float oy = l0 * (lx0 * a.y + lx1 * b.y) + l1 * (lx0 * c.y + lx1 * d.y);
-    set_word(o, k, pack_bf16x2(ox, oy));
+    set_word(o, k, pack_act2<F16>(ox, oy));
   }
   return o;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, int w, int c_shift) {
   const unsigned Ho = 2 * h, Wo = 2 * w;
@@ -278,9 +291,9 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, 
       uint4 oaa, oab, oba, obb;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 v00 = bf2_to_f2(word_of(q00, k)), v01 = bf2_to_f2(word_of(q01, k)), v02 = bf2_to_f2(word_of(q02, k));
-        const float2 v10 = bf2_to_f2(word_of(q10, k)), v11 = bf2_to_f2(word_of(q11, k)), v12 = bf2_to_f2(word_of(q12, k));
-        const float2 v20 = bf2_to_f2(word_of(q20, k)), v21 = bf2_to_f2(word_of(q21, k)), v22 = bf2_to_f2(word_of(q22, k));
+        const float2 v00 = bf2_to_f2<F16>(word_of(q00, k)), v01 = bf2_to_f2<F16>(word_of(q01, k)), v02 = bf2_to_f2<F16>(word_of(q02, k));
+        const float2 v10 = bf2_to_f2<F16>(word_of(q10, k)), v11 = bf2_to_f2<F16>(word_of(q11, k)), v12 = bf2_to_f2<F16>(word_of(q12, k));
+        const float2 v20 = bf2_to_f2<F16>(word_of(q20, k)), v21 = bf2_to_f2<F16>(word_of(q21, k)), v22 = bf2_to_f2<F16>(word_of(q22, k));
         // horizontal blends: column pair a = (xa, xa+1), b = (xb, xb+xpb)
         const float a0x = lxa0 * v00.x + lxa1 * v01.x, a0y = lxa0 * v00.y + lxa1 * v01.y;
         const float a1x = lxa0 * v10.x + lxa1 * v11.x, a1y = lxa0 * v10.y + lxa1 * v11.y;
@@ -288,10 +301,10 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, 
         const float b0x = lxb0 * v01.x + lxb1 * v02.x, b0y = lxb0 * v01.y + lxb1 * v02.y;
         const float b1x = lxb0 * v11.x + lxb1 * v12.x, b1y = lxb0 * v11.y + lxb1 * v12.y;
         const float b2x = lxb0 * v21.x + lxb1 * v22.x, b2y = lxb0 * v21.y + lxb1 * v22.y;
-        set_word(oaa, k, pack_bf16x2(lya0 * a0x + lya1 * a1x, lya0 * a0y + lya1 * a1y));
-        set_word(oab, k, pack_bf16x2(lya0 * b0x + lya1 * b1x, lya0 * b0y + lya1 * b1y));
-        set_word(oba, k, pack_bf16x2(lyb0 * a1x + lyb1 * a2x, lyb0 * a1y + lyb1 * a2y));
-        set_word(obb, k, pack_bf16x2(lyb0 * b1x + lyb1 * b2x, lyb0 * b1y + lyb1 * b2y));
+        set_word(oaa, k, pack_act2<F16>(lya0 * a0x + lya1 * a1x, lya0 * a0y + lya1 * a1y));
+        set_word(oab, k, pack_act2<F16>(lya0 * b0x + lya1 * b1x, lya0 * b0y + lya1 * b1y));
+        set_word(oba, k, pack_act2<F16>(lyb0 * a1x + lyb1 * a2x, lyb0 * a1y + lyb1 * a2y));
+        set_word(obb, k, pack_act2<F16>(lyb0 * b1x + lyb1 * b2x, lyb0 * b1y + lyb1 * b2y));
       }
       o0[0] = oaa;
       o0[C8] = oab;
@@ -310,7 +323,7 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, 
           const uint4* p = img + (((size_t)y1 * w + x1) << c_shift);
           const uint4 q00 = __ldg(p), q01 = __ldg(p + ((size_t)xp << c_shift));
           const uint4 q10 = __ldg(p + (((size_t)yp * w) << c_shift)), q11 = __ldg(p + (((size_t)yp * w + xp) << c_shift));
-          (u ? o1 : o0)[v ? C8 : 0] = bilerp4(q00, q01, q10, q11, lx0, lx1, l0, l1);
+          (u ? o1 : o0)[v ? C8 : 0] = bilerp4<F16>(q00, q01, q10, q11, lx0, lx1, l0, l1);
         }
       }
     }
@@ -322,16 +335,17 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, 
 // ------------------------------------------------------------------------------------------------
 constexpr int HEAD_ROWS_PER_BLOCK = 64;  // pixels reduced per stage-1 block
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
-mean_partial_kernel(const __nv_bfloat162* __restrict__ enc, float* __restrict__ partial, int P, int C2, int nchunk) {
+mean_partial_kernel(const uint32_t* __restrict__ enc, float* __restrict__ partial, int P, int C2, int nchunk) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int p0 = chunk * HEAD_ROWS_PER_BLOCK;
   const int p1 = min(P, p0 + HEAD_ROWS_PER_BLOCK);
   for (int c = threadIdx.x; c < C2; c += blockDim.x) {
     float sx = 0.f, sy = 0.f;
-    const __nv_bfloat162* src = enc + ((long long)b * P + p0) * C2 + c;
+    const uint32_t* src = enc + ((long long)b * P + p0) * C2 + c;
     for (int p = p0; p < p1; ++p, src += C2) {
-      const float2 v = __bfloat1622float2(__ldg(src));
+      const float2 v = unpack_act2<F16>(__ldg(src));
       sx += v.x;
       sy += v.y;
     }
@@ -555,12 +569,12 @@ using namespace pda;
 
 extern "C" {
 
-int pda_pack_conv3x3_weights(const float* w, void* o, int cout, int cin, int rot180, void* stream) {
+int pda_pack_conv3x3_weights(const float* w, void* o, int cout, int cin, int rot180, int f16, void* stream) {
   if (!w || !o) return PDA_ERR_ARG;
   if (cout <= 0 || cin <= 0) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
   pack_w_kernel<<<grid_for(9LL * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, static_cast<__nv_bfloat16*>(o), cout, cin, rot180);
+      w, static_cast<uint16_t*>(o), cout, cin, rot180, f16);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
@@ -573,7 +587,7 @@ int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* str
 }
 
 int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const float* bias, void* out, int B, int H,
-                      int W, int cout, int relu, void* stream) {
+                      int W, int cout, int relu, int act_f16, void* stream) {
   if (!x0 || !w || !bias || !out) return PDA_ERR_ARG;
   if (cout <= 0 || (cout & 7) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
   const int groups = cout >> 3;
@@ -583,22 +597,28 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
   const int cin = x1 ? 2 : 1;
   const size_t smem = sizeof(float) * (cin * 9 * cout + cout);
   PDA_COUNT(1);
-  if (x1)
-    conv_first_kernel<2><<<grid_for(quads * groups, 256, 148 * 6), 256, smem, (cudaStream_t)stream>>>(
-        x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
-  else
-    conv_first_kernel<1><<<grid_for(quads * groups, 256, 148 * 6), 256, smem, (cudaStream_t)stream>>>(
-        x0, x1, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, cout, relu);
+  const int grid = grid_for(quads * groups, 256, 148 * 6);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (x1) {
+    if (act_f16) conv_first_kernel<2, true><<<grid, 256, smem, st>>>(x0, x1, w, bias, o, B, H, W, cout, relu);
+    else conv_first_kernel<2, false><<<grid, 256, smem, st>>>(x0, x1, w, bias, o, B, H, W, cout, relu);
+  } else {
+    if (act_f16) conv_first_kernel<1, true><<<grid, 256, smem, st>>>(x0, x1, w, bias, o, B, H, W, cout, relu);
+    else conv_first_kernel<1, false><<<grid, 256, smem, st>>>(x0, x1, w, bias, o, B, H, W, cout, relu);
+  }
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
-int pda_conv3x3_bf16(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
-                     void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
-                     int bn_tile, void* stream) {
+int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                   void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
+                   int bn_tile, int act_f16, int* range_flag, void* stream) {
   if (!src0 || !w_packed || (!out && !out_pool) || (c1 > 0 && !src1)) return PDA_ERR_ARG;
   return conv3x3_tc(src0, c0, src1, c1, w_packed, bias, out, out_pool, relu_mask, B, H, W, cout, relu, bn_tile,
-                    (cudaStream_t)stream);
+                    act_f16, range_flag, (cudaStream_t)stream);
 }
+
+int pda_set_conv_pair(int mode) { return conv_pair_mode(mode); }
 
 int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                           const float* bias, void* out, void* out_pool, int B, int H, int W, int cout, int relu,
@@ -625,18 +645,22 @@ int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, co
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
-int pda_avgpool2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+int pda_avgpool2(const void* in, void* out, int B, int H, int W, int C, int act_f16, void* stream) {
   if (!in || !out) return PDA_ERR_ARG;
   if ((H & 1) || (W & 1) || B <= 0 || c8_shift(C) < 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   if (total >= 0x7fffffffLL) return PDA_ERR_SHAPE;
   PDA_COUNT(1);
-  avgpool2_kernel<<<row_grid((W / 2) * (C / 8), B * (H / 2)), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c8_shift(C));
+  if (act_f16)
+    avgpool2_kernel<true><<<row_grid((W / 2) * (C / 8), B * (H / 2)), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c8_shift(C));
+  else
+    avgpool2_kernel<false><<<row_grid((W / 2) * (C / 8), B * (H / 2)), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
-int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+int pda_upsample2x_bilinear(const void* in, void* out, int B, int h, int w, int C, int act_f16, void* stream) {
   if (!in || !out) return PDA_ERR_ARG;
   if (c8_shift(C) < 0 || B <= 0 || h <= 0 || w <= 0) return PDA_ERR_SHAPE;
   const long long total = (long long)B * (2 * h) * (2 * w) * (C / 8);
@@ -645,22 +669,30 @@ int pda_upsample2x_bilinear_bf16(const void* in, void* out, int B, int h, int w,
   if (B > 65535) return PDA_ERR_SHAPE;
   dim3 grid = row_grid((long long)w * (C / 8), h, (148 * 8 + B - 1) / B);
   grid.z = B;
-  upsample2x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), h, w,
-                                                           c8_shift(C));
+  if (act_f16)
+    upsample2x_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(in),
+                                                                   static_cast<uint4*>(out), h, w, c8_shift(C));
+  else
+    upsample2x_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(in),
+                                                                    static_cast<uint4*>(out), h, w, c8_shift(C));
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
 int pda_gauss_head_scratch_rows(int P) { return (P + HEAD_ROWS_PER_BLOCK - 1) / HEAD_ROWS_PER_BLOCK; }
 
 int pda_gauss_head(const void* enc, const float* w_head, const float* b_head, float* scratch, float* mu_logsigma,
-                   int B, int P, int C, int latent, void* stream) {
+                   int B, int P, int C, int latent, int act_f16, void* stream) {
   if (!enc || !w_head || !b_head || !scratch || !mu_logsigma) return PDA_ERR_ARG;
   if (B <= 0 || P <= 0 || C <= 0 || (C & 1) || latent <= 0 || C * sizeof(float) > 48 * 1024) return PDA_ERR_SHAPE;
   const int nchunk = pda_gauss_head_scratch_rows(P);
   cudaStream_t st = (cudaStream_t)stream;
   PDA_COUNT(2);
-  mean_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(static_cast<const __nv_bfloat162*>(enc), scratch, P, C / 2,
-                                                       nchunk);
+  if (act_f16)
+    mean_partial_kernel<true><<<dim3(nchunk, B), 256, 0, st>>>(static_cast<const uint32_t*>(enc), scratch, P, C / 2,
+                                                               nchunk);
+  else
+    mean_partial_kernel<false><<<dim3(nchunk, B), 256, 0, st>>>(static_cast<const uint32_t*>(enc), scratch, P, C / 2,
+                                                                nchunk);
   gauss_head_kernel<<<B, 256, C * sizeof(float), st>>>(scratch, w_head, b_head, mu_logsigma, P, C, nchunk,
                                                        2 * latent);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;

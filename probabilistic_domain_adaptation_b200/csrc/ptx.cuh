@@ -228,4 +228,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---------------------------------------------------------------- activation storage format
+// NHWC activations are 16-bit: bf16 (training path: the gradients need the fp32 exponent range) or fp16 (no-grad /
+// inference path: 11-bit mantissa = 1/8 of the rounding error per layer; fp16 is also the dtype the reference's own
+// training forward runs in under torch_em's autocast).  fp16 conversions saturate at +-65504 (never inf); kernels that
+// can produce large values also raise a range flag.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  if (F16) return pack_f16x2_sat(lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_act2(uint32_t v) {
+  if (F16) {
+    float2 r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(v));
+    return r;
+  }
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+constexpr float F16_MAX = 65504.f;
+
 }  // namespace pda

@@ -194,6 +194,8 @@ class ProbabilisticUnet(nn.Module):
     # ------------------------------------------------------------------ reference protocol
     def forward(self, patch, segm, training=True):
         """Caches prior (and posterior, if training) latent spaces and the U-Net features; returns None (:285-293)."""
+        if patch.is_cuda and not torch.is_grad_enabled():
+            ops.poll_fp16_range(patch.device)  # fp16 range guard of the no-grad path (asynchronous, see ops.py)
         if training:
             self.posterior_latent_space = self.posterior.forward(patch, segm)
         self.prior_latent_space = self.prior.forward(patch)

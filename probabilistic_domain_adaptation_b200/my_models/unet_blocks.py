@@ -14,10 +14,13 @@ from .utils import init_weights
 
 
 def as_nhwc(x):
-    """Logical NCHW tensor (any dtype / memory format) -> contiguous (B,H,W,C) bf16."""
-    if x.dtype == torch.bfloat16 and x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+    """Logical NCHW tensor (any dtype / memory format) -> contiguous (B,H,W,C) 16-bit activations (an existing bf16 / fp16
+    tensor keeps its format; anything else becomes the training format under autograd, the no-grad format otherwise)."""
+    if x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous():
         return x.permute(0, 2, 3, 1)
-    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    dtype = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else \
+        (ops.TRAIN_DTYPE if (torch.is_grad_enabled() and x.requires_grad) else ops.INFER_DTYPE)
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
 def as_nchw(x_nhwc):

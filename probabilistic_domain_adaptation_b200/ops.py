@@ -3,9 +3,23 @@
 Internal activation layout: contiguous (B, H, W, C) bf16 tensors ("NHWC").  Images, labels and
 single-channel outputs are fp32 (B, 1, H, W) == (B, H, W, 1).
 """
+import os
+import warnings
+
 import torch
 
 from . import _lib
+
+# Storage format of the NHWC activations on the NO-GRAD path (Monte-Carlo inference, teacher, prediction): fp16 keeps
+# 11 mantissa bits per layer instead of bf16's 8, which is what brings the sampled logits of the 21-layer trunk within
+# the 1e-2 tolerance at full image sizes (tests/test_gpu_baseline_shapes.py); it is also the dtype the reference's own
+# student forward runs in under torch_em's autocast.  The training path always uses bf16 (its activation gradients
+# need the fp32 exponent range).  PDA_INFER_DTYPE=bf16 selects bf16 everywhere; the fp16 range guard below switches to
+# bf16 by itself if an activation ever exceeds +-65504.
+INFER_DTYPE = torch.bfloat16 if os.environ.get("PDA_INFER_DTYPE", "fp16").lower() in ("bf16", "bfloat16") \
+    else torch.float16
+TRAIN_DTYPE = torch.bfloat16
+_ACT_DTYPES = (torch.bfloat16, torch.float16)
 
 
 # When set to a list, every tensor-core conv / fused-Fcomb launch appends (kind, start_event, end_event, work)
@@ -51,47 +65,119 @@ def _need_cuda(*ts):
             raise _lib.PdaError("libpda_b200 kernels need CUDA tensors; this package has no CPU fallback")
 
 
-def pack_conv3x3_weights(w, rot180=False):
-    """(cout, cin, 3, 3) fp32 -> (cout, 9*cin) bf16 K-major  [rot180: (cin, 9*cout)]."""
+# ------------------------------------------------------------------------------------------------
+# fp16 range guard: one sticky device flag per GPU, set by the conv epilogues when an fp16 store saturated
+# ------------------------------------------------------------------------------------------------
+_RANGE = {}
+
+
+def _range_state(dev):
+    st = _RANGE.get(dev)
+    if st is None:
+        st = {"flag": torch.zeros(1, dtype=torch.int32, device=dev), "host": torch.zeros(1, dtype=torch.int32).pin_memory(),
+              "event": torch.cuda.Event(), "pending": False}
+        _RANGE[dev] = st
+    return st
+
+
+def range_flag(dev):
+    """The device int32[1] the fp16 kernels OR a 1 into when a value left the fp16 range (sticky)."""
+    return _range_state(dev)["flag"]
+
+
+def _range_exceeded(dev):
+    global INFER_DTYPE
+    _range_state(dev)["flag"].zero_()
+    if INFER_DTYPE == torch.float16:
+        INFER_DTYPE = torch.bfloat16
+        warnings.warn("libpda_b200: an activation exceeded the fp16 range (+-65504) on the no-grad path; the stored value "
+                      "was clipped.  Switching the no-grad path to bf16 activations for the rest of this process "
+                      "(PDA_INFER_DTYPE=bf16 selects that from the start).", RuntimeWarning)
+
+
+def check_fp16_range(dev=None):
+    """Synchronous check of the sticky flag(s); returns True when every fp16 activation so far was in range.  On a
+    violation the no-grad path switches to bf16 (with a RuntimeWarning) and the flag is cleared."""
+    ok = True
+    for d in ([dev] if dev is not None else list(_RANGE)):
+        if int(_range_state(d)["flag"].item()) != 0:
+            _range_exceeded(d)
+            ok = False
+    return ok
+
+
+def poll_fp16_range(dev):
+    """Asynchronous form, called at the start of every no-grad forward: looks at the copy of the flag that an earlier call
+    put in flight (no host synchronisation) and enqueues the next copy.  A violation is therefore noticed one or two
+    forwards later; the values of the offending forward were clipped to +-65504, never inf."""
+    if INFER_DTYPE != torch.float16 or torch.cuda.is_current_stream_capturing():
+        return
+    st = _range_state(dev)
+    if st["pending"] and st["event"].query():
+        st["pending"] = False
+        if int(st["host"][0]) != 0:
+            _range_exceeded(dev)
+    if not st["pending"]:
+        st["host"].copy_(st["flag"], non_blocking=True)
+        st["event"].record()
+        st["pending"] = True
+
+
+def _is_f16(t):
+    if t.dtype not in _ACT_DTYPES:
+        raise _lib.PdaError(f"NHWC activations must be bf16 or fp16, got {t.dtype}")
+    return int(t.dtype == torch.float16)
+
+
+def pack_conv3x3_weights(w, rot180=False, dtype=torch.bfloat16):
+    """(cout, cin, 3, 3) fp32 -> (cout, 9*cin) bf16 / fp16 K-major  [rot180: (cin, 9*cout)]."""
     _need_cuda(w)
     lib = _lib.load()
     cout, cin = w.shape[0], w.shape[1]
     w = w.detach().contiguous().float()
-    out = torch.empty((cin, 9 * cout) if rot180 else (cout, 9 * cin), dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.pda_pack_conv3x3_weights(w.data_ptr(), out.data_ptr(), cout, cin, int(rot180), _stream()),
-               "pack_conv3x3_weights")
+    out = torch.empty((cin, 9 * cout) if rot180 else (cout, 9 * cin), dtype=dtype, device=w.device)
+    _lib.check(lib.pda_pack_conv3x3_weights(w.data_ptr(), out.data_ptr(), cout, cin, int(rot180),
+                                            int(dtype == torch.float16), _stream()), "pack_conv3x3_weights")
     return out
 
 
-def conv3x3_first(x0, x1, w, bias, relu=True):
-    """x0 (and optional x1): fp32 (B,1,H,W); w: (cout, cin, 3, 3) fp32 -> (B,H,W,cout) bf16."""
+def conv3x3_first(x0, x1, w, bias, relu=True, dtype=None):
+    """x0 (and optional x1): fp32 (B,1,H,W); w: (cout, cin, 3, 3) fp32 -> (B,H,W,cout) NHWC activations.
+    dtype: storage format of the output (default: INFER_DTYPE, the no-grad format; the training path passes bf16)."""
     _need_cuda(x0, x1, w, bias)
     lib = _lib.load()
     B, _, H, W = x0.shape
     cout = w.shape[0]
     x0 = x0.contiguous().float()
     x1 = None if x1 is None else x1.contiguous().float()
-    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x0.device)
+    dtype = INFER_DTYPE if dtype is None else dtype
+    out = torch.empty((B, H, W, cout), dtype=dtype, device=x0.device)
     _lib.check(lib.pda_conv3x3_first(x0.data_ptr(), _ptr(x1), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                     B, H, W, cout, int(relu), _stream()), "conv3x3_first")
+                                     B, H, W, cout, int(relu), int(dtype == torch.float16), _stream()),
+               "conv3x3_first")
     return out
 
 
 def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=False, bn_tile=0, simt=False,
             relu_mask=None):
-    """src0/src1: NHWC bf16 (src1 optional, channel-concatenated after src0); returns (full, pooled).
+    """src0/src1: NHWC bf16 or fp16 (src1 optional, channel-concatenated after src0); returns (full, pooled) in the
+    same format; w_packed must be packed in that format too.
     relu_mask (B,H,W,cout) bf16: the output is zeroed where relu_mask <= 0 (fused ReLU backward, dgrad use)."""
     _need_cuda(src0, src1, w_packed, bias)
     lib = _lib.load()
     B, H, W, c0 = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
     cout = w_packed.shape[0]
+    f16 = _is_f16(src0)
     assert w_packed.shape[1] == 9 * (c0 + c1), (w_packed.shape, c0, c1)
     assert src0.is_contiguous() and (src1 is None or src1.is_contiguous())
-    full = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=src0.device) if want_full else None
-    pool = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=src0.device) if want_pool else None
+    assert w_packed.dtype == src0.dtype and (src1 is None or src1.dtype == src0.dtype), "mixed activation formats"
+    full = torch.empty((B, H, W, cout), dtype=src0.dtype, device=src0.device) if want_full else None
+    pool = torch.empty((B, H // 2, W // 2, cout), dtype=src0.dtype, device=src0.device) if want_pool else None
     if relu_mask is not None:
         assert relu_mask.shape == (B, H, W, cout) and relu_mask.is_contiguous() and relu_mask.dtype == torch.bfloat16
+    if (simt or FORCE_SIMT_CONV) and f16:
+        raise _lib.PdaError("the CUDA-core cross-check conv is bf16 only (set PDA_INFER_DTYPE=bf16)")
     if simt or FORCE_SIMT_CONV:
         rc = lib.pda_conv3x3_bf16_simt(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
                                        _ptr(full), _ptr(pool), B, H, W, cout, int(relu), _stream())
@@ -99,9 +185,9 @@ def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=Fal
             full = relu_pool_bwd(full, None, relu_mask)
     else:
         with _Timed("conv3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
-            rc = lib.pda_conv3x3_bf16(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
-                                      _ptr(full), _ptr(pool), _ptr(relu_mask), B, H, W, cout, int(relu),
-                                      int(bn_tile), _stream())
+            rc = lib.pda_conv3x3_tc(src0.data_ptr(), c0, _ptr(src1), c1, w_packed.data_ptr(), _ptr(bias),
+                                    _ptr(full), _ptr(pool), _ptr(relu_mask), B, H, W, cout, int(relu),
+                                    int(bn_tile), f16, range_flag(src0.device).data_ptr() if f16 else 0, _stream())
     _lib.check(rc, "conv3x3")
     return full, pool
 
@@ -110,8 +196,8 @@ def avgpool2(x):
     _need_cuda(x)
     lib = _lib.load()
     B, H, W, C = x.shape
-    out = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.pda_avgpool2_bf16(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream()), "avgpool2")
+    out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    _lib.check(lib.pda_avgpool2(x.data_ptr(), out.data_ptr(), B, H, W, C, _is_f16(x), _stream()), "avgpool2")
     return out
 
 
@@ -119,8 +205,9 @@ def upsample2x(x):
     _need_cuda(x)
     lib = _lib.load()
     B, h, w, C = x.shape
-    out = torch.empty((B, 2 * h, 2 * w, C), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.pda_upsample2x_bilinear_bf16(x.data_ptr(), out.data_ptr(), B, h, w, C, _stream()), "upsample2x")
+    out = torch.empty((B, 2 * h, 2 * w, C), dtype=x.dtype, device=x.device)
+    _lib.check(lib.pda_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), B, h, w, C, _is_f16(x), _stream()),
+               "upsample2x")
     return out
 
 
@@ -134,7 +221,7 @@ def gauss_head(enc, w_head, b_head, latent):
     scratch = torch.empty((B, rows, C), dtype=torch.float32, device=enc.device)
     out = torch.empty((B, 2 * latent), dtype=torch.float32, device=enc.device)
     _lib.check(lib.pda_gauss_head(enc.data_ptr(), w_head.data_ptr(), b_head.data_ptr(), scratch.data_ptr(),
-                                  out.data_ptr(), B, P, C, latent, _stream()), "gauss_head")
+                                  out.data_ptr(), B, P, C, latent, _is_f16(enc), _stream()), "gauss_head")
     return out
 
 
@@ -162,14 +249,14 @@ def kl_diag_gauss(mls_q, mls_p):
 
 def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, want_mean=True, want_weight=True,
                        want_mask=False, want_logits=False, want_probs=False, precision="bf16"):
-    """feat (B,H,W,64) bf16; z (S,B,L) fp32.  Returns dict of (B,1,H,W) / (S,B,1,H,W) tensors.
+    """feat (B,H,W,64) bf16 or fp16; z (S,B,L) fp32.  Returns dict of (B,1,H,W) / (S,B,1,H,W) tensors.
     "range_flag" (precision "bf16" only): the call's scratch; element 0 is the int32 fp16-range flag that the kernel
     raises (and acts on, by re-running the batch in fp32 on the device) -- `fcomb_bwd` takes it as `fwd_flag`."""
     _need_cuda(feat, z, w1)
     lib = _lib.load()
     B, H, W, C = feat.shape
     S, Bz, L = z.shape
-    assert Bz == B and C == 64 and w1.shape[1] == C + L
+    assert Bz == B and C == 64 and w1.shape[1] == C + L and feat.is_contiguous()
     dev = feat.device
     P = H * W
     mean = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_mean else None
@@ -186,9 +273,9 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
         if precision == "bf16":
             # per-call scratch from torch's caching allocator: nothing is shared between launches, streams or graphs
             scratch = torch.empty(lib.pda_fcomb_scratch_floats(S, B), dtype=torch.float32, device=dev)
-            rc = lib.pda_fcomb_mc_consensus(*args, scratch.data_ptr(), _stream())
+            rc = lib.pda_fcomb_mc_consensus(*args, scratch.data_ptr(), _is_f16(feat), _stream())
         else:
-            rc = lib.pda_fcomb_mc_consensus_fp32(*args, _stream())
+            rc = lib.pda_fcomb_mc_consensus_fp32(*args, _is_f16(feat), _stream())
     _lib.check(rc, "fcomb_mc_consensus")
     return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs, "range_flag": scratch}
 
@@ -295,7 +382,7 @@ def gauss_head_fwd_train(enc, w_head, b_head, latent):
     scratch = torch.empty((B, rows, C), dtype=torch.float32, device=enc.device)
     out = torch.empty((B, 2 * latent), dtype=torch.float32, device=enc.device)
     _lib.check(lib.pda_gauss_head(enc.data_ptr(), w_head.data_ptr(), b_head.data_ptr(), scratch.data_ptr(),
-                                  out.data_ptr(), B, P, C, latent, _stream()), "gauss_head")
+                                  out.data_ptr(), B, P, C, latent, _is_f16(enc), _stream()), "gauss_head")
     return out, scratch
 
 

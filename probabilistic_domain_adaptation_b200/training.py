@@ -73,7 +73,8 @@ class ConvStackFn(torch.autograd.Function):
         for j, conv in enumerate(convs):
             last = j == n - 1
             if j == 0 and x0 is not None:
-                cur = ops.conv3x3_first(x0, x1, conv.weight.detach(), conv.bias.detach(), True)
+                cur = ops.conv3x3_first(x0, x1, conv.weight.detach(), conv.bias.detach(), True,
+                                        dtype=ops.TRAIN_DTYPE)
                 if last and pool_last:
                     pooled = ops.avgpool2(cur)
             else:
@@ -126,8 +127,14 @@ class ConvStackFn(torch.autograd.Function):
         return (dx, dsrc1, None, None, None, None, *grads)
 
 
+def _train_fmt(t):
+    """Inputs that come from a no-grad (fp16) block -- e.g. a frozen encoder -- enter the training path as bf16."""
+    return t if t is None or t.dtype == ops.TRAIN_DTYPE else t.to(ops.TRAIN_DTYPE)
+
+
 def conv_stack_train(convs, x, src1, first_input, pool_last):
     x0, x1 = first_input if first_input is not None else (None, None)
+    x, src1 = _train_fmt(x), _train_fmt(src1)
     params = []
     for c in convs:
         params += [c.weight, c.bias]
@@ -136,6 +143,7 @@ def conv_stack_train(convs, x, src1, first_input, pool_last):
 
 def conv3x3_train(x, src1, conv, relu, want_full, want_pool):
     # the full-resolution map is always kept in training: it is the ReLU mask of the backward
+    x, src1 = _train_fmt(x), _train_fmt(src1)
     full, pool = Conv3x3Fn.apply(x, src1, conv.weight, conv.bias, conv, relu, want_pool)
     return full, pool
 
@@ -147,7 +155,7 @@ class ConvFirstFn(torch.autograd.Function):
     def forward(ctx, x0, x1, weight, bias, relu):
         if not relu:
             raise NotImplementedError("first-layer backward assumes the fused ReLU")
-        out = ops.conv3x3_first(x0, x1, weight.detach(), bias.detach(), relu)
+        out = ops.conv3x3_first(x0, x1, weight.detach(), bias.detach(), relu, dtype=ops.TRAIN_DTYPE)
         ctx.save_for_backward(x0, x1, out)
         return out
 
@@ -164,7 +172,7 @@ class AvgPool2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         ctx.shape = x.shape
-        return ops.avgpool2(x)
+        return ops.avgpool2(_train_fmt(x))
 
     @staticmethod
     def backward(ctx, g):
@@ -174,7 +182,7 @@ class AvgPool2Fn(torch.autograd.Function):
 class Upsample2xFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return ops.upsample2x(x)
+        return ops.upsample2x(_train_fmt(x))
 
     @staticmethod
     def backward(ctx, g):
@@ -186,6 +194,7 @@ class GaussHeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, weight, bias, latent):
+        enc = _train_fmt(enc)
         out, scratch = ops.gauss_head_fwd_train(enc, weight.detach(), bias.detach(), latent)
         ctx.latent = latent
         ctx.save_for_backward(enc, weight, scratch)
@@ -328,5 +337,5 @@ def fcomb_train(feat, z, w, **want):
     if z.shape[0] != 1 or extras or not want.get("want_logits"):
         raise NotImplementedError("autograd through the fused Monte-Carlo kernel: only S=1 logits are differentiable "
                                   "(the reference's consensus sampling runs under torch.no_grad())")
-    logits = FcombTrainFn.apply(feat, z[0], *w)
+    logits = FcombTrainFn.apply(_train_fmt(feat), z[0], *w)
     return {"mean": None, "weight": None, "mask": None, "logits": logits[None], "probs": None}

@@ -1,11 +1,13 @@
 """GPU parity AT THE SHAPES THE NUMBERS ARE QUOTED ON (BASELINE.json configs 1 and 5), in RAW units.
 
 Tolerance rule (BASELINE.json north_star, restated once in DESIGN.md section 2): with the same latent draws, sampled
-logits of the bf16 path are within 1e-2 ABSOLUTE of the reference on the synthetic configuration the benchmark names
-(seed-0 weights at the reference's init scale: logits span about +-0.5).  The error of the bf16 trunk is relative, so
-for weights whose logits span +-G/2 the bound scales to 1e-2 * G; the tests below print and assert the raw numbers for
-both, split the error into its two stages (bf16 conv trunk vs fp16 hidden layer of the fused Fcomb kernel) and check the
-consensus mask against the reference's own mask.
+logits are within 1e-2 ABSOLUTE of the reference on the synthetic configuration the benchmark names (seed-0 weights at
+the reference's init scale: logits span about +-0.7).  Measured history: with bf16 activations the 21-layer trunk reached
+1.2e-2 at 256 x 256 and 1.4e-2 at 1024 x 1024 (max over all logits; 99.99 % below 0.9e-2) -- over the bound.  The no-grad
+path therefore stores activations and weights as fp16 (3 more mantissa bits, fp32 accumulation unchanged): 1.7e-3 at
+256 x 256.  The error is relative, so for weights whose logits span +-G/2 it scales with G; the tests below print and
+assert the raw numbers for gains 1, 8 and 24, split the error into its two stages (conv trunk vs fp16 hidden layer of the
+fused Fcomb kernel) and check the consensus mask against the reference's own mask.
 
 The oracle (oracle/punet_oracle.py, fp32 on the host cores) needs ~0.5 s for 256 x 256, ~3 s for 512 x 512 and ~15 s for
 1024 x 1024 at S = 16.
@@ -100,16 +102,19 @@ def _compare(tag, b, h, w, s, gain):
     return res
 
 
-@pytest.mark.parametrize("gain", [1.0, 8.0])
+@pytest.mark.parametrize("gain", [1.0, 8.0, 24.0])
 def test_config1_256x256_s16_raw_logit_error(gain):
-    """BASELINE config 1 exactly: 1 x 1 x 256 x 256, S = 16 + consensus mask."""
+    """BASELINE config 1 exactly: 1 x 1 x 256 x 256, S = 16 + consensus mask.  Gain 1 is the configuration the benchmark
+    names (logits +-0.65): the literal 1e-2 bound, measured 1.7e-3.  Gains 8 and 24 stretch the logits to +-5 / +-16 so
+    that probabilities saturate and the consensus mask takes both values; the error scales with the gain and still
+    stays below 1e-2 * gain / 4."""
     r = _compare(f"c1_256_gain{gain:g}", 1, 256, 256, 16, gain)
     assert r["mask_bit_exact_on_own_probs"]
-    assert r["logit_max_abs_err"] < 1e-2 * gain, r            # the literal north-star bound at gain 1
-    assert r["logit_p9999_abs_err"] < 0.6e-2 * gain, r
-    assert r["stage_fcomb_fp16_max_abs_err"] < 0.25e-2 * gain, r
-    assert r["mask_agreement"] > 0.99, r
-    if gain > 1:
+    assert r["logit_max_abs_err"] < 1e-2 * max(1.0, gain / 4), r   # the literal north-star bound at gain 1
+    assert r["logit_p9999_abs_err"] < 0.5e-2 * max(1.0, gain / 4), r
+    assert r["stage_fcomb_fp16_max_abs_err"] < 0.2e-2 * gain, r
+    assert r["mask_agreement"] > 0.995, r
+    if gain >= 24:
         assert 0.0 < r["mask_fraction_reference"] < 1.0, r    # both mask values occur
 
 
@@ -117,9 +122,9 @@ def test_one_512_tile_s16_raw_logit_error():
     """One 512 x 512 tile (the network input of the tiled prediction driver; a quarter of a config-5 tile)."""
     r = _compare("tile_512_gain8", 1, 512, 512, 16, 8.0)
     assert r["mask_bit_exact_on_own_probs"]
-    assert r["logit_max_abs_err"] < 1e-2 * 8.0, r
-    assert r["logit_p9999_abs_err"] < 0.6e-2 * 8.0, r
-    assert r["mask_agreement"] > 0.99, r
+    assert r["logit_max_abs_err"] < 1e-2 * 2.0, r            # measured 1.4e-2 on logits of +-6
+    assert r["logit_p9999_abs_err"] < 0.6e-2 * 2.0, r
+    assert r["mask_agreement"] > 0.995, r
 
 
 def test_config5_1024_tile_s16_raw_logit_error():
@@ -128,9 +133,17 @@ def test_config5_1024_tile_s16_raw_logit_error():
     positions that depend on the image size, so the reference itself is not crop-consistent.)"""
     r = _compare("c5_1024_gain8", 1, 1024, 1024, 16, 8.0)
     assert r["mask_bit_exact_on_own_probs"]
-    assert r["logit_max_abs_err"] < 1e-2 * 8.0, r
-    assert r["logit_p9999_abs_err"] < 0.6e-2 * 8.0, r
-    assert r["mask_agreement"] > 0.99, r
+    assert r["logit_max_abs_err"] < 1e-2 * 2.0, r            # measured 1.5e-2 on logits of +-6.2
+    assert r["logit_p9999_abs_err"] < 0.6e-2 * 2.0, r
+    assert r["mask_agreement"] > 0.995, r
+
+
+def test_config5_1024_unit_gain_literal_tolerance():
+    """The literal north-star statement at the bench's tile size: seed-0 weights at the init scale (logits +-0.8),
+    1 x 1 x 1024 x 1024, S = 4 (the per-sample error does not depend on S): max |logit error| < 1e-2."""
+    r = _compare("c5_1024_gain1_s4", 1, 1024, 1024, 4, 1.0)
+    assert r["logit_max_abs_err"] < 1e-2, r
+    assert r["logit_p9999_abs_err"] < 0.5e-2, r
 
 
 def test_config5_batch_of_four_equals_single_tiles():

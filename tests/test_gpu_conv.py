@@ -44,30 +44,98 @@ CONV_CASES = [
 ]
 
 
+# "tc": tensor-core kernel on bf16 activations (training format); "tc_f16": the same kernel on fp16 activations (the
+# no-grad format, fp16 x fp16 MMAs); "simt": CUDA-core cross-check (bf16)
 @pytest.mark.parametrize("B,H,W,c0,c1,cout,pool,bn", CONV_CASES)
-@pytest.mark.parametrize("simt", [False, True])
-def test_conv3x3_matches_fp32_reference(B, H, W, c0, c1, cout, pool, bn, simt):
+@pytest.mark.parametrize("mode", ["tc", "tc_f16", "simt"])
+def test_conv3x3_matches_fp32_reference(B, H, W, c0, c1, cout, pool, bn, mode):
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
+    dt = torch.float16 if mode == "tc_f16" else torch.bfloat16
+    ulp = 2 ** -11 if mode == "tc_f16" else 2 ** -8   # one ulp of the 16-bit output format (half an ulp + fp32 noise)
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + H * 10 + cout)
-    s0 = torch.randn(B, H, W, c0, generator=g).to(dev).to(torch.bfloat16)
-    s1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(torch.bfloat16) if c1 else None
+    s0 = torch.randn(B, H, W, c0, generator=g).to(dev).to(dt)
+    s1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(dt) if c1 else None
     ctot = c0 + c1
     w = (torch.randn(cout, ctot, 3, 3, generator=g) * (2.0 / (9 * ctot)) ** 0.5).to(dev)
-    w = w.to(torch.bfloat16).float()  # bf16-representable so that only accumulation order differs
+    w = w.to(dt).float()  # representable in the operand format so that only accumulation order differs
     bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
-    wp = ops.pack_conv3x3_weights(w)
-    full, pooled = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn, simt=simt)
+    wp = ops.pack_conv3x3_weights(w, dtype=dt)
+    full, pooled = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn,
+                               simt=(mode == "simt"))
     torch.cuda.synchronize()
+    assert full.dtype == dt
     rfull, rpool = _ref_conv([s0] + ([s1] if c1 else []), w, bias, True, pool)
-    # outputs are bf16: half an ulp (2^-9 relative) + fp32 accumulation noise
     err = (full.float() - rfull).abs()
-    tol = 2 ** -8 * rfull.abs() + 1e-3
+    tol = ulp * rfull.abs() + 1e-3
     assert (err <= tol).all(), f"full: max err {err.max().item()} at {err.argmax().item()}"
     if pool:
         err = (pooled.float() - rpool).abs()
-        tol = 2 ** -8 * rpool.abs() + 1e-3
+        tol = ulp * rpool.abs() + 1e-3
         assert (err <= tol).all(), f"pool: max err {err.max().item()}"
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout,pool,bn", CONV_CASES + [(2, 64, 128, 64, 0, 64, True, 0),
+                                                                      (1, 128, 136, 256, 128, 128, False, 0),
+                                                                      (3, 24, 8, 64, 0, 256, False, 0)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_conv3x3_cta_pair_kernel_is_bit_identical(B, H, W, c0, c1, cout, pool, bn, dt):
+    """csrc/conv3x3_tc2.cu (cta_group::2: one M = 256 MMA per CTA pair, weight tile split across the pair) against the
+    single-CTA kernel: same operands, same fp32 accumulation per output row -> identical bits; odd tile counts exercise
+    the ghost tile of the peer CTA."""
+    from probabilistic_domain_adaptation_b200 import _lib, ops
+    dev = _dev()
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(B * 77 + H + cout)
+    s0 = torch.randn(B, H, W, c0, generator=g).to(dev).to(dt)
+    s1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(dt) if c1 else None
+    ctot = c0 + c1
+    w = (torch.randn(cout, ctot, 3, 3, generator=g) * (2.0 / (9 * ctot)) ** 0.5).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    wp = ops.pack_conv3x3_weights(w, dtype=dt)
+    prev = lib.pda_set_conv_pair(0)
+    try:
+        f0, p0 = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn)
+        lib.pda_set_conv_pair(1)
+        f1, p1 = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn)
+        # twice, so that a stale barrier phase / TMEM state of the first launch would show
+        f2, p2 = ops.conv3x3(s0, s1, wp, bias, relu=True, want_full=True, want_pool=pool, bn_tile=bn)
+        torch.cuda.synchronize()
+    finally:
+        lib.pda_set_conv_pair(prev)
+    assert torch.equal(f0, f1) and torch.equal(f1, f2)
+    if pool:
+        assert torch.equal(p0, p1) and torch.equal(p1, p2)
+
+
+def test_conv3x3_fp16_range_flag_and_saturation():
+    """fp16 outputs saturate at +-65504 (never inf) and raise the sticky device flag; in-range launches leave it alone;
+    the asynchronous poll switches the no-grad path to bf16."""
+    import warnings
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(1)
+    s0 = torch.rand(1, 16, 16, 64, generator=g).to(dev).to(torch.float16)
+    w = (torch.rand(64, 64, 3, 3, generator=g) * 0.05).to(dev)
+    bias = torch.zeros(64, device=dev)
+    wp = ops.pack_conv3x3_weights(w, dtype=torch.float16)
+    flag = ops.range_flag(dev)
+    flag.zero_()
+    full, _ = ops.conv3x3(s0, None, wp, bias)
+    assert int(flag.item()) == 0 and torch.isfinite(full).all()
+    big, _ = ops.conv3x3((s0.float() * 6e4).clamp(max=6e4).to(torch.float16), None, wp, bias)
+    assert int(flag.item()) == 1
+    assert torch.isfinite(big).all() and float(big.float().max()) == 65504.0
+    saved = ops.INFER_DTYPE
+    try:
+        ops.INFER_DTYPE = torch.float16
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            assert ops.check_fp16_range(dev) is False
+        assert ops.INFER_DTYPE == torch.bfloat16 and int(flag.item()) == 0
+        assert any("fp16 range" in str(r.message) for r in rec)
+    finally:
+        ops.INFER_DTYPE = saved
 
 
 def test_conv3x3_pool_only_output():
@@ -83,40 +151,48 @@ def test_conv3x3_pool_only_output():
     assert f2 is None and torch.equal(p1, p2)
 
 
+DTYPES = [torch.bfloat16, torch.float16]
+ULP = {torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11}
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("cin", [1, 2])
-def test_first_conv(cin):
+def test_first_conv(cin, dt):
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
     g = torch.Generator().manual_seed(3)
     x = torch.randn(2, cin, 24, 40, generator=g).to(dev)
     w = (torch.randn(64, cin, 3, 3, generator=g) * 0.4).to(dev)
     b = (torch.randn(64, generator=g) * 0.1).to(dev)
-    out = ops.conv3x3_first(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if cin == 2 else None, w, b)
+    out = ops.conv3x3_first(x[:, 0:1].contiguous(), x[:, 1:2].contiguous() if cin == 2 else None, w, b, dtype=dt)
+    assert out.dtype == dt
     ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float().permute(0, 2, 3, 1)
     err = (out.float() - ref).abs()
-    assert (err <= 2 ** -8 * ref.abs() + 1e-5).all(), err.max().item()
+    assert (err <= ULP[dt] * ref.abs() + 1e-5).all(), err.max().item()
 
 
-def test_avgpool_and_upsample():
+@pytest.mark.parametrize("dt", DTYPES)
+def test_avgpool_and_upsample(dt):
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(2, 10, 18, 128, generator=g).to(dev).to(torch.bfloat16)
+    x = torch.randn(2, 10, 18, 128, generator=g).to(dev).to(dt)
     xn = x.float().permute(0, 3, 1, 2)
     p = ops.avgpool2(x)
     rp = F.avg_pool2d(xn, 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1)
-    assert ((p.float() - rp).abs() <= 2 ** -8 * rp.abs() + 1e-6).all()
+    assert p.dtype == dt and ((p.float() - rp).abs() <= ULP[dt] * rp.abs() + 1e-6).all()
     u = ops.upsample2x(x)
     ru = F.interpolate(xn, mode="bilinear", scale_factor=2, align_corners=True).permute(0, 2, 3, 1)
     err = (u.float() - ru).abs()
-    assert (err <= 2 ** -8 * ru.abs() + 1e-5).all(), err.max().item()
+    assert u.dtype == dt and (err <= ULP[dt] * ru.abs() + 1e-5).all(), err.max().item()
 
 
-def test_gauss_head_and_latents():
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gauss_head_and_latents(dt):
     from probabilistic_domain_adaptation_b200 import ops
     dev = _dev()
     g = torch.Generator().manual_seed(9)
-    enc = torch.randn(3, 5, 9, 512, generator=g).to(dev).to(torch.bfloat16)
+    enc = torch.randn(3, 5, 9, 512, generator=g).to(dev).to(dt)
     w = (torch.randn(12, 512, 1, 1, generator=g) * 0.05).to(dev)
     b = (torch.randn(12, generator=g) * 0.01).to(dev)
     out = ops.gauss_head(enc, w, b, 6)

@@ -195,13 +195,15 @@ def test_dice_score_and_validation_step(golden):
     torch.manual_seed(11)
     loss, dice, metric = steps.validation_step(model, x.to(dev), y.to(dev), n_samples=8)
     assert loss.dim() == 0 and dice.dim() == 0 and torch.isfinite(loss)
-    # same RNG stream -> same prediction -> same dice through the numpy reference arithmetic
-    model.forward(x.to(dev), y.to(dev), training=True)
-    model.elbo(y.to(dev))
-    torch.manual_seed(11)
-    model.forward(x.to(dev), y.to(dev), training=True)
-    _ = model.posterior_latent_space.rsample()  # elbo() draws one posterior sample before the prior samples
-    pred = consensus.sample_from_model(model, 8)
+    # same RNG stream -> same prediction -> same dice through the numpy reference arithmetic (under no_grad, like
+    # validation_step itself: the no-grad path and the training path use different activation formats)
+    with torch.no_grad():
+        model.forward(x.to(dev), y.to(dev), training=True)
+        model.elbo(y.to(dev))
+        torch.manual_seed(11)
+        model.forward(x.to(dev), y.to(dev), training=True)
+        _ = model.posterior_latent_space.rsample()  # elbo() draws one posterior sample before the prior samples
+        pred = consensus.sample_from_model(model, 8)
     ref = po.dice_score(pred.cpu().numpy().squeeze(), y.numpy().squeeze())
     assert abs(dice.item() - ref) < 1e-5 and abs(metric.item() - (1.0 - ref)) < 1e-5
 
