@@ -49,9 +49,9 @@ void pda_reset_launch_count(void);
 int pda_pack_conv3x3_weights(const float* w_oihw, void* w_packed, int cout, int cin, int rot180, int f16,
                              void* stream);
 
-/* Same for many convs in one launch (after an optimizer or EMA step).  table: device int64 [n_chunks][7] =
- * (w_oihw ptr, bf16 packed ptr or 0, bf16 rot180-packed ptr or 0, fp16 packed ptr or 0, cout, cin, first output element
- * of the chunk); chunks of 16384. */
+/* Same for many convs in one launch (after an optimizer or EMA step).  table: device int64 [n_chunks][8] =
+ * (w_oihw ptr, bf16 packed ptr or 0, bf16 rot180-packed ptr or 0, fp16 packed ptr or 0, cout, cin, co0, ci0): one row =
+ * one 32 (co) x 32 (ci) x 9 tile starting at (co0, ci0); cout and cin must be multiples of 32. */
 int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* stream);
 
 /* First layer of every net (cin = 1, or 2 for the posterior whose input is cat(patch, segm),
@@ -171,10 +171,17 @@ int pda_augment_view(const float* img, const float* noise, float* out, int B, in
 /* Weight (+bias) gradient of conv3x3: dW[co][ci][ky][kx] = sum_p dZ[p][co] * X[p + tap][ci] on tcgen05 tensor cores
  * (K = pixels; both operands read as MN-major straight from NHWC; persistent stream-K schedule).
  * X = concat(src0, src1) as in the forward.
- * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  scratch: fp32 [cout*9*(c0+c1) + cout].  dw_oihw fp32 OIHW,
- * dbias fp32 [cout] (may be NULL).  accumulate != 0 adds to dw/dbias instead of overwriting. */
+ * dz: NHWC bf16 [B][H][W][cout] (already masked by ReLU).  dw_oihw fp32 OIHW, dbias fp32 [cout] (may be NULL).
+ * accumulate != 0 adds to dw/dbias instead of overwriting.
+ * scratch: fp32 [pda_conv3x3_wgrad_scratch_floats(c0 + c1, cout)] (tap-major partial sums, bias sums).  It must be all
+ *   zero when the kernel starts and the call leaves it all zero again (the re-layout kernel that follows clears what it
+ *   reads): a caller that keeps one scratch per layer passes scratch_is_zero != 0 after having zeroed it once; with 0
+ *   the call clears it first (one memset).  (Measured dead end: re-laying out inside the main kernel by the last CTA
+ *   of each 64 x 64 item removed the second launch but cost +35 % kernel time -- one SM per item, latency-bound.) */
+long long pda_conv3x3_wgrad_scratch_floats(int ctot, int cout);
 int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
-                           float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate, void* stream);
+                           float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate,
+                           int scratch_is_zero, void* stream);
 
 /* dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): ReLU backward fused with the backward of the 2x2 average pool that
  * consumes Y (unet_blocks.py:17,20).  NHWC bf16; dfull or dpool may be NULL; y == NULL skips the ReLU mask
@@ -186,6 +193,8 @@ int pda_relu_pool_bwd_bf16(const void* dfull, const void* dpool, const void* y, 
 int pda_upsample2x_bilinear_bwd_bf16(const void* dout, void* din, int B, int h, int w, int C, void* stream);
 
 /* First layer (cin 1 or 2) weight/bias gradient; out = forward output (for the ReLU mask), dout its gradient.
+ * out == NULL: dout is already masked by this layer's ReLU (it comes out of the next layer's dgrad conv, whose
+ * epilogue applies that mask): the kernel then reads half the bytes.
  * scratch: caller-allocated fp32 [pda_conv3x3_first_bwd_scratch_floats(...)] for the per-block partial sums. */
 long long pda_conv3x3_first_bwd_scratch_floats(int B, int H, int W, int cout, int cin);
 int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,

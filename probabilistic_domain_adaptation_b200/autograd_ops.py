@@ -60,8 +60,9 @@ def refresh_packed(module, rot180=True, bf16=True, f16=None):
             rot = torch.empty((cin, 9 * cout), dtype=torch.bfloat16, device=w.device) if rot180 else None
             half = torch.empty((cout, 9 * cin), dtype=torch.float16, device=w.device) if f16 else None
             bufs.append((packed, rot, half))
-            for start in range(0, 9 * cout * cin, _PACK_CHUNK):
-                rows.append((w.data_ptr(), ops._ptr(packed), ops._ptr(rot), ops._ptr(half), cout, cin, start))
+            for co0 in range(0, cout, 32):          # one 32 x 32 x 9 tile per block of the pack kernel
+                for ci0 in range(0, cin, 32):
+                    rows.append((w.data_ptr(), ops._ptr(packed), ops._ptr(rot), ops._ptr(half), cout, cin, co0, ci0))
         table = torch.tensor(rows, dtype=torch.int64).to(convs[0].weight.device)
         state = {"key": key, "bufs": bufs, "table": table, "convs": convs}
         module.__dict__["_pda_pack_state"] = state

@@ -26,6 +26,7 @@ struct ConvArgs {
   const __nv_bfloat16* mask;  // NHWC [B][H][W][cout] or nullptr: outputs are zeroed where mask <= 0 (ReLU backward
                               // of the layer that produced this conv's input, fused into the dgrad epilogue)
   int act_f16;                // activations / weights / outputs are fp16 (no-grad path) instead of bf16
+  int wide, wide_base_offset; // CTA-pair kernel: one 16-px slab per chunk (csrc/conv3x3_tc2.cu)
   int* range_flag;            // fp16 only, may be nullptr: set to 1 when an output exceeds the fp16 range (the store
                               // saturates at +-65504)
 };

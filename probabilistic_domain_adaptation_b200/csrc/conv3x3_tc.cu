@@ -490,6 +490,7 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   a.out_pool = static_cast<__nv_bfloat16*>(out_pool);
   a.mask = static_cast<const __nv_bfloat16*>(mask);
   a.act_f16 = act_f16;
+  a.wide = a.wide_base_offset = 0;
   a.range_flag = act_f16 ? range_flag : nullptr;
   CUtensorMap tA0, tA1, tB;
   int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);

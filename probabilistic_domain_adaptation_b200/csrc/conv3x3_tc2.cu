@@ -22,6 +22,10 @@
 #include "conv.cuh"
 #include "ptx.cuh"
 
+#ifndef PDA_CONV_WIDE_DEFAULT
+#define PDA_CONV_WIDE_DEFAULT 0
+#endif
+
 namespace pda {
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -85,13 +89,19 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int BN, int MT, bool RES>
+// WIDE: one slab of 16-pixel rows per 64-channel chunk serves all three kx taps (the tap's A operand starts kx pixels =
+// kx * 128 B into the row) instead of three column-shifted 8-pixel slabs: one TMA load and 2/3 of the shared-memory fill
+// traffic per chunk.  Bit-identical results; measured within +-3 % of the 8-pixel slabs on every layer
+// (profiles/r02_conv_wide_slab.md), so the fill traffic is not what limits these kernels: kept as an option
+// (PDA_CONV_WIDE=1), not the default.
+template <int BN, int MT, bool RES, bool WIDE = false>
 struct Conv2Cfg {
   static constexpr int SLAB_ROWS = 16 * MT + 2;
-  static constexpr int A_BYTES = SLAB_ROWS * 1024;     // one slab: SLAB_ROWS x (8 px x 128 B)
+  static constexpr int ROW_BYTES = WIDE ? 2048 : 1024; // one slab row: 16 or 8 px x 128 B
+  static constexpr int A_BYTES = SLAB_ROWS * ROW_BYTES;
   static constexpr int BH = BN / 2;                    // weight rows held by one CTA of the pair
   static constexpr int B_BYTES = BH * 128;             // this CTA's half of one (tap, chunk) weight tile
-  static constexpr int A_STAGES = 4;
+  static constexpr int A_STAGES = WIDE ? (MT == 2 ? 2 : 3) : 4;
   static constexpr int B_STAGES = RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6));
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
@@ -111,12 +121,12 @@ struct Conv2Cfg {
 
 constexpr int CONV2_THREADS = 320;
 
-template <int BN, int MT, bool RES, bool F16>
+template <int BN, int MT, bool RES, bool F16, bool WIDE>
 __global__ void __launch_bounds__(CONV2_THREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                    const ConvArgs p) {
-  using L = Conv2Cfg<BN, MT, RES>;
+  using L = Conv2Cfg<BN, MT, RES, WIDE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -216,18 +226,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (int ch = 0; ch < chunks; ++ch) {
         const int c = ch << 6;
         for (int kx = 0; kx < 3; ++kx) {
-          mbar_wait(a_empty(as), aph ^ 1);
-          if (leader_lane) {
-            const uint32_t bar = mapa_shared(a_full(as), 0);
-            if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_BYTES);
-            const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
-            if (c < p.c0)
-              tma_load_4d_pair(dst, &tmA0, bar, c, x0 + kx - 1, y0 - 1, img);
-            else
-              tma_load_4d_pair(dst, &tmA1, bar, c - p.c0, x0 + kx - 1, y0 - 1, img);
+          if (!WIDE || kx == 0) {
+            mbar_wait(a_empty(as), aph ^ 1);
+            if (leader_lane) {
+              const uint32_t bar = mapa_shared(a_full(as), 0);
+              if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_BYTES);
+              const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
+              const int xs = WIDE ? x0 - 1 : x0 + kx - 1;
+              if (c < p.c0)
+                tma_load_4d_pair(dst, &tmA0, bar, c, xs, y0 - 1, img);
+              else
+                tma_load_4d_pair(dst, &tmA1, bar, c - p.c0, xs, y0 - 1, img);
+            }
+            __syncwarp();
+            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
           }
-          __syncwarp();
-          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
           if (!RES) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -263,9 +276,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const uint32_t dcol = tmem_base + buf * (MT * BN);
         for (int ch = 0; ch < chunks; ++ch) {
           for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(a_full(as), aph);
-            tc_fence_after();
-            const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES;
+            if (!WIDE || kx == 0) {
+              mbar_wait(a_full(as), aph);
+              tc_fence_after();
+            }
+            const uint32_t sa = sbase + L::A_OFF + as * L::A_BYTES + (WIDE ? kx * 128 : 0);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               uint32_t sb;
@@ -281,7 +296,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                 const uint32_t acc = (ch | kx | ky) != 0 ? 1u : 0u;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t da = umma_desc_k_sw128(sa + (16 * mt + ky) * 1024);
+                  const uint32_t arow = sa + (16 * mt + ky) * L::ROW_BYTES;
+                  // WIDE: arow is kx * 128 B into a 1024-byte swizzle atom; the rows continue linearly into the next atom
+                  // of the same 16-pixel slab row.  The descriptor's base-offset field stays 0 (measured: the swizzle is
+                  // applied to absolute shared-memory address bits; with the field set the result is wrong).
+                  const uint64_t da = umma_desc_k_sw128(arow, L::ROW_BYTES);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_pair(dcol + mt * BN, da + 2 * k, db + 2 * k, idesc, (acc | k) != 0 ? 1u : 0u);
@@ -293,9 +312,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                 if (++bs == L::B_STAGES) { bs = 0; bph ^= 1; }
               }
             }
-            if (leader_lane) umma_commit_pair(a_empty(as));
-            __syncwarp();
-            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+            if (!WIDE || kx == 2) {
+              if (leader_lane) umma_commit_pair(a_empty(as));
+              __syncwarp();
+              if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+            }
           }
         }
         if (leader_lane) umma_commit_pair(acc_full(buf));
@@ -444,11 +465,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MT, bool RES, bool F16>
+template <int BN, int MT, bool RES, bool F16, bool WIDE>
 static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                             const ConvArgs& args, cudaStream_t stream) {
-  using L = Conv2Cfg<BN, MT, RES>;
-  auto kern = conv3x3_tc2_kernel<BN, MT, RES, F16>;
+  using L = Conv2Cfg<BN, MT, RES, WIDE>;
+  auto kern = conv3x3_tc2_kernel<BN, MT, RES, F16, WIDE>;
   static int configured[64];
   static int max_clusters[64];
   int dev = 0;
@@ -490,8 +511,11 @@ static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const 
 template <int BN, int MT, bool RES>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                         const ConvArgs& args, cudaStream_t stream) {
-  return args.act_f16 ? launch_conv2_fmt<BN, MT, RES, true>(a0, a1, b, o, args, stream)
-                      : launch_conv2_fmt<BN, MT, RES, false>(a0, a1, b, o, args, stream);
+  if (args.wide)
+    return args.act_f16 ? launch_conv2_fmt<BN, MT, RES, true, true>(a0, a1, b, o, args, stream)
+                        : launch_conv2_fmt<BN, MT, RES, false, true>(a0, a1, b, o, args, stream);
+  return args.act_f16 ? launch_conv2_fmt<BN, MT, RES, true, false>(a0, a1, b, o, args, stream)
+                      : launch_conv2_fmt<BN, MT, RES, false, false>(a0, a1, b, o, args, stream);
 }
 
 // same contract as conv3x3_tc (csrc/conv3x3_tc.cu); selected by it for shapes with at least two pixel tiles
@@ -518,11 +542,20 @@ int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* 
   a.mask = static_cast<const __nv_bfloat16*>(mask);
   a.act_f16 = act_f16;
   a.range_flag = act_f16 ? range_flag : nullptr;
+  {
+    static const int wide_mode = [] {
+      const char* e = getenv("PDA_CONV_WIDE");  // 0: three 8-px slabs per chunk; 1: one 16-px slab per chunk
+      return e ? atoi(e) : PDA_CONV_WIDE_DEFAULT;
+    }();
+    a.wide = wide_mode != 0;
+    a.wide_base_offset = 0;
+  }
+  const int box_w = a.wide ? 16 : 8;
   CUtensorMap tA0, tA1, tB;
-  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);
+  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, box_w, a.tile_h + 2, 64);
   if (r) return r;
   if (c1 > 0) {
-    r = make_act_tensor_map(&tA1, src1, B, H, W, c1, 8, a.tile_h + 2, 64);
+    r = make_act_tensor_map(&tA1, src1, B, H, W, c1, box_w, a.tile_h + 2, 64);
     if (r) return r;
   } else {
     tA1 = tA0;

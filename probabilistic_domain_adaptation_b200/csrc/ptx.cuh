@@ -192,6 +192,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
   d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
   return d;
 }
+// A start address that is NOT aligned to the 1024-byte swizzle pattern is legal as it is: start `r` 128-byte rows into
+// an atom and the operand's rows continue linearly into the following atom; the swizzle is a function of the absolute
+// shared-memory address bits, which is also how TMA wrote the data.  (Setting the descriptor's "matrix base offset" bits
+// 49-51 to (addr >> 7) & 7 for such a start gives WRONG results on sm_100a -- measured, profiles/r02_conv_wide_slab.md.)
 // MN-major operand, 128-byte swizzle: 64 MN-elements contiguous (128 B) per K row; 8 K-rows per 1024 B atom.
 // LBO = byte distance between successive 64-element MN blocks, SBO = byte distance between 8-row K groups.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

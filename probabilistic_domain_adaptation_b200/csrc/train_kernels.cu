@@ -187,10 +187,13 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
   unsigned pix = blockIdx.x * lanes_px + lpx;
   // the two 16-byte activation loads of the NEXT pixel are issued before this pixel's 72 / 144 FMAs: with ~200
   // registers per thread only 8 warps are resident per SM, so the loads in flight per thread decide the bandwidth
+  // out == nullptr: dout is already masked by the layer's own ReLU (it comes out of the dgrad conv of the next layer,
+  // whose epilogue applies exactly that mask): half the HBM traffic
+  const bool masked = out != nullptr;
   uint4 q_dz = make_uint4(0, 0, 0, 0), q_y = q_dz;
   if (pix < npix) {
     q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)pix * cout + g * 8));
-    q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)pix * cout + g * 8));
+    if (masked) q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)pix * cout + g * 8));
   }
   for (; pix < npix; pix += pstride) {
     const unsigned img = pix / HW, rem = pix - img * HW;
@@ -202,11 +205,11 @@ conv_first_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1
     unpack8f(q_y, yv);
     if (pix + pstride < npix) {
       q_dz = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)(pix + pstride) * cout + g * 8));
-      q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)(pix + pstride) * cout + g * 8));
+      if (masked) q_y = __ldg(reinterpret_cast<const uint4*>(out + (size_t)(pix + pstride) * cout + g * 8));
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      dz[j] = yv[j] > 0.f ? dz[j] : 0.f;
+      if (masked) dz[j] = yv[j] > 0.f ? dz[j] : 0.f;
       accb[j] += dz[j];
     }
 #pragma unroll
@@ -992,7 +995,7 @@ long long pda_conv3x3_first_bwd_scratch_floats(int B, int H, int W, int cout, in
 
 int pda_conv3x3_first_bwd(const float* x0, const float* x1, const void* out, const void* dout, float* dw, float* db,
                           int B, int H, int W, int cout, float* scratch, void* stream) {
-  if (!x0 || !out || !dout || !dw || !db || !scratch) return PDA_ERR_ARG;
+  if (!x0 || !dout || !dw || !db || !scratch) return PDA_ERR_ARG;  // out may be NULL: dout already ReLU-masked
   const int groups = cout >> 3;
   if (cout <= 0 || (cout & 7) || 256 % groups) return PDA_ERR_SHAPE;
   if ((long long)B * H * W * cout >= 0x7fffffffLL) return PDA_ERR_SHAPE;

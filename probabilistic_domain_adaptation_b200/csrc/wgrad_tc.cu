@@ -16,16 +16,17 @@
 //   pixel tile = 16 rows x 8 px of one image = K 128, as 8 K-steps of 16 px (two rows)
 //   B (N x K)  = X^T: ONE slab [18 rows][8 px][64 ci]; the three ky taps of an output row are the slab rows
 //                y, y+1, y+2 = three 64-channel N blocks 1024 B apart  ->  N = 192
-//   A (M x K)  = dZ^T: three column-shifted slabs [16 rows][8 px][64 co] (shift 1 - kx; TMA zero-fills the border).
-//                M = 128 = the kx = 0 and kx = 1 slabs (LBO = slab stride); a second MMA takes kx = 2
+//   A (M x K)  = dZ^T: ONE buffer [16 rows][16 px][64 co] (px x0 - 1 ..; TMA zero-fills the border); tap kx reads each row
+//                from pixel 2 - kx on (descriptor start address + (2 - kx) * 128 B).  M = 128 = the block pair
+//                (kx 2 | kx 1) (LBO = 128 B: the same rows one pixel apart); a second MMA (M = 64) takes kx = 0
 //   D          = [128 (kx, co)][192 (ky, ci)] + an M = 64 accumulator [64 co][192] = 384 TMEM columns (+16: bias sums)
 // Two MMAs per K-step instead of five (plus a 16-column "ones" MMA for the bias gradient on the items of input chunk 0).
 // Measured with in-kernel cycle counters (round 1e): the MMA warp waits ~130 cycles per step for data and spends ~2130
 // cycles per step issuing against a full MMA queue, i.e. the tensor pipe runs 16 MMAs in 2130 cycles where the tensor
 // rate alone would need 1536.  The shared-memory port explains it: 66 KB of TMA fill + 144 KB of operand fetch per step
-// = 1640 cycles at 128 B/clk (skipping two of the three dZ slab loads: -7 %; skipping the kx = 2 MMA: -21 %).  The X
-// slab is fetched twice (M is capped at 128, the three kx need 192 rows) and the dZ tile is loaded three times (once
-// per column shift): those are the remaining levers.
+// = 1640 cycles at 128 B/clk (skipping two of the three dZ slab loads: -7 %; skipping the kx = 2 MMA: -21 %).  Round 2
+// loads dZ once (32 KB instead of 48 KB per step, four pipeline stages instead of three); the X slab is still fetched
+// twice per K-step (M is capped at 128, the three kx need 192 rows): that half-rate M = 64 MMA is the remaining lever.
 // Persistent stream-K schedule: the (item, pixel tile) steps are split into 148 equal contiguous ranges; a CTA flushes
 // its accumulators with coalesced fp32 atomics (lanes = output channels) into a zero-initialised scratch
 // [9 taps][ctot][cout] whenever its range crosses an item boundary.
@@ -34,6 +35,10 @@
 
 namespace pda {
 
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct WgradArgs {
   int B, H, W;
   int c0, c1, cout;
@@ -41,22 +46,27 @@ struct WgradArgs {
   int num_tiles;   // pixel tiles = B * tiles_x * tiles_y
   int n64;         // cout / 64
   int items;       // n64 * (c0 + c1) / 64
-  float* scratch;  // [9][ctot][cout] fp32, zero-initialised by the caller
-  float* dbias;    // [cout] fp32, zero-initialised, or nullptr: bias gradient = column sums of dZ, from one extra
-                   // "ones" MMA on the items of input-channel chunk 0
+  float* scratch;  // [9][ctot][cout] fp32, all zero at launch
+  float* dbias;    // [cout] fp32 scratch behind it, zero at launch, or nullptr: bias gradient = column sums of dZ, from
+                   // one extra "ones" MMA on the items of input-channel chunk 0
 };
 
 struct WgradSmem {
-  static constexpr int DZ_SLAB = 16 * 1024;          // [16 rows][8 px][64 co] bf16
+  // ONE dZ buffer of 16-pixel rows (px x0 - 1 .. x0 + 14, TMA zero-fills outside the image) serves the three column
+  // shifts: the A operand of tap kx starts (2 - kx) pixels = (2 - kx) * 128 B into a row (an unaligned start inside the
+  // 1024-byte swizzle atom is fine: the swizzle acts on absolute address bits, profiles/r02_conv_wide_slab.md) and its
+  // eight K rows run on into the second atom of the row.  Round 1 loaded three shifted 8-pixel slabs (48 KB per stage).
+  static constexpr int DZ_ROW = 2048;                // one row of the dZ buffer: 16 px x 128 B
+  static constexpr int DZ_BUF = 16 * DZ_ROW;         // [16 rows][16 px][64 co] bf16
   static constexpr int X_SLAB = 18 * 1024;           // [18 rows][8 px][64 ci] bf16
-  static constexpr int X_OFF = 3 * DZ_SLAB;
-  static constexpr int STAGE_BYTES = 3 * DZ_SLAB + X_SLAB;
-  static constexpr int STAGES = 3;
+  static constexpr int X_OFF = DZ_BUF;
+  static constexpr int STAGE_BYTES = DZ_BUF + X_SLAB;
+  static constexpr int STAGES = 4;
   static constexpr int ONES_OFF = STAGES * STAGE_BYTES;  // 1 KB of bf16 ones: an MN-major B block whose K rows all alias
   static constexpr int BAR_OFF = ONES_OFF + 1024;
   static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 2) * 8;
   static constexpr int DYN_BYTES = SLOT_OFF + 16 + 1024;
-  static constexpr int TMEM_COLS = 512;              // [0,192) kx 0|1, [192,384) kx 2, [384,400) bias column sums
+  static constexpr int TMEM_COLS = 512;              // [0,192) kx 2|1, [192,384) kx 0, [384,400) bias column sums
   static constexpr int D2_COL = 192, BIAS_COL = 384;
 };
 
@@ -123,9 +133,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
         mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
         const int c = ch << 6;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)  // dZ shifted by 1 - kx columns (out-of-image columns arrive as zeros)
-          tma_load_4d(sa + kx * L::DZ_SLAB, &tmDZ, full_bar(s), nb << 6, x0 + 1 - kx, y0, img);
+        // dZ columns x0 - 1 .. x0 + 14 (out-of-image columns arrive as zeros)
+        tma_load_4d(sa, &tmDZ, full_bar(s), nb << 6, x0 - 1, y0, img);
         if (c < p.c0)
           tma_load_4d(sa + L::X_OFF, &tmX0, full_bar(s), c, x0, y0 - 1, img);
         else
@@ -162,20 +171,23 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
       tc_fence_after();
       if (leader) {
         const uint32_t sa = sbase + s * L::STAGE_BYTES;
-        // MN-major SWIZZLE_128B: 64-channel blocks LBO apart, 8-pixel K groups (one slab row) 1024 B apart (SBO)
-        const uint64_t da01 = umma_desc_mn_sw128(sa, L::DZ_SLAB, 1024);                  // M = (kx 0 | kx 1) x co
-        const uint64_t da2 = umma_desc_mn_sw128(sa + 2 * L::DZ_SLAB, 0, 1024);           // M = 64: kx 2 x co
-        const uint64_t da1 = umma_desc_mn_sw128(sa + L::DZ_SLAB, 0, 1024);               // unshifted dZ (bias sums)
+        // MN-major SWIZZLE_128B: 64-channel blocks LBO apart, 8-pixel K groups SBO apart.  dZ: tap kx reads the row
+        // from pixel (2 - kx) on; the M = 128 operand is the block pair (kx 2 | kx 1) = the same rows one pixel
+        // (LBO = 128 B) apart; a K group is one row of the 16-pixel buffer (SBO = 2048).  X: N blocks = the slab rows
+        // y, y+1, y+2 (LBO = 1024), K groups = slab rows (SBO = 1024).
+        const uint64_t da21 = umma_desc_mn_sw128(sa, 128, L::DZ_ROW);                    // M = (kx 2 | kx 1) x co
+        const uint64_t da0 = umma_desc_mn_sw128(sa + 2 * 128, 0, L::DZ_ROW);             // M = 64: kx 0 x co
+        const uint64_t da1 = umma_desc_mn_sw128(sa + 128, 0, L::DZ_ROW);                 // unshifted dZ (bias sums)
         const uint64_t db = umma_desc_mn_sw128(sa + L::X_OFF, 1024, 1024);               // N = (ky 0 | 1 | 2) x ci
         const uint64_t d1s = umma_desc_mn_sw128(sbase + L::ONES_OFF, 0, 0);              // all-ones K rows
         const bool bias_item = p.dbias != nullptr && item / p.n64 == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          // 16 pixels per MMA = 2 rows of 8 px = 2048 B: +128 in 16-byte units
+          // 16 pixels per MMA = 2 image rows of 8 px: dZ advances 2 x 2048 B, X 2 x 1024 B (16-byte units)
           const uint32_t acc = (!first || k != 0) ? 1u : 0u;
-          umma_bf16(tmem, da01 + 128 * k, db + 128 * k, idesc, acc);
-          umma_bf16(tmem + L::D2_COL, da2 + 128 * k, db + 128 * k, idesc64, acc);
-          if (bias_item) umma_bf16(tmem + L::BIAS_COL, da1 + 128 * k, d1s, idesc_bias, acc);  // sum_px dZ[px][co]
+          umma_bf16(tmem, da21 + 256 * k, db + 128 * k, idesc, acc);
+          umma_bf16(tmem + L::D2_COL, da0 + 256 * k, db + 128 * k, idesc64, acc);
+          if (bias_item) umma_bf16(tmem + L::BIAS_COL, da1 + 256 * k, d1s, idesc_bias, acc);  // sum_px dZ[px][co]
         }
         umma_commit(empty_bar(s));
       }
@@ -201,9 +213,9 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
       const size_t tap_stride = static_cast<size_t>(ctot) * p.cout;
 #pragma unroll 1
       for (int part = 0; part < 2; ++part) {
-        // part 0: M = 128 accumulator, row = (kx, co) = this thread's lane.  part 1: M = 64 accumulator of kx = 2:
+        // part 0: M = 128 accumulator, row = (kx, co) = this thread's lane.  part 1: M = 64 accumulator of kx = 0:
         // rows 16 q .. 16 q + 15 sit in the first 16 lanes of lane quarter q
-        const int kx = part == 0 ? (q >> 1) : 2;
+        const int kx = part == 0 ? 2 - (q >> 1) : 0;   // accumulator rows: (kx 2 | kx 1) x co, then kx 0 x co
         const bool live = part == 0 || lane < 16;
         float* pbase = part == 0 ? base : base - co_l + 16 * q + lane;
 #pragma unroll 1
@@ -248,12 +260,14 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
 }
 
 // scratch [9][ctot][cout] fp32 -> dW OIHW fp32 [cout][ctot][3][3] (written, or accumulated when accumulate != 0);
-// the bias sums accumulated behind the scratch go to dbias.
+// the bias sums accumulated behind the scratch go to dbias.  clean != 0: everything that is read is ZEROED again, so that a
+// scratch the caller keeps per layer is ready for the next launch without a memset (measured: the extra stores cost more
+// than the memset they replace -- +4 % on the weight-gradient path -- so the Python host does not use it).
 // A 32 (ci) x 32 (co) tile with all nine taps goes through shared memory: reads are coalesced along co, and for one co
 // the 32 ci x 9 taps are 288 CONTIGUOUS floats of dW (grid: ctot / 32 x cout / 32; both are multiples of 64).
 __global__ void __launch_bounds__(256)
-wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot, int accumulate,
-                     float* __restrict__ dbias) {
+wgrad_scatter_kernel(float* __restrict__ scratch, float* __restrict__ dw, int cout, int ctot, int accumulate,
+                     float* __restrict__ dbias, int clean) {
   __shared__ float tile[9][32][33];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +275,7 @@ wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, 
     if (threadIdx.x < 32) {
       const float v = scratch[9ull * cout * ctot + co0 + threadIdx.x];
       dbias[co0 + threadIdx.x] = accumulate ? dbias[co0 + threadIdx.x] + v : v;
+      if (clean) scratch[9ull * cout * ctot + co0 + threadIdx.x] = 0.f;
     }
   }
 #pragma unroll
@@ -268,7 +283,9 @@ wgrad_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int ci_l = warp + 8 * k;
-      tile[tap][ci_l][lane] = scratch[(static_cast<size_t>(tap) * ctot + ci0 + ci_l) * cout + co0 + lane];
+      const size_t si = (static_cast<size_t>(tap) * ctot + ci0 + ci_l) * cout + co0 + lane;
+      tile[tap][ci_l][lane] = scratch[si];
+      if (clean) scratch[si] = 0.f;
     }
   __syncthreads();
 #pragma unroll
@@ -317,9 +334,15 @@ bias_grad_kernel(const __nv_bfloat162* __restrict__ dz, float* __restrict__ db, 
 
 using namespace pda;
 
+// scratch layout (fp32 words): [9 * cout * ctot] tap-major partial sums | [cout] bias sums
+extern "C" long long pda_conv3x3_wgrad_scratch_floats(int ctot, int cout) {
+  if (ctot <= 0 || cout <= 0) return 0;
+  return 9LL * cout * ctot + cout;
+}
+
 extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz,
                                       float* scratch, float* dw_oihw, float* dbias, int B, int H, int W, int cout,
-                                      int accumulate, void* stream_) {
+                                      int accumulate, int scratch_is_zero, void* stream_) {
   if (!src0 || !dz || !scratch || !dw_oihw || (c1 > 0 && !src1)) return PDA_ERR_ARG;
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -334,8 +357,7 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   a.n64 = cout >> 6;
   a.items = a.n64 * (ctot >> 6);
   a.scratch = scratch;
-  // the bias sums are accumulated in the cout floats BEHIND the weight scratch (one memset covers both) and handed to
-  // dbias by the scatter kernel
+  // the bias sums are accumulated in the cout floats BEHIND the weight scratch
   a.dbias = dbias ? scratch + 9ull * cout * ctot : nullptr;
   CUtensorMap tX0, tX1, tDZ;
   int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, 8, 18, 64);
@@ -346,9 +368,12 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   } else {
     tX1 = tX0;
   }
-  r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 8, 16, 64);
+  r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 16, 16, 64);
   if (r) return r;
-  if (cudaMemsetAsync(scratch, 0, sizeof(float) * (9ull * cout * ctot + cout), stream) != cudaSuccess) return PDA_ERR_CUDA;
+  // scratch_is_zero: the caller keeps this scratch across calls; the scatter kernel leaves it all-zero again (no memset)
+  if (!scratch_is_zero &&
+      cudaMemsetAsync(scratch, 0, sizeof(float) * pda_conv3x3_wgrad_scratch_floats(ctot, cout), stream) != cudaSuccess)
+    return PDA_ERR_CUDA;
   static int configured[64];
   if (dyn_smem_attr_needed(configured, WgradSmem::DYN_BYTES)) {
     if (cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -361,6 +386,7 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   wgrad3x3_tc_kernel<<<grid, 192, WgradSmem::DYN_BYTES, stream>>>(tX0, tX1, tDZ, a);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
   PDA_COUNT(1);
-  wgrad_scatter_kernel<<<dim3(ctot / 32, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, cout, ctot, accumulate, dbias);
+  wgrad_scatter_kernel<<<dim3(ctot / 32, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, cout, ctot, accumulate, dbias,
+                                                                       scratch_is_zero);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

@@ -313,21 +313,42 @@ def multi_tensor_ema(table, momentum, iteration_dev=None):
 # ------------------------------------------------------------------------------------------------
 # training (backward) wrappers
 # ------------------------------------------------------------------------------------------------
-def conv3x3_wgrad(src0, src1, dz, want_bias=True):
-    """dW (cout, c0+c1, 3, 3) fp32 and db (cout,) of conv3x3 from its NHWC bf16 inputs and dZ."""
+# Self-cleaning per-layer scratch for the weight-gradient kernel (no memset per launch).  Off: measured slower than a
+# fresh scratch + memset (the clean-up stores double the re-layout kernel's write traffic).
+WGRAD_PERSISTENT_SCRATCH = False
+
+
+def wgrad_scratch(owner, ctot, cout, dev):
+    """The persistent, self-cleaning scratch of one conv layer's weight-gradient kernel (zeroed once, here; the kernel
+    leaves it all zero again after every launch, so no memset runs per step).  Kept on the nn.Conv2d container."""
+    n = _lib.load().pda_conv3x3_wgrad_scratch_floats(ctot, cout)
+    cached = owner.__dict__.get("_pda_wgrad_scratch")
+    if cached is None or cached.numel() != n or cached.device != dev:
+        cached = owner.__dict__["_pda_wgrad_scratch"] = torch.zeros(n, dtype=torch.float32, device=dev)
+    return cached
+
+
+def conv3x3_wgrad(src0, src1, dz, want_bias=True, owner=None):
+    """dW (cout, c0+c1, 3, 3) fp32 and db (cout,) of conv3x3 from its NHWC bf16 inputs and dZ.
+    owner: the nn.Conv2d container of the layer -- its persistent zero-invariant scratch is used (no memset per call)."""
     _need_cuda(src0, src1, dz)
     lib = _lib.load()
     B, H, W, c0 = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
     cout = dz.shape[3]
     assert dz.shape[:3] == src0.shape[:3] and dz.is_contiguous() and src0.is_contiguous()
+    assert src0.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16
     dev = src0.device
-    scratch = torch.empty(cout * 9 * (c0 + c1) + cout, dtype=torch.float32, device=dev)
+    if owner is not None and WGRAD_PERSISTENT_SCRATCH:
+        scratch, is_zero = wgrad_scratch(owner, c0 + c1, cout, dev), 1
+    else:
+        scratch = torch.empty(lib.pda_conv3x3_wgrad_scratch_floats(c0 + c1, cout), dtype=torch.float32, device=dev)
+        is_zero = 0
     dw = torch.empty((cout, c0 + c1, 3, 3), dtype=torch.float32, device=dev)
     db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
     with _Timed("wgrad3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
         rc = lib.pda_conv3x3_wgrad_bf16(src0.data_ptr(), c0, _ptr(src1), c1, dz.data_ptr(), scratch.data_ptr(),
-                                        dw.data_ptr(), _ptr(db), B, H, W, cout, 0, _stream())
+                                        dw.data_ptr(), _ptr(db), B, H, W, cout, 0, is_zero, _stream())
     _lib.check(rc, "conv3x3_wgrad")
     return dw, db
 
@@ -357,16 +378,19 @@ def upsample2x_bwd(dout):
     return din
 
 
-def conv3x3_first_bwd(x0, x1, out, dout):
+def conv3x3_first_bwd(x0, x1, out, dout, premasked=False):
+    """premasked: dout already carries the layer's ReLU mask (output of the next layer's dgrad conv with relu_mask=out):
+    the forward output is then not read at all."""
     _need_cuda(x0, x1, out, dout)
     lib = _lib.load()
-    B, H, W, cout = out.shape
+    B, H, W, cout = dout.shape
     cin = 1 if x1 is None else 2
-    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=out.device)
-    db = torch.empty((cout,), dtype=torch.float32, device=out.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dout.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=dout.device)
     scratch = torch.empty(lib.pda_conv3x3_first_bwd_scratch_floats(B, H, W, cout, cin), dtype=torch.float32,
-                          device=out.device)
-    _lib.check(lib.pda_conv3x3_first_bwd(x0.data_ptr(), _ptr(x1), out.data_ptr(), dout.data_ptr(), dw.data_ptr(),
+                          device=dout.device)
+    _lib.check(lib.pda_conv3x3_first_bwd(x0.data_ptr(), _ptr(x1), 0 if premasked else out.data_ptr(), dout.data_ptr(),
+                                         dw.data_ptr(),
                                          db.data_ptr(), B, H, W, cout, scratch.data_ptr(), _stream()),
                "conv3x3_first_bwd")
     return dw, db

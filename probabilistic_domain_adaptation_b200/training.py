@@ -46,7 +46,7 @@ class Conv3x3Fn(torch.autograd.Function):
                 dsrc1, _ = ops.conv3x3(dz, None, wrot[c0:], None, relu=False)
         if need_w or need_b:
             # the bias gradient (column sums of dZ) rides along in the weight-gradient kernel
-            dw, db = ops.conv3x3_wgrad(x, src1, dz, want_bias=True)
+            dw, db = ops.conv3x3_wgrad(x, src1, dz, want_bias=True, owner=ctx.conv)
         return dx, dsrc1, dw, db, None, None, None
 
 
@@ -109,12 +109,14 @@ class ConvStackFn(torch.autograd.Function):
             need_w = ctx.needs_input_grad[6 + 2 * j] or ctx.needs_input_grad[7 + 2 * j]
             if j == 0 and ctx.first_planes:
                 if need_w:
-                    grads[0], grads[1] = ops.conv3x3_first_bwd(x0, x1, ys[0], dz)  # (mask by ys[0] is idempotent)
+                    # for n > 1 dz left the dgrad conv of layer 1 already masked by ys[0]; the single-layer block got
+                    # its mask from relu_pool_bwd above
+                    grads[0], grads[1] = ops.conv3x3_first_bwd(x0, x1, ys[0], dz, premasked=True)
                 break
             xin = ys[j - 1] if j > 0 else x
             s1 = src1 if j == 0 else None
             if need_w:
-                grads[2 * j], grads[2 * j + 1] = ops.conv3x3_wgrad(xin, s1, dz, want_bias=True)
+                grads[2 * j], grads[2 * j + 1] = ops.conv3x3_wgrad(xin, s1, dz, want_bias=True, owner=conv)
             if j > 0:
                 dz, _ = ops.conv3x3(dz, None, packed_weight(conv, rot180=True), None, relu=False, relu_mask=ys[j - 1])
             else:

@@ -225,3 +225,22 @@ def test_multi_tensor_ema_bit_exact():
     ops.multi_tensor_ema(table, m)
     for t, r in zip(teacher, ref):
         assert torch.equal(t, r)
+
+
+def test_refresh_packed_matches_single_tensor_pack():
+    """autograd_ops.refresh_packed (ONE launch for all convs of a module: forward bf16, rot180 bf16, forward fp16) equals
+    the per-conv pack kernel bit for bit."""
+    import torch.nn as nn
+    from probabilistic_domain_adaptation_b200 import autograd_ops, ops
+    dev = _dev()
+    torch.manual_seed(3)
+    mod = nn.Sequential(nn.Conv2d(64, 128, 3, padding=1), nn.Conv2d(128, 64, 3, padding=1),
+                        nn.Conv2d(192, 256, 3, padding=1), nn.Conv2d(1, 64, 3, padding=1)).to(dev)
+    autograd_ops.refresh_packed(mod, rot180=True, bf16=True, f16=True)
+    for conv in list(mod)[:3]:
+        w = conv.weight.detach()
+        assert torch.equal(conv.__dict__["_pda_packed"][1], ops.pack_conv3x3_weights(w))
+        assert torch.equal(conv.__dict__["_pda_packed_rot"][1], ops.pack_conv3x3_weights(w, rot180=True))
+        if ops.INFER_DTYPE == torch.float16:
+            assert torch.equal(conv.__dict__["_pda_packed_f16"][1], ops.pack_conv3x3_weights(w, dtype=torch.float16))
+    assert "_pda_packed" not in mod[3].__dict__          # the cin = 1 first layer is not a tensor-core conv
