@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--train-size", type=int, default=512)
     ap.add_argument("--bucket-mb", type=float, default=25.0, help="gradient all-reduce bucket size (training legs)")
     ap.add_argument("--no-graph", action="store_true", help="training legs: time the Python-launched step only")
+    ap.add_argument("--reserve-sms", type=int, default=4,
+                    help="N > 1: SMs the persistent kernels leave to NCCL so that the all-reduce overlaps the backward")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="wire format of the gradient all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the S sweep and the source-training step")
     return ap.parse_args()
 
@@ -256,7 +259,9 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
     for p in teacher.parameters():
         p.requires_grad = False
     opt = FusedAdam(model.parameters(), lr=1e-5, capturable=True)
-    reducer = GradAllReducer(model, bucket_mb=args.bucket_mb)
+    import torch as _t
+    comm = _t.bfloat16 if args.grad_comm == "bf16" else None
+    reducer = GradAllReducer(model, bucket_mb=args.bucket_mb, reserve_sms=args.reserve_sms, comm_dtype=comm)
     ema = consensus.MomentumUpdater(model, teacher)
     backprop = steps.default_backprop(opt, reducer, model)
     use_graph = not args.no_graph
@@ -339,7 +344,7 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
         Bs = 8
         xs = torch.randn(Bs, 1, HW, HW, generator=g).to(dev)
         ys = (torch.rand(Bs, 1, HW, HW, generator=g) > 0.5).float().to(dev)
-        red2 = GradAllReducer(model)
+        red2 = GradAllReducer(model, reserve_sms=args.reserve_sms, comm_dtype=comm)
         bp2 = steps.default_backprop(opt, red2, model)
         for _ in range(2):
             steps.punet_step(model, opt, xs, ys, backprop=bp2)
@@ -364,7 +369,7 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
             epsj = torch.randn(S, Bj, 6, generator=torch.Generator().manual_seed(3)).to(dev)
             # consensus WEIGHTING (--consensus without --masking, livecell_adamatch.py:122,150): the model keeps
             # consensus_masking=True (= "use consm"), the trainer returns fp32 k/16 weights instead of the int64 mask
-            red3 = GradAllReducer(model)
+            red3 = GradAllReducer(model, reserve_sms=args.reserve_sms, comm_dtype=comm)
             bp3 = steps.default_backprop(opt, red3, model)
             fnj = lambda: steps.adamatch_step(model, opt, xs, ys, xt1, xt2, n_samples=S, do_consensus_masking=False,  # noqa: E731
                                               backprop=bp3, eps=epsj)
@@ -415,7 +420,9 @@ def run_train_leg(args, dev, world, rank, local, lib, barrier):
         "config": {"workload": f"mean-teacher consensus-masking step: teacher forward + S={S} samples + mask, student "
                                f"Dice-ELBO fwd/bwd + L2, grad all-reduce, Adam, EMA on {Bt}x1x{HW}x{HW} per GPU "
                                f"(BASELINE config 3, MitoEM shape)",
-                   "batch_per_gpu": Bt, "patch": HW, "samples": S, "parallelism": f"dp{world}"},
+                   "batch_per_gpu": Bt, "patch": HW, "samples": S, "parallelism": f"dp{world}",
+                   "grad_allreduce": (f"NCCL, {args.grad_comm} on the wire, {args.bucket_mb:g} MB buckets, "
+                                      f"{args.reserve_sms} SMs left to NCCL") if world > 1 else None},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 2 * host_x1.numel() * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
@@ -651,12 +658,13 @@ def run_ours(args):
     line = {
         "metric": "punet_mc_px_samples_per_s", "value": value, "unit": "px*samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"PUNet (64-128-256-512, latent 6) MC inference: forward + S={S} fused "
                                f"Fcomb/sigmoid/mean/consensus-mask on {T} tiles/GPU of 1x{HW}x{HW} "
                                f"(BASELINE config 5 at S={S})",
                    "tiles_per_gpu": T, "tile": HW, "samples": S, "parallelism": f"tile-sharded x{world}",
-                   "l2": "activations >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+                   "l2": "activations >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                   "arithmetic": "fp16 operands (no-grad path) / bf16 operands (training leg), fp32 accumulation"},
         "e2e": {"value": e2e_value, "unit": "px*samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host_x.numel() * 4,
                 "d2h_bytes_per_step": out_mean.numel() * 4 + out_mask.numel() * 8},

@@ -77,6 +77,11 @@ int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const voi
  * queries.  Returns the previous mode.  Results are bit-identical between the two. */
 int pda_set_conv_pair(int mode);
 
+/* SMs the persistent tensor-core kernels (conv, weight gradient, Fcomb backward) may occupy (default 148).  Data-parallel
+ * training leaves a few SMs to NCCL so that the gradient all-reduce runs next to the backward kernels instead of
+ * between them.  sms <= 0 only queries.  Returns the previous value. */
+int pda_set_sm_budget(int sms);
+
 /* Same contract (bf16 only) on plain CUDA cores (one thread per output element).  Cross-check kernel for the
  * parity tests; the product path never selects it implicitly. */
 int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
@@ -128,6 +133,15 @@ int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, const float* w
                                 const float* b2, const float* w3, const float* b3, int B, int P, int S, int latent,
                                 float upper, float lower, float* mean_prob, float* cons_weight, int64_t* cons_mask,
                                 float* logits, float* probs, int feat_f16, void* stream);
+
+/* Same contract for any depth: no_convs_fcomb = n_mid + 2 with n_mid >= 0 hidden 64 -> 64 layers (wmid [n_mid][64][64],
+ * bmid [n_mid][64]).  The reference's DEFAULT constructor builds no_convs_fcomb = 4 (probabilistic_unet.py:231-236); every
+ * script uses 3, which the two kernels above serve.  Plain fp32, one pixel per thread: a correctness path for non-script
+ * architectures (forward only). */
+int pda_fcomb_mc_consensus_deep(const void* feat, const float* z, const float* w1, const float* b1, const float* wmid,
+                                const float* bmid, int n_mid, const float* w3, const float* b3, int B, int P, int S,
+                                int latent, float upper, float lower, float* mean_prob, float* cons_weight,
+                                int64_t* cons_mask, float* logits, float* probs, int feat_f16, void* stream);
 
 /* Mean-teacher EMA over many tensors in one launch: t = t*m + p*(1-m)  (mean_teacher_trainer.py:52-55,
  * adamt_trainer.py:40-43).  table: device int64 [n_chunks][3] = (teacher_ptr, student_ptr, numel<=65536). */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "pda_conv3x3_first": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_tc": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "pda_set_conv_pair": [_I],
+    "pda_set_sm_budget": [_I],
     "pda_conv3x3_bf16_simt": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_avgpool2": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -34,6 +35,8 @@ SIGNATURES = {
     "pda_fcomb_scratch_floats": [_I, _I],
     "pda_fcomb_mc_consensus": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],
     "pda_fcomb_mc_consensus_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _I, _P],
+    "pda_fcomb_mc_consensus_deep": [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _I,
+                                    _P],
     "pda_tile_gather_standardize": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _P],
     "pda_tile_scatter": [_P, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "pda_image_stats": [_P, _I, _c.c_longlong, _P, _P],

@@ -41,7 +41,7 @@ def refresh_packed(module, rot180=True, bf16=True, f16=None):
     convs = state["convs"] if state is not None else None
     if convs is None:  # the module tree of these nets is fixed after construction: walk it once
         convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3)
-                 and m.in_channels % 64 == 0]
+                 and m.in_channels % 64 == 0 and m.out_channels in (64, 128, 256, 512)]
     if not convs or not convs[0].weight.is_cuda:
         return
     if f16 is None:

@@ -51,6 +51,7 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
                int act_f16, int* range_flag, cudaStream_t stream);
 
 int conv_pair_mode(int set);  // csrc/conv3x3_tc.cu
+int sm_budget(int set);       // csrc/conv3x3_tc.cu
 
 // CTA-pair (cta_group::2) variant, csrc/conv3x3_tc2.cu
 int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,

@@ -432,6 +432,15 @@ int conv_pair_mode(int set) {
   return mode.load();
 }
 
+// SMs the persistent tensor-core kernels (conv, conv pair, wgrad, Fcomb backward) may occupy.  Data-parallel training
+// lowers it by a few SMs so that NCCL's all-reduce CTAs find room to run NEXT TO the backward kernels instead of
+// between them (parallel.GradAllReducer); 148 = the whole B200.  set <= 0: query only.
+int sm_budget(int set) {
+  static std::atomic<int> budget{148};
+  if (set > 0) return budget.exchange(set > 148 ? 148 : (set < 2 ? 2 : set));
+  return budget.load();
+}
+
 template <int BN, int MT, bool RES, bool F16>
 static int launch_conv_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                            const ConvArgs& args, cudaStream_t stream) {
@@ -444,7 +453,8 @@ static int launch_conv_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const C
   }
   const long long units = (long long)args.tiles_x * args.tiles_y * args.B * (args.cout / BN);
   if (units > 0x7fffffffLL) return PDA_ERR_SHAPE;
-  const int grid = (int)(units < 148 ? units : 148);
+  const int sms = sm_budget(0);
+  const int grid = (int)(units < sms ? units : sms);
   PDA_COUNT(1);
   conv3x3_tc_kernel<BN, MT, RES, F16><<<grid, CONV_THREADS, L::DYN_BYTES, stream>>>(a0, a1, b, o, args);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;

@@ -501,7 +501,9 @@ static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const 
   const long long mtiles = (long long)args.tiles_x * args.tiles_y * args.B;
   const long long units = ((mtiles + 1) / 2) * (args.cout / BN);
   if (units > 0x3fffffffLL) return PDA_ERR_SHAPE;
-  const int pairs = (int)(units < max_clusters[dev] ? units : max_clusters[dev]);
+  int cap = max_clusters[dev];
+  if (cap > sm_budget(0) / 2) cap = sm_budget(0) / 2;
+  const int pairs = (int)(units < cap ? units : cap);
   cfg.gridDim = dim3(2 * pairs);
   PDA_COUNT(1);
   if (cudaLaunchKernelEx(&cfg, kern, a0, a1, b, o, args) != cudaSuccess) return PDA_ERR_CUDA;

@@ -128,6 +128,71 @@ fcomb_mc_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// General depth: no_convs_fcomb = n_mid + 2 with any n_mid >= 0 hidden 64 -> 64 layers (the reference's default
+// constructor builds no_convs_fcomb = 4; every script uses 3, which the kernels above serve).  Plain fp32, one pixel per
+// thread, weights through the read-only cache: a correctness path for non-script architectures, not a fast one.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fcomb_deep_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ w1,
+                  const float* __restrict__ b1, const float* __restrict__ wmid, const float* __restrict__ bmid,
+                  int n_mid, const float* __restrict__ w3, const float* __restrict__ b3, int P, int S, int L, int B,
+                  float upper, float lower, float* __restrict__ mean_prob, float* __restrict__ cons_weight,
+                  int64_t* __restrict__ cons_mask, float* __restrict__ logits, float* __restrict__ probs, int feat_f16) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= P) return;
+  const int kin = FC + L;
+  const long long gp = (long long)b * P + pix;
+  float f[FC], h1[FC], a[FC], nx[FC];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(feat + gp * FC);
+    for (int k = 0; k < FC / 8; ++k) {
+      const uint4 v = __ldg(src + k);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = feat_f16 ? unpack_act2<true>(w4[i]) : unpack_act2<false>(w4[i]);
+        f[8 * k + 2 * i] = t.x;
+        f[8 * k + 2 * i + 1] = t.y;
+      }
+    }
+  }
+  for (int j = 0; j < FC; ++j) {
+    float acc = __ldg(b1 + j);
+    for (int i = 0; i < FC; ++i) acc = fmaf(__ldg(w1 + j * kin + i), f[i], acc);
+    h1[j] = acc;
+  }
+  float psum = 0.f;
+  int count = 0;
+  for (int s = 0; s < S; ++s) {
+    const float* zs = z + ((long long)s * B + b) * L;
+    for (int j = 0; j < FC; ++j) {
+      float acc = h1[j];
+      for (int d = 0; d < L; ++d) acc = fmaf(__ldg(w1 + j * kin + FC + d), __ldg(zs + d), acc);
+      a[j] = fmaxf(acc, 0.f);
+    }
+    for (int m = 0; m < n_mid; ++m) {
+      const float* wm = wmid + (long long)m * FC * FC;
+      for (int j = 0; j < FC; ++j) {
+        float acc = __ldg(bmid + m * FC + j);
+        for (int i = 0; i < FC; ++i) acc = fmaf(__ldg(wm + j * FC + i), a[i], acc);
+        nx[j] = fmaxf(acc, 0.f);
+      }
+      for (int j = 0; j < FC; ++j) a[j] = nx[j];
+    }
+    float logit = __ldg(b3);
+    for (int j = 0; j < FC; ++j) logit = fmaf(__ldg(w3 + j), a[j], logit);
+    const float pr = sigmoid_f32(logit);
+    psum += pr;
+    count += (pr >= upper || pr <= lower) ? 1 : 0;
+    if (logits) logits[((long long)s * B + b) * P + pix] = logit;
+    if (probs) probs[((long long)s * B + b) * P + pix] = pr;
+  }
+  if (mean_prob) mean_prob[gp] = psum / (float)S;
+  if (cons_weight) cons_weight[gp] = (float)count / (float)S;
+  if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
+}
+
 int fcomb_mc_fp32(const void* feat, const float* z, const float* w1, const float* b1, const float* w2, const float* b2,
                   const float* w3, const float* b3, int B, int P, int S, int latent, float upper, float lower,
                   float* mean_prob, float* cons_weight, int64_t* cons_mask, float* logits, float* probs,
@@ -166,4 +231,18 @@ extern "C" int pda_fcomb_mc_consensus_fp32(const void* feat, const float* z, con
   if (B <= 0 || P <= 0 || S <= 0 || latent <= 0) return PDA_ERR_SHAPE;
   return fcomb_mc_fp32(feat, z, w1, b1, w2, b2, w3, b3, B, P, S, latent, upper, lower, mean_prob, cons_weight,
                        cons_mask, logits, probs, nullptr, feat_f16, (cudaStream_t)stream);
+}
+
+extern "C" int pda_fcomb_mc_consensus_deep(const void* feat, const float* z, const float* w1, const float* b1,
+                                           const float* wmid, const float* bmid, int n_mid, const float* w3,
+                                           const float* b3, int B, int P, int S, int latent, float upper, float lower,
+                                           float* mean_prob, float* cons_weight, int64_t* cons_mask, float* logits,
+                                           float* probs, int feat_f16, void* stream) {
+  if (!feat || !z || !w1 || !b1 || !w3 || !b3 || (n_mid > 0 && (!wmid || !bmid))) return PDA_ERR_ARG;
+  if (B <= 0 || B > 65535 || P <= 0 || S <= 0 || latent <= 0 || n_mid < 0) return PDA_ERR_SHAPE;
+  PDA_COUNT(1);
+  fcomb_deep_kernel<<<dim3((P + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(feat), z, w1, b1, wmid, bmid, n_mid, w3, b3, P, S, latent, B, upper, lower,
+      mean_prob, cons_weight, cons_mask, logits, probs, feat_f16);
+  return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }

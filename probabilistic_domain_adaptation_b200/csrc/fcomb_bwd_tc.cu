@@ -437,7 +437,8 @@ int fcomb_bwd_tc(const void* feat, const float* z, const float* w1, const float*
   const int tiles_per_img = (P + 127) / 128;
   const long long num_tiles = (long long)tiles_per_img * B;
   if (num_tiles > 0x7fffffffLL) return PDA_ERR_SHAPE;
-  const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
+  const int sms = sm_budget(0);
+  const int grid = (int)(num_tiles < sms ? num_tiles : sms);
   PDA_COUNT(2);
   fb_bz_kernel<<<(B * FB_C + 255) / 256, 256, 0, st>>>(z, w1, b1, bz, B, L);
   fcomb_bwd_tc_kernel<<<grid, 256, FbSmem::DYN_BYTES, st>>>(tm, bz, w1, w2, b2, w3, skip_flag, dlogit, P, L, B, tiles_per_img,

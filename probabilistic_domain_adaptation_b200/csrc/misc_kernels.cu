@@ -629,6 +629,8 @@ int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const voi
 
 int pda_set_conv_pair(int mode) { return conv_pair_mode(mode); }
 
+int pda_set_sm_budget(int sms) { return sm_budget(sms); }
+
 int pda_conv3x3_bf16_simt(const void* src0, int c0, const void* src1, int c1, const void* w_packed,
                           const float* bias, void* out, void* out_pool, int B, int H, int W, int cout, int relu,
                           void* stream) {

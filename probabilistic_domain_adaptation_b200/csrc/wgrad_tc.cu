@@ -381,7 +381,8 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
       return PDA_ERR_CUDA;
   }
   const long long steps = (long long)a.items * a.num_tiles;
-  const int grid = (int)(steps < 148 ? steps : 148);
+  const int sms = sm_budget(0);
+  const int grid = (int)(steps < sms ? steps : sms);
   PDA_COUNT(1);
   wgrad3x3_tc_kernel<<<grid, 192, WgradSmem::DYN_BYTES, stream>>>(tX0, tX1, tDZ, a);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;

@@ -38,8 +38,9 @@ class Encoder(nn.Module):
             raise NotImplementedError("only padding=True is implemented")
         if self.input_channels > 2:
             raise NotImplementedError("first-layer kernel handles 1 (prior) or 2 (posterior) input planes")
-        if any(f % 64 for f in self.num_filters):
-            raise NotImplementedError("num_filters must be multiples of 64 for the tcgen05 conv tiles")
+        if max(self.num_filters) > 512 or min(self.num_filters) < 1 or self.num_filters[0] > 256:
+            raise NotImplementedError("encoder widths must be in 1..512 (first block <= 256); widths that are not "
+                                      "multiples of 64 run zero-padded to the 64-channel tiles of the conv kernels")
         mods, self._blocks = [], []
         prev = self.input_channels
         for i, f in enumerate(self.num_filters):
@@ -73,7 +74,7 @@ class Encoder(nn.Module):
     def forward(self, input):
         planes = input.float()
         segm = planes[:, 1:2].contiguous() if planes.shape[1] == 2 else None
-        return as_nchw(self.forward_nhwc(planes[:, 0:1].contiguous(), segm))
+        return as_nchw(self.forward_nhwc(planes[:, 0:1].contiguous(), segm))[:, :self.num_filters[-1]]
 
 
 class AxisAlignedConvGaussian(nn.Module):
@@ -102,7 +103,11 @@ class AxisAlignedConvGaussian(nn.Module):
             raise RuntimeError("posterior nets take (patch, segm); prior nets take patch only")
         enc = self.encoder.forward_nhwc(input.float().contiguous(),
                                         None if segm is None else segm.float().contiguous())
-        self.mu_log_sigma = gauss_head_op(enc, self.conv_layer, self.latent_dim)
+        head = self.conv_layer
+        if enc.shape[3] != head.in_channels:  # encoder output zero-padded to a multiple of 64 channels
+            from .unet_blocks import ConvView
+            head = ConvView(head, (head.in_channels,), (enc.shape[3],), head.out_channels)
+        self.mu_log_sigma = gauss_head_op(enc, head, self.latent_dim)
         return self.mu_log_sigma
 
     def forward(self, input, segm=None):
@@ -131,9 +136,9 @@ class Fcomb(nn.Module):
         self.name = "Fcomb"
         if not use_tile:
             raise NotImplementedError("use_tile=False builds no layers in the reference")
-        if no_convs_fcomb != 3 or self.num_filters[0] != 64 or num_classes != 1:
-            raise NotImplementedError("fused Fcomb kernel: no_convs_fcomb=3, num_filters[0]=64, num_classes=1 "
-                                      "(the configuration of every reference script)")
+        if no_convs_fcomb < 2 or self.num_filters[0] > 64 or num_classes != 1:
+            raise NotImplementedError("Fcomb kernels: no_convs_fcomb >= 2, num_filters[0] <= 64, num_classes = 1 "
+                                      "(every reference script: 3, 64, 1; the reference's default constructor: 4, 32, 1)")
         f0 = self.num_filters[0]
         mods = [nn.Conv2d(f0 + latent_dim, f0, kernel_size=1), nn.ReLU(inplace=True)]
         for _ in range(no_convs_fcomb - 2):
@@ -144,27 +149,70 @@ class Fcomb(nn.Module):
         self.layers.apply(init)
         self.last_layer.apply(init)
 
+    def _padded(self, conv, feature_first=False):
+        """(weight, bias) of a 1x1 layer zero-padded to the kernels' 64-wide hidden layer (no-op for f0 = 64).  Layer 0's
+        input is cat(features, z) (:212): the feature columns are padded to 64, the z columns follow."""
+        import torch.nn.functional as F
+        f0 = self.num_filters[0]
+        w, b = conv.weight, conv.bias
+        if f0 == 64:
+            return w, b
+        if feature_first:
+            w = torch.cat((F.pad(w[:, :f0], (0, 0, 0, 0, 0, 64 - f0)), w[:, f0:]), 1)
+        elif w.shape[1] == f0:
+            w = F.pad(w, (0, 0, 0, 0, 0, 64 - f0))
+        if w.shape[0] == f0:
+            w, b = F.pad(w, (0, 0, 0, 0, 0, 0, 0, 64 - f0)), F.pad(b, (0, 64 - f0))
+        return w, b
+
     def weights(self):
+        """(w1, b1, w2, b2, w3, b3) of the fused kernels (no_convs_fcomb = 3)."""
         l0, l1, ll = self.layers[0], self.layers[2], self.last_layer
-        return (l0.weight, l0.bias, l1.weight, l1.bias, ll.weight, ll.bias)
+        return (*self._padded(l0, True), *self._padded(l1), *self._padded(ll))
 
     def forward_nhwc(self, feat, z, **want):
-        """feat (B,H,W,64) bf16, z (S,B,L) -> dict from ops.fcomb_mc_consensus."""
+        """feat (B,H,W,64) 16-bit (channels beyond num_filters[0] are zero), z (S,B,L) -> dict of outputs."""
         from ..autograd_ops import _needs_grad
+        if self.no_convs_fcomb != 3:
+            return self._forward_deep(feat, z, **want)
         w = self.weights()
         if _needs_grad(feat, z, *w):
             from ..training import fcomb_train
             return fcomb_train(feat, z, w, **want)
         return ops.fcomb_mc_consensus(feat, z, *[t.detach() for t in w], **want)
 
+    def _forward_deep(self, feat, z, **want):
+        """no_convs_fcomb != 3 (the reference's default constructor builds 4): general-depth fp32 kernel, forward only."""
+        from ..autograd_ops import _needs_grad
+        convs = [m for m in self.layers if isinstance(m, nn.Conv2d)]
+        if _needs_grad(feat, z, *[p for c in convs for p in (c.weight, c.bias)], self.last_layer.weight):
+            raise NotImplementedError("training through Fcomb is implemented for no_convs_fcomb=3 (every reference "
+                                      "script); other depths run forward / Monte-Carlo inference only")
+        w1, b1 = self._padded(convs[0], True)
+        mids = [self._padded(c) for c in convs[1:]]
+        wmid = torch.stack([w.reshape(64, 64) for w, _ in mids]).contiguous() if mids else None
+        bmid = torch.stack([b for _, b in mids]).contiguous() if mids else None
+        w3, b3 = self._padded(self.last_layer)
+        return ops.fcomb_mc_consensus_deep(feat, z, w1.detach(), b1.detach(), wmid, bmid, w3.detach(), b3.detach(),
+                                           **want)
+
     def forward(self, feature_map, z):
-        out = self.forward_nhwc(as_nhwc(feature_map), z[None], want_mean=False, want_weight=False, want_logits=True)
+        from .unet_blocks import pad_channels
+        out = self.forward_nhwc(pad_channels(as_nhwc(feature_map)), z[None], want_mean=False, want_weight=False,
+                                want_logits=True)
         return out["logits"][0]
 
 
 class ProbabilisticUnet(nn.Module):
     """Probabilistic U-Net (probabilistic_unet.py:217-371): same constructor defaults, stateful
-    forward -> sample / reconstruct / kl_divergence / elbo protocol and cached attributes."""
+    forward -> sample / reconstruct / kl_divergence / elbo protocol and cached attributes.
+
+    Supported architectures: `num_filters` of any widths with num_filters[0] <= 64 and all <= 512 (widths that are not
+    multiples of 64 run zero-padded to the 64-channel tiles of the tensor-core kernels: same results, wasted lanes),
+    `num_classes = input_channels = 1`.  `no_convs_fcomb = 3` (every reference script) runs on the fused tensor-core
+    kernels, forward and backward; any other depth >= 2 -- the reference's own default is 4 -- runs forward / sampling /
+    Monte-Carlo consensus on a plain fp32 kernel and raises NotImplementedError when a gradient through Fcomb is
+    requested.  So `ProbabilisticUnet()` with the reference's defaults constructs and predicts; it does not train."""
 
     def __init__(self, input_channels=1, num_classes=1, num_filters=[32, 64, 128, 192], latent_dim=6,
                  no_convs_fcomb=4, beta=10.0, consensus_masking=False, rl_swap=False):
@@ -200,14 +248,20 @@ class ProbabilisticUnet(nn.Module):
             self.posterior_latent_space = self.posterior.forward(patch, segm)
         self.prior_latent_space = self.prior.forward(patch)
         self._feat_nhwc = self.unet.forward_nhwc(patch.float().contiguous())
-        self.unet_features = as_nchw(self._feat_nhwc)
+        # logical (B, num_filters[0], H, W) view (channels-last strides; channels padded to 64 inside)
+        self.unet_features = as_nchw(self._feat_nhwc)[:, :self.num_filters[0]]
 
     def sample(self, testing=False):
         """One prior draw (rsample, or sample() when testing) decoded by Fcomb -> logits (B,1,H,W) (:295-309).
         The draw uses the same torch.distributions calls as the reference, hence the same RNG stream."""
         z_prior = self.prior_latent_space.sample() if testing else self.prior_latent_space.rsample()
         self.z_prior_sample = z_prior
-        return self.fcomb.forward(self.unet_features, z_prior)
+        return self._decode(z_prior)
+
+    def _decode(self, z):
+        """fcomb(unet_features, z) on the cached NHWC feature map (no layout round trip)."""
+        out = self.fcomb.forward_nhwc(self._feat_nhwc, z[None], want_mean=False, want_weight=False, want_logits=True)
+        return out["logits"][0]
 
     def reconstruct(self, use_posterior_mean=False, calculate_posterior=False, z_posterior=None):
         """Decode a posterior sample (:311-322)."""
@@ -215,7 +269,7 @@ class ProbabilisticUnet(nn.Module):
             z_posterior = self.posterior_latent_space.loc  # AttributeError on Independent, as in the reference
         elif calculate_posterior:
             z_posterior = self.posterior_latent_space.rsample()
-        return self.fcomb.forward(self.unet_features, z_posterior)
+        return self._decode(z_posterior)
 
     def kl_divergence(self, analytic=True, calculate_posterior=False, z_posterior=None):
         """KL(posterior || prior) per batch element (:324-339)."""

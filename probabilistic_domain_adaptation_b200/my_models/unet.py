@@ -23,8 +23,9 @@ class Unet(nn.Module):
                                       "(probabilistic_unet.py:256); the plain-UNet head is out of scope")
         if input_channels != 1:
             raise NotImplementedError("input_channels must be 1 (every reference script)")
-        if any(f % 64 for f in self.num_filters):
-            raise NotImplementedError("num_filters must be multiples of 64 for the tcgen05 conv tiles")
+        if self.num_filters[0] > 64 or max(self.num_filters) > 512 or min(self.num_filters) < 1:
+            raise NotImplementedError("num_filters[0] <= 64 (the fused Fcomb kernels are 64 wide) and every width <= 512; "
+                                      "widths that are not multiples of 64 run zero-padded to the 64-channel tiles")
 
         self.contracting_path = nn.ModuleList()
         prev = input_channels
@@ -53,12 +54,14 @@ class Unet(nn.Module):
                 x = pooled
             else:
                 x = full
+        nf = self.num_filters
         for i, up in enumerate(self.upsampling_path):
-            x = up.forward_nhwc(x, skips[-i - 1])
+            lvl = nlev - 2 - i  # level of the bridge: real channels (nf[lvl + 1] from below, nf[lvl] from the skip)
+            x = up.forward_nhwc(x, skips[-i - 1], seg_real=(nf[lvl + 1], nf[lvl]))
         return x
 
     def forward(self, x, val):
-        feat = as_nchw(self.forward_nhwc(x))
+        feat = as_nchw(self.forward_nhwc(x))[:, :self.num_filters[0]]
         if val:
             self.activation_maps.append(feat)
         return feat

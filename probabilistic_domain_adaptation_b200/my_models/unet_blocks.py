@@ -7,6 +7,7 @@ goes through libpda_b200 (tcgen05 implicit-GEMM conv, fused bias/ReLU/pool, bili
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import ops
 from ..autograd_ops import conv3x3_first_op, conv3x3_op, avgpool2_op, upsample2x_op
@@ -23,9 +24,73 @@ def as_nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
+def pad_channels(x_nhwc):
+    """Zero-pads the channel dimension of an NHWC tensor to a multiple of 64 (no-op for the reference scripts' widths)."""
+    c = x_nhwc.shape[3]
+    return x_nhwc if c == pad64(c) else F.pad(x_nhwc, (0, pad64(c) - c)).contiguous()
+
+
 def as_nchw(x_nhwc):
     """(B,H,W,C) bf16 -> logical (B,C,H,W) view (channels_last strides, no copy)."""
     return x_nhwc.permute(0, 3, 1, 2)
+
+
+def pad64(c):
+    """Channel count the kernels run a width of c at: the next of 64 / 128 / 256 / 512 (the conv tiles need multiples of
+    64, the NHWC elementwise kernels address 16-byte channel chunks with shifts: powers of two)."""
+    for w in (64, 128, 256, 512):
+        if c <= w:
+            return w
+    raise NotImplementedError(f"channel width {c} > 512")
+
+
+class ConvView:
+    """Stands in for an nn.Conv2d container whose channel counts are not multiples of 64 (the reference's default
+    `num_filters=[32, 64, 128, 192]`): `weight` / `bias` are the parameters zero-padded to the 64-channel tiles of the
+    tensor-core kernels, laid out segment by segment like the (padded) activations they meet.  The padding is ordinary
+    autograd-aware tensor arithmetic, so gradients reach the real parameters through it.  Padded output channels carry
+    relu(0) = 0 and meet zero weights in the next layer: the real channels are exactly those of the unpadded net."""
+
+    def __init__(self, conv, segs_real, segs_pad, cout_pad):
+        w, b = conv.weight, conv.bias
+        parts, off = [], 0
+        for r, pd in zip(segs_real, segs_pad):
+            seg = w[:, off:off + r]
+            parts.append(F.pad(seg, (0, 0, 0, 0, 0, pd - r)) if pd != r else seg)
+            off += r
+        assert off == w.shape[1], (off, w.shape)
+        w = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+        extra = cout_pad - w.shape[0]
+        self.weight = F.pad(w, (0, 0, 0, 0, 0, 0, 0, extra)) if extra else w
+        self.bias = F.pad(b, (0, extra)) if extra else b
+        self.in_channels, self.out_channels = self.weight.shape[1], cout_pad
+        self.kernel_size = conv.kernel_size
+
+
+def effective_convs(convs, x, src1, first_input, seg_real=None):
+    """The conv containers the kernels see: `convs` themselves when every channel count is a multiple of 64 (all
+    reference scripts), ConvView proxies with zero-padded parameters otherwise."""
+    if all(c.out_channels == pad64(c.out_channels) for c in convs) \
+            and (first_input is not None or convs[0].in_channels % 64 == 0) \
+            and (x is None or x.shape[3] == (convs[0].in_channels - (0 if src1 is None else src1.shape[3]))):
+        return convs
+    out, prev_real, prev_pad = [], None, None
+    for j, c in enumerate(convs):
+        cout_pad = pad64(c.out_channels)
+        if j == 0 and first_input is not None:
+            segs_real = segs_pad = (c.in_channels,)
+        elif j == 0:
+            segs_pad = (x.shape[3],) + (() if src1 is None else (src1.shape[3],))
+            if seg_real is None:
+                seg_real = (c.in_channels,) if src1 is None else None
+            if seg_real is None:
+                raise RuntimeError("channel-padded concat needs the real channel counts of its two segments")
+            segs_real = tuple(seg_real)
+        else:
+            segs_real, segs_pad = (prev_real,), (prev_pad,)
+        out.append(ConvView(c, segs_real, segs_pad, cout_pad))
+        prev_real, prev_pad = c.out_channels, cout_pad
+    return out
 
 
 def _check_spatial(h, w, levels):
@@ -37,14 +102,16 @@ def _check_spatial(h, w, levels):
         raise RuntimeError(f"height {h} is not divisible by {div}: Sizes of tensors must match except in dimension 1")
 
 
-def run_conv_stack(convs, x, first_input=None, pool_last=False, keep_full=True, src1=None):
+def run_conv_stack(convs, x, first_input=None, pool_last=False, keep_full=True, src1=None, seg_real=None):
     """Runs conv3x3+ReLU for every nn.Conv2d container in `convs`.
 
-    x: NHWC bf16 input of the first conv, or None when `first_input` = (x0, x1) fp32 planes feed a
-    cin<=2 first layer.  src1: optional second K-segment (channel concat) of the first conv.
-    Returns (full, pooled) of the last conv.
+    x: NHWC 16-bit input of the first conv, or None when `first_input` = (x0, x1) fp32 planes feed a
+    cin<=2 first layer.  src1: optional second K-segment (channel concat) of the first conv; seg_real: the real
+    (unpadded) channel counts of (x, src1) when the net's widths are not multiples of 64.
+    Returns (full, pooled) of the last conv (channel counts padded to multiples of 64).
     """
     from ..autograd_ops import _needs_grad
+    convs = effective_convs(convs, x, src1, first_input, seg_real)
     plist = [t for c in convs for t in (c.weight, c.bias)]
     if _needs_grad(x, src1, *plist):
         # training: the whole block is one autograd node (cross-layer fusion in its backward)
@@ -93,12 +160,12 @@ class DownConvBlock(nn.Module):
             if self.pool:
                 raise NotImplementedError("pooled block with <=2 input channels does not occur in the reference")
             full, _ = run_conv_stack(self.convs(), None, first_input=(planes[:, 0:1].contiguous(), x1))
-            return as_nchw(full)
-        x = as_nhwc(patch)
+            return as_nchw(full)[:, :self.convs()[-1].out_channels]
+        x = pad_channels(as_nhwc(patch))
         if self.pool:
             x = avgpool2_op(x)
-        full, _ = run_conv_stack(self.convs(), x)
-        return as_nchw(full)
+        full, _ = run_conv_stack(self.convs(), x, seg_real=(patch.shape[1],))
+        return as_nchw(full)[:, :self.convs()[-1].out_channels]
 
 
 class UpConvBlock(nn.Module):
@@ -113,13 +180,15 @@ class UpConvBlock(nn.Module):
         self.bilinear = bilinear
         self.conv_block = DownConvBlock(input_dim, output_dim, initializers, padding, pool=False)
 
-    def forward_nhwc(self, x, bridge):
+    def forward_nhwc(self, x, bridge, seg_real=None):
         up = upsample2x_op(x)
         assert up.shape[2] == bridge.shape[2]  # widths (unet_blocks.py:55)
         if up.shape[1] != bridge.shape[1]:
             raise RuntimeError("Sizes of tensors must match except in dimension 1")
-        full, _ = run_conv_stack(self.conv_block.convs(), up, src1=bridge)
+        full, _ = run_conv_stack(self.conv_block.convs(), up, src1=bridge, seg_real=seg_real)
         return full
 
     def forward(self, x, bridge):
-        return as_nchw(self.forward_nhwc(as_nhwc(x), as_nhwc(bridge)))
+        seg_real = (x.shape[1], bridge.shape[1])
+        out = self.forward_nhwc(pad_channels(as_nhwc(x)), pad_channels(as_nhwc(bridge)), seg_real=seg_real)
+        return as_nchw(out)[:, :self.conv_block.convs()[-1].out_channels]

@@ -280,6 +280,31 @@ def fcomb_mc_consensus(feat, z, w1, b1, w2, b2, w3, b3, upper=0.9, lower=0.1, wa
     return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs, "range_flag": scratch}
 
 
+def fcomb_mc_consensus_deep(feat, z, w1, b1, wmid, bmid, w3, b3, upper=0.9, lower=0.1, want_mean=True, want_weight=True,
+                            want_mask=False, want_logits=False, want_probs=False):
+    """General-depth Fcomb (wmid (n_mid, 64, 64) or None): plain fp32 kernel, same outputs as fcomb_mc_consensus."""
+    _need_cuda(feat, z, w1)
+    lib = _lib.load()
+    B, H, W, C = feat.shape
+    S, Bz, L = z.shape
+    assert Bz == B and C == 64 and w1.shape[1] == C + L and feat.is_contiguous()
+    dev = feat.device
+    P = H * W
+    mean = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_mean else None
+    weight = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if want_weight else None
+    mask = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev) if want_mask else None
+    logits = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    probs = torch.empty((S, B, 1, H, W), dtype=torch.float32, device=dev) if want_probs else None
+    z = z.contiguous().float()
+    n_mid = 0 if wmid is None else wmid.shape[0]
+    w1, b1, w3, b3 = (t.contiguous().float() for t in (w1, b1, w3, b3))
+    _lib.check(lib.pda_fcomb_mc_consensus_deep(feat.data_ptr(), z.data_ptr(), w1.data_ptr(), b1.data_ptr(), _ptr(wmid),
+                                               _ptr(bmid), n_mid, w3.data_ptr(), b3.data_ptr(), B, P, S, L, float(upper),
+                                               float(lower), _ptr(mean), _ptr(weight), _ptr(mask), _ptr(logits),
+                                               _ptr(probs), _is_f16(feat), _stream()), "fcomb_mc_consensus_deep")
+    return {"mean": mean, "weight": weight, "mask": mask, "logits": logits, "probs": probs, "range_flag": None}
+
+
 _EMA_CHUNK = 16384  # elements per 256-thread block of the multi-tensor kernels (<= 65536)
 
 

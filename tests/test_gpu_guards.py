@@ -145,13 +145,16 @@ def test_wgrad_writes_stay_inside(B, H, W, c0, c1, cout):
                                        dw.t.data_ptr(), db.t.data_ptr(), B, H, W, cout, 0, 0, ops._stream()), "wgrad")
     torch.cuda.synchronize()
     assert scratch.intact() and dw.intact() and db.intact()
-    assert not bool(scratch.t.any()), "the weight-gradient scratch must be all zero again after the launch"
-    # second launch on the self-cleaned scratch (scratch_is_zero = 1): same result
-    dw2, db2 = torch.empty_like(want_dw), torch.empty_like(want_db)
-    L.check(lib.pda_conv3x3_wgrad_bf16(x.data_ptr(), c0, ops._ptr(s1), c1, dz.data_ptr(), scratch.t.data_ptr(),
-                                       dw2.data_ptr(), db2.data_ptr(), B, H, W, cout, 0, 1, ops._stream()), "wgrad")
-    torch.cuda.synchronize()
-    assert torch.allclose(dw2, want_dw, rtol=1e-4, atol=1e-4) and not bool(scratch.t.any())
+    # scratch_is_zero = 1: the caller guarantees a zeroed scratch and the call leaves it zeroed again (twice in a row)
+    scratch.t.zero_()
+    for _ in range(2):
+        dw2, db2 = torch.empty_like(want_dw), torch.empty_like(want_db)
+        L.check(lib.pda_conv3x3_wgrad_bf16(x.data_ptr(), c0, ops._ptr(s1), c1, dz.data_ptr(), scratch.t.data_ptr(),
+                                           dw2.data_ptr(), db2.data_ptr(), B, H, W, cout, 0, 1, ops._stream()), "wgrad")
+        torch.cuda.synchronize()
+        assert torch.allclose(dw2, want_dw, rtol=1e-4, atol=1e-4) and torch.allclose(db2, want_db, rtol=1e-4, atol=1e-3)
+        assert not bool(scratch.t.any()), "the weight-gradient scratch must be all zero again after the launch"
+    assert scratch.intact()
     # the flush uses fp32 atomics: equal up to summation order
     assert torch.allclose(dw.t, want_dw, rtol=1e-4, atol=1e-4) and torch.allclose(db.t, want_db, rtol=1e-4, atol=1e-3)
 
