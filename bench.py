@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--train-size", type=int, default=512)
     ap.add_argument("--bucket-mb", type=float, default=25.0, help="gradient all-reduce bucket size (training legs)")
     ap.add_argument("--no-graph", action="store_true", help="training legs: time the Python-launched step only")
-    ap.add_argument("--reserve-sms", type=int, default=4,
+    ap.add_argument("--reserve-sms", type=int, default=0,
                     help="N > 1: SMs the persistent kernels leave to NCCL so that the all-reduce overlaps the backward")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="wire format of the gradient all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the S sweep and the source-training step")

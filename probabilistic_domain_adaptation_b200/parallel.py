@@ -45,13 +45,15 @@ class GradAllReducer:
     all buckets and rebinds p.grad to its averaged view inside the flat buffer.  Call `finish()` after backward and
     before optimizer.step().
 
-    reserve_sms: with more than one rank, the persistent tensor-core kernels leave this many SMs free
-    (`pda_set_sm_budget`) so that NCCL's CTAs run NEXT TO the backward kernels -- those otherwise occupy all 148 SMs with
-    one ~200 KB CTA each and the all-reduce only progresses between kernels (round 1: +0.57 ms exposed at 8 GPUs).
+    reserve_sms (default 0): with more than one rank, the persistent tensor-core kernels leave this many SMs free
+    (`pda_set_sm_budget`) so that NCCL's CTAs can run NEXT TO the backward kernels -- those otherwise occupy all 148 SMs
+    with one ~200 KB CTA each and the all-reduce only progresses between kernels (round 1: +0.57 ms exposed at 8 GPUs).
     comm_dtype: torch.bfloat16 halves the bytes on the wire (gradients are averaged in bf16, then widened back into the
-    fp32 buckets the optimizer reads); default fp32 = exact averaging."""
+    fp32 buckets the optimizer reads); default fp32 = exact averaging.
+    Measured at 2 GPUs (profiles/r02_2gpu_allreduce_options.md): neither option changes the step time (15.22 ms with
+    4 SMs reserved, 15.23 ms without, 15.28 ms with bf16 on the wire), so both stay off by default."""
 
-    def __init__(self, module, bucket_mb=25.0, process_group=None, reserve_sms=4, comm_dtype=None):
+    def __init__(self, module, bucket_mb=25.0, process_group=None, reserve_sms=0, comm_dtype=None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.comm_dtype = None if comm_dtype in (None, torch.float32) else comm_dtype
