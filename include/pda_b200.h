@@ -72,6 +72,15 @@ int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const voi
                    void* out, void* out_pool, const void* relu_mask, int B, int H, int W, int cout, int relu,
                    int bn_tile, int act_f16, int* range_flag, void* stream);
 
+/* The first conv of an UpConvBlock (unet_blocks.py:51-57) with the bilinear x2 up-sampling FUSED: input = channel concat of
+ * F.interpolate(up_src, scale_factor=2, mode='bilinear', align_corners=True) (up_src NHWC [B][H/2][W/2][c0], never
+ * materialised at full resolution: the conv kernel's epilogue warps interpolate the operand slabs straight into shared
+ * memory) and src1 [B][H][W][c1].  Same outputs, bit for bit, as pda_upsample2x_bilinear followed by pda_conv3x3_tc.
+ * H, W even; CTA-pair kernel only (PDA_ERR_SHAPE for images of a single pixel tile). */
+int pda_conv3x3_up_tc(const void* up_src, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                      void* out, void* out_pool, int B, int H, int W, int cout, int relu, int act_f16, int* range_flag,
+                      void* stream);
+
 /* Kernel selection for pda_conv3x3_tc: 0 = one CTA per 128-pixel tile (csrc/conv3x3_tc.cu), 1 = CTA pairs issuing
  * M = 256 tcgen05.mma.cta_group::2 with the weight tile split across the pair (csrc/conv3x3_tc2.cu).  mode < 0 only
  * queries.  Returns the previous mode.  Results are bit-identical between the two. */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "pda_pack_conv3x3_weights_multi": [_P, _I, _P],
     "pda_conv3x3_first": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pda_conv3x3_tc": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "pda_conv3x3_up_tc": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "pda_set_conv_pair": [_I],
     "pda_set_sm_budget": [_I],
     "pda_conv3x3_bf16_simt": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -27,12 +27,14 @@ struct ConvArgs {
                               // of the layer that produced this conv's input, fused into the dgrad epilogue)
   int act_f16;                // activations / weights / outputs are fp16 (no-grad path) instead of bf16
   int wide, wide_base_offset; // CTA-pair kernel: one 16-px slab per chunk (csrc/conv3x3_tc2.cu)
+  const void* up_src;         // CTA-pair kernel: K segment 0 = bilinear x2 of this [B][H/2][W/2][c0] tensor, or nullptr
   int* range_flag;            // fp16 only, may be nullptr: set to 1 when an output exceeds the fp16 range (the store
                               // saturates at +-65504)
 };
 
 void* get_encode_tiled();  // cuTensorMapEncodeTiled driver entry point (or nullptr)
-int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h, int box_c);
+int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h, int box_c,
+                        int swizzle128 = 1);
 int make_mat_tensor_map(CUtensorMap* tm, const void* ptr, long long inner, long long outer, int box_inner,
                         int box_outer);
 
@@ -56,7 +58,7 @@ int sm_budget(int set);       // csrc/conv3x3_tc.cu
 // CTA-pair (cta_group::2) variant, csrc/conv3x3_tc2.cu
 int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                 void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
-                int act_f16, int* range_flag, cudaStream_t stream);
+                int act_f16, int* range_flag, cudaStream_t stream, const void* up_src = nullptr);
 
 // log2(C / 8) for C = 8 * 2^k (the NHWC kernels address 16-byte channel chunks with shifts), else -1
 static inline int c8_shift(int C) {

@@ -394,7 +394,7 @@ static EncodeTiledFn get_encode_fn() {
 void* get_encode_tiled() { return reinterpret_cast<void*>(get_encode_fn()); }
 
 int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h,
-                        int box_c) {
+                        int box_c, int swizzle128) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PDA_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -402,7 +402,8 @@ int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, i
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PDA_OK : PDA_ERR_TENSORMAP;
 }
@@ -501,6 +502,7 @@ int conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const void* w
   a.mask = static_cast<const __nv_bfloat16*>(mask);
   a.act_f16 = act_f16;
   a.wide = a.wide_base_offset = 0;
+  a.up_src = nullptr;
   a.range_flag = act_f16 ? range_flag : nullptr;
   CUtensorMap tA0, tA1, tB;
   int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, 8, a.tile_h + 2, 64);

@@ -25,9 +25,19 @@
 #ifndef PDA_CONV_WIDE_DEFAULT
 #define PDA_CONV_WIDE_DEFAULT 0
 #endif
+#ifndef PDA_UPS_A_STAGES64
+#define PDA_UPS_A_STAGES64 2
+#endif
+// pixels per slab row of the fused up-sampling mode (the taps read 10; 16 = the WIDE layout)
+#ifndef PDA_UPS_ROW_PX
+#define PDA_UPS_ROW_PX 10
+#endif
 
 namespace pda {
 
+__device__ __forceinline__ void named_bar2(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -94,20 +104,32 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // traffic per chunk.  Bit-identical results; measured within +-3 % of the 8-pixel slabs on every layer
 // (profiles/r02_conv_wide_slab.md), so the fill traffic is not what limits these kernels: kept as an option
 // (PDA_CONV_WIDE=1), not the default.
-template <int BN, int MT, bool RES, bool WIDE = false>
+template <int BN, int MT, bool RES, bool WIDE = false, bool UPS = false>
 struct Conv2Cfg {
   static constexpr int SLAB_ROWS = 16 * MT + 2;
-  static constexpr int ROW_BYTES = WIDE ? 2048 : 1024; // one slab row: 16 or 8 px x 128 B
-  static constexpr int A_BYTES = SLAB_ROWS * ROW_BYTES;
+  // one slab row: 16 or 8 px x 128 B.  UPS: PDA_UPS_ROW_PX pixels -- the pitch need not be a whole number of 1024-byte
+  // swizzle atoms because both TMA and the MMA unit derive the swizzle from shared-memory ADDRESS bits
+  static constexpr int ROW_BYTES = UPS ? PDA_UPS_ROW_PX * 128 : (WIDE ? 2048 : 1024);
+  // UPS: the low-resolution patch one slab interpolates from (rows x 7 px x 64 channels, unswizzled), double-buffered
+  static constexpr int PATCH_ROWS = 8 * MT + 3;
+  static constexpr int PATCH_PX = 7;
+  static constexpr int PATCH_BYTES = PATCH_ROWS * PATCH_PX * 128;
+  static constexpr int P_STAGES = UPS ? 2 : 0;
+  static constexpr int A_TX = SLAB_ROWS * ROW_BYTES;             // bytes one TMA slab load delivers
+  static constexpr int A_BYTES = (A_TX + 1023) & ~1023;          // stage pitch: whole swizzle atoms
   static constexpr int BH = BN / 2;                    // weight rows held by one CTA of the pair
   static constexpr int B_BYTES = BH * 128;             // this CTA's half of one (tap, chunk) weight tile
-  static constexpr int A_STAGES = WIDE ? (MT == 2 ? 2 : 3) : 4;
-  static constexpr int B_STAGES = RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : 8) : 6));
+  // (UPS, N = 64: a third slab stage -- PDA_UPS_A_STAGES64 = 3, paid for with two of the eight weight stages -- measured
+  // no faster: that layer is bound by the shared-memory port, which the software producer's reads and writes share)
+  static constexpr int A_STAGES = WIDE ? (MT == 2 ? ((UPS && BN == 64) ? PDA_UPS_A_STAGES64 : 2) : 3) : 4;
+  static constexpr int B_STAGES =
+      RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : ((UPS && PDA_UPS_A_STAGES64 == 3) ? 6 : 8)) : 6));
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
   static constexpr int STG_OFF = B_OFF + B_STAGES * B_BYTES;   // 8 epilogue warps x 4 KB output staging
-  static constexpr int BAR_OFF = STG_OFF + 8 * 4096;
-  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int P_OFF = STG_OFF + 8 * 4096;
+  static constexpr int BAR_OFF = P_OFF + P_STAGES * PATCH_BYTES;
+  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4 + P_STAGES;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BIAS_OFF = SLOT_OFF + 16;
   static constexpr int MAX_COUT = 512;
@@ -117,16 +139,32 @@ struct Conv2Cfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
   static_assert(B_BYTES % 1024 == 0, "weight half-tile must be whole swizzle atoms");
+  static_assert(A_BYTES % 1024 == 0 && PATCH_BYTES % 128 == 0, "stage alignment");
 };
 
 constexpr int CONV2_THREADS = 320;
 
-template <int BN, int MT, bool RES, bool F16, bool WIDE>
+// UPS: K segment 0 is the bilinear x2 up-sampling (align_corners = True: unet_blocks.py:51) of a LOW-RESOLUTION tensor
+// p.up_src [B][H/2][W/2][c0]; it is never materialised.  TMA cannot interpolate, so the eight epilogue warps -- idle for
+// ~90 % of a unit -- are the producer of those chunks:
+//   * TMA stages the low-resolution patch a slab interpolates from ((8 MT + 3) rows x 7 px x 64 channels, unswizzled) in
+//     a two-deep ring, issued two chunks ahead by the producer's thread 0 (tmA0 is the patch map in this mode)
+//   * 240 of the 256 threads own one (pixel column, 8-channel group) of the slab and a run of consecutive rows; they blend
+//     in fp32 in the order upsample2x_kernel uses (bit-identical to up-sampling first), write the slab swizzled the way
+//     TMA would have written it, fence it for the async proxy, and thread 0 arrives on the stage's full barrier (count 2
+//     in this mode: one arrival per CTA for every chunk, software-produced or TMA-loaded)
+//   * slab rows are PDA_UPS_ROW_PX = 10 pixels (the three kx taps read pixels kx .. kx + 7), not the WIDE layout's 16
+//   * per unit they first produce the unit's segment-0 chunks, then drain the PREVIOUS unit's accumulators
+//   * a party that skips a stage use (the TMA warp skips the produced chunks, the producer the loaded ones) still waits
+//     on the stage's empty barrier for it: a parity wait cannot tell phase n from phase n + 2
+// Measured at the 4 x 1024^2 up-path shapes (tools/conv_up_bench.py): 0.66 / 0.76 / 1.10 ms (upsample2x + conv) ->
+// 0.57 / 0.60 / 0.88 ms.
+template <int BN, int MT, bool RES, bool F16, bool WIDE, bool UPS>
 __global__ void __launch_bounds__(CONV2_THREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                    const ConvArgs p) {
-  using L = Conv2Cfg<BN, MT, RES, WIDE>;
+  using L = Conv2Cfg<BN, MT, RES, WIDE, UPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -137,6 +175,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + L::B_STAGES + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 2 + s); };
+  auto p_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 4 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::SLOT_OFF);
   float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFF);
 
@@ -160,7 +199,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     // flip.  (A remote arrive of the peer's producer per stage -- mbarrier.arrive.release.cluster = MEMBAR + ERRBAR --
     // serialised its loop to one stage per ~1000 cycles: measured, the whole kernel ran at half speed.)
     for (int s = 0; s < L::A_STAGES; ++s) {
-      mbar_init(a_full(s), 1);
+      mbar_init(a_full(s), UPS ? 2 : 1);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < L::B_STAGES; ++s) {
@@ -171,6 +210,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), 16);  // one arrive per epilogue warp of BOTH CTAs (leader's barrier)
     }
+    for (int s = 0; s < L::P_STAGES; ++s) mbar_init(p_full(s), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -226,11 +266,17 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (int ch = 0; ch < chunks; ++ch) {
         const int c = ch << 6;
         for (int kx = 0; kx < 3; ++kx) {
-          if (!WIDE || kx == 0) {
+          if ((!WIDE || kx == 0) && UPS && c < p.c0) {
+            // produced by the epilogue warps.  The wait keeps this warp within one phase of the stage's barrier: a
+            // parity wait cannot tell phase n from phase n + 2, so a party that skips uses must still observe them.
+            mbar_wait(a_empty(as), aph ^ 1);
+            if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+          } else if (!WIDE || kx == 0) {
             mbar_wait(a_empty(as), aph ^ 1);
             if (leader_lane) {
               const uint32_t bar = mapa_shared(a_full(as), 0);
-              if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_BYTES);
+              if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_TX);
+              else if (UPS) mbar_arrive_cluster(bar);  // count-2 barrier in this mode
               const uint32_t dst = sbase + L::A_OFF + as * L::A_BYTES;
               const int xs = WIDE ? x0 - 1 : x0 + kx - 1;
               if (c < p.c0)
@@ -336,8 +382,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     uint8_t* stage = smem + L::STG_OFF + ew * 4096;
     const uint32_t stage_u32 = sbase + L::STG_OFF + ew * 4096;
     const int sw = lane & 7;
-    uint32_t it = 0;
-    for (int u = pair; u < units; u += npairs, ++it) {
+    auto drain = [&](int u, uint32_t it) {
       int nb, img, ty, tx;
       bool ghost;
       unit_tile(u, nb, img, ty, tx, ghost);
@@ -451,6 +496,142 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           }
         }
       }
+    };
+    if (!UPS) {
+      uint32_t it = 0;
+      for (int u = pair; u < units; u += npairs, ++it) drain(u, it);
+    } else {
+      // ---------------------------------------------------------- software producer of the up-sampled K segment
+      const int ptid = threadIdx.x - 64;                  // 0 .. 255
+      const int h = p.H >> 1, w = p.W >> 1;               // low-resolution source
+      const float rh = (p.H > 1) ? (float)(h - 1) / (float)(p.H - 1) : 0.f;
+      const float rw = (p.W > 1) ? (float)(w - 1) / (float)(p.W - 1) : 0.f;
+      const int nchunk0 = p.c0 >> 6;
+      // The low-resolution patch a slab interpolates from is staged in shared memory by TMA (tmA0: unswizzled boxes of
+      // PATCH_ROWS x 7 px x 64 channels), two software-produced chunks ahead: gathering straight from global memory left
+      // this producer latency-bound (measured: the 192 -> 64 layer at 1024^2 ran at 58 % of the unfused conv's rate).
+      // Thread ptid 0 issues the loads: it knows a patch buffer is free when all 256 threads have passed the named barrier
+      // that ends a chunk, so the ring needs no empty barriers.
+      auto issue_patch = [&](uint32_t j) {                // j = index in this CTA's sequence of software-produced chunks
+        const uint32_t it2 = j / (uint32_t)nchunk0;
+        const int ch2 = (int)(j - it2 * (uint32_t)nchunk0);
+        const long long u2 = (long long)pair + (long long)it2 * npairs;
+        if (u2 >= units) return;
+        int nb, img, ty, tx;
+        bool ghost;
+        unit_tile((int)u2, nb, img, ty, tx, ghost);
+        const int xa = max(tx * 8 - 1, 0), ya = max(ty * (16 * MT) - 1, 0);
+        const uint32_t ps = j & 1;
+        mbar_expect_tx(p_full(ps), L::PATCH_BYTES);
+        tma_load_4d(sbase + L::P_OFF + ps * L::PATCH_BYTES, &tmA0, p_full(ps), ch2 << 6, (int)(rw * (float)xa),
+                    (int)(rh * (float)ya), img);
+      };
+      if (ptid == 0) {
+        issue_patch(0);
+        issue_patch(1);
+      }
+      constexpr int RSEG = (L::SLAB_ROWS + 2) / 3;         // slab rows per thread: 3 row segments x 80 columns = 240 threads
+      const int col_seg = ptid / 80, col_rem = ptid - col_seg * 80;
+      const int col_px = col_rem >> 3, col_g = col_rem & 7;
+      const int col_rows_begin = col_seg * RSEG;          // threads 240..255: past the last row, no items
+      int as = 0;
+      uint32_t aph = 0;
+      uint32_t it = 0, j = 0;
+      int prev_u = -1;
+      for (int u = pair; u < units; u += npairs, ++it) {
+        int nb, img, ty, tx;
+        bool ghost;
+        unit_tile(u, nb, img, ty, tx, ghost);
+        const int x0 = tx * 8 - 1, y0 = ty * (16 * MT) - 1;   // image coordinates of slab (row 0, px 0)
+        const int x_lo = (int)(rw * (float)max(x0, 0)), y_lo = (int)(rh * (float)max(y0, 0));  // patch origin
+        // this thread's pixel column of the slab
+        const int col_x = x0 + col_px;
+        const bool x_in = col_x >= 0 && col_x < p.W;
+        const float sx = rw * (float)col_x;
+        const int x1 = x_in ? (int)sx : 0;
+        const float lx1 = sx - (float)x1, lx0 = 1.f - lx1;
+        const int x_step = (x1 < w - 1) ? 128 : 0;
+        const int col_off = (min(max(x1 - x_lo, 0), L::PATCH_PX - 2) << 7) + (col_g << 4);
+        for (int ch = 0; ch < nchunk0; ++ch, ++j) {
+          const uint32_t ps = j & 1;
+          mbar_wait(p_full(ps), (j >> 1) & 1);
+          mbar_wait(a_empty(as), aph ^ 1);
+          uint8_t* slab = smem + L::A_OFF + as * L::A_BYTES;
+          const uint8_t* patch = smem + L::P_OFF + ps * L::PATCH_BYTES;
+          // A thread owns one (pixel column px of the 10 the taps read, 8-channel group g) and a run of consecutive slab
+          // rows: the column's horizontal blend is loop-invariant, and the horizontally blended source rows are carried
+          // from one slab row to the next (the source row advances by 0 or 1 per output row), so a 16-byte item costs
+          // about half a source-row blend plus the vertical blend.  Same fp32 operations in the same order as
+          // upsample2x_kernel (misc_kernels.cu): bit-identical to up-sampling first.
+          if (col_rows_begin < L::SLAB_ROWS) {
+            const uint8_t* pcol = patch + col_off;
+            auto hblend = [&](int ry, float (&hrow)[8]) {
+              const uint4 qa = *reinterpret_cast<const uint4*>(pcol + ry * (L::PATCH_PX << 7));
+              const uint4 qb = *reinterpret_cast<const uint4*>(pcol + ry * (L::PATCH_PX << 7) + x_step);
+              const uint32_t a4[4] = {qa.x, qa.y, qa.z, qa.w}, b4[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 va = unpack_act2<F16>(a4[k]), vb = unpack_act2<F16>(b4[k]);
+                hrow[2 * k] = blend2(lx0, lx1, va.x, vb.x);
+                hrow[2 * k + 1] = blend2(lx0, lx1, va.y, vb.y);
+              }
+            };
+            float h0[8], h1[8];
+            int cached_y1 = -2;
+            const int r_end = min(col_rows_begin + RSEG, L::SLAB_ROWS);
+            for (int r = col_rows_begin; r < r_end; ++r) {
+              const int y = y0 + r;
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);             // outside the image: the conv's zero padding
+              if (x_in && y >= 0 && y < p.H) {
+                const float sy = rh * (float)y;
+                const int y1 = (int)sy;
+                const float l1 = sy - (float)y1, l0 = 1.f - l1;
+                if (y1 != cached_y1) {
+                  const int ry = min(y1 - y_lo, L::PATCH_ROWS - 2);
+                  if (y1 == cached_y1 + 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) h0[k] = h1[k];
+                  } else {
+                    hblend(ry, h0);
+                  }
+                  if (y1 < h - 1) {
+                    hblend(ry + 1, h1);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) h1[k] = h0[k];
+                  }
+                  cached_y1 = y1;
+                }
+                uint32_t o4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  o4[k] = pack_act2<F16>(blend2(l0, l1, h0[2 * k], h1[2 * k]), blend2(l0, l1, h0[2 * k + 1], h1[2 * k + 1]));
+                o = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+              }
+              // SWIZZLE_128B as TMA writes it: 16-byte chunk index XOR address bits 7..9 (the stage base is 1024-aligned)
+              const int off = r * L::ROW_BYTES + col_px * 128;
+              *reinterpret_cast<uint4*>(slab + off + ((col_g ^ ((off >> 7) & 7)) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
+          named_bar2(2, 256);
+          if (ptid == 0) {
+            if (rank == 0) mbar_arrive(a_full(as));
+            else mbar_arrive_cluster(mapa_shared(a_full(as), 0));
+            issue_patch(j + 2);            // into the patch buffer every thread has just finished reading
+          }
+          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+        }
+        if (prev_u >= 0) drain(prev_u, it - 1);
+        prev_u = u;
+        // the chunks the TMA warp loads: observe every use of the stage (see the note in the TMA warp), after the drain so
+        // that the waits cost nothing -- the next unit's first chunk needs a later use of the same stages anyway
+        for (int ch = nchunk0; ch < chunks; ++ch) {
+          mbar_wait(a_empty(as), aph ^ 1);
+          if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
+        }
+      }
+      if (prev_u >= 0) drain(prev_u, it - 1);
     }
     if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
   }
@@ -465,11 +646,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MT, bool RES, bool F16, bool WIDE>
+template <int BN, int MT, bool RES, bool F16, bool WIDE, bool UPS = false>
 static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                             const ConvArgs& args, cudaStream_t stream) {
-  using L = Conv2Cfg<BN, MT, RES, WIDE>;
-  auto kern = conv3x3_tc2_kernel<BN, MT, RES, F16, WIDE>;
+  using L = Conv2Cfg<BN, MT, RES, WIDE, UPS>;
+  auto kern = conv3x3_tc2_kernel<BN, MT, RES, F16, WIDE, UPS>;
   static int configured[64];
   static int max_clusters[64];
   int dev = 0;
@@ -513,6 +694,11 @@ static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const 
 template <int BN, int MT, bool RES>
 static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                         const ConvArgs& args, cudaStream_t stream) {
+  if (args.up_src != nullptr) {
+    if (RES) return PDA_ERR_SHAPE;  // (an up-sampled segment never meets the resident-weight configuration)
+    return args.act_f16 ? launch_conv2_fmt<BN, MT, false, true, true, true>(a0, a1, b, o, args, stream)
+                        : launch_conv2_fmt<BN, MT, false, false, true, true>(a0, a1, b, o, args, stream);
+  }
   if (args.wide)
     return args.act_f16 ? launch_conv2_fmt<BN, MT, RES, true, true>(a0, a1, b, o, args, stream)
                         : launch_conv2_fmt<BN, MT, RES, false, true>(a0, a1, b, o, args, stream);
@@ -523,7 +709,9 @@ static int launch_conv2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
 // same contract as conv3x3_tc (csrc/conv3x3_tc.cu); selected by it for shapes with at least two pixel tiles
 int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* wpacked, const float* bias, void* out,
                 void* out_pool, const void* mask, int B, int H, int W, int cout, int relu, int bn_override,
-                int act_f16, int* range_flag, cudaStream_t stream) {
+                int act_f16, int* range_flag, cudaStream_t stream, const void* up_src) {
+  // up_src != nullptr: segment 0 = bilinear x2 of up_src [B][H/2][W/2][c0] (src0 is ignored)
+  if (up_src != nullptr && ((H & 1) || (W & 1) || c1 <= 0 || !src1)) return PDA_ERR_SHAPE;
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || cout > 512 || B <= 0 || H <= 0 || W <= 0)
     return PDA_ERR_SHAPE;
   if (out_pool && ((H & 1) || (W & 1))) return PDA_ERR_SHAPE;
@@ -549,16 +737,25 @@ int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* 
       const char* e = getenv("PDA_CONV_WIDE");  // 0: three 8-px slabs per chunk; 1: one 16-px slab per chunk
       return e ? atoi(e) : PDA_CONV_WIDE_DEFAULT;
     }();
-    a.wide = wide_mode != 0;
+    a.wide = wide_mode != 0 || up_src != nullptr;
     a.wide_base_offset = 0;
   }
-  const int box_w = a.wide ? 16 : 8;
+  a.up_src = up_src;
+  const int box_w = up_src != nullptr ? PDA_UPS_ROW_PX : (a.wide ? 16 : 8);
   CUtensorMap tA0, tA1, tB;
-  int r = make_act_tensor_map(&tA0, src0, B, H, W, c0, box_w, a.tile_h + 2, 64);
-  if (r) return r;
+  int r;
+  if (up_src == nullptr) {
+    r = make_act_tensor_map(&tA0, src0, B, H, W, c0, box_w, a.tile_h + 2, 64);
+    if (r) return r;
+  }
   if (c1 > 0) {
     r = make_act_tensor_map(&tA1, src1, B, H, W, c1, box_w, a.tile_h + 2, 64);
     if (r) return r;
+    if (up_src != nullptr) {
+      // the low-resolution source, read as unswizzled patches of (8 * mt + 3) rows x 7 px x 64 channels
+      r = make_act_tensor_map(&tA0, up_src, B, H / 2, W / 2, c0, 7, 8 * mt + 3, 64, /*swizzle128=*/0);
+      if (r) return r;
+    }
   } else {
     tA1 = tA0;
   }
@@ -569,7 +766,7 @@ int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* 
     r = make_act_tensor_map(&tO, out, B, H, W, cout, 8, 4, 64);
     if (r) return r;
   }
-  const bool resident = (bn == 64 && cout == 64 && c0 + c1 == 64 && mt == 2);
+  const bool resident = (bn == 64 && cout == 64 && c0 + c1 == 64 && mt == 2 && up_src == nullptr);
   if (mt == 2) {
     if (bn == 128) return launch_conv2<128, 2, false>(tA0, tA1, tB, tO, a, stream);
     return resident ? launch_conv2<64, 2, true>(tA0, tA1, tB, tO, a, stream)

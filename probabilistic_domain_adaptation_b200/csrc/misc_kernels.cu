@@ -256,8 +256,8 @@ __device__ __forceinline__ uint4 bilerp4(const uint4& q00, const uint4& q01, con
   for (int k = 0; k < 4; ++k) {
     const float2 a = bf2_to_f2<F16>(word_of(q00, k)), b = bf2_to_f2<F16>(word_of(q01, k));
     const float2 c = bf2_to_f2<F16>(word_of(q10, k)), d = bf2_to_f2<F16>(word_of(q11, k));
-    const float ox = l0 * (lx0 * a.x + lx1 * b.x) + l1 * (lx0 * c.x + lx1 * d.x);
-    const float oy = l0 * (lx0 * a.y + lx1 * b.y) + l1 * (lx0 * c.y + lx1 * d.y);
+    const float ox = blend2(l0, l1, blend2(lx0, lx1, a.x, b.x), blend2(lx0, lx1, c.x, d.x));
+    const float oy = blend2(l0, l1, blend2(lx0, lx1, a.y, b.y), blend2(lx0, lx1, c.y, d.y));
     set_word(o, k, pack_act2<F16>(ox, oy));
   }
   return o;
@@ -304,16 +304,16 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int h, 
         const float2 v10 = bf2_to_f2<F16>(word_of(q10, k)), v11 = bf2_to_f2<F16>(word_of(q11, k)), v12 = bf2_to_f2<F16>(word_of(q12, k));
         const float2 v20 = bf2_to_f2<F16>(word_of(q20, k)), v21 = bf2_to_f2<F16>(word_of(q21, k)), v22 = bf2_to_f2<F16>(word_of(q22, k));
         // horizontal blends: column pair a = (xa, xa+1), b = (xb, xb+xpb)
-        const float a0x = lxa0 * v00.x + lxa1 * v01.x, a0y = lxa0 * v00.y + lxa1 * v01.y;
-        const float a1x = lxa0 * v10.x + lxa1 * v11.x, a1y = lxa0 * v10.y + lxa1 * v11.y;
-        const float a2x = lxa0 * v20.x + lxa1 * v21.x, a2y = lxa0 * v20.y + lxa1 * v21.y;
-        const float b0x = lxb0 * v01.x + lxb1 * v02.x, b0y = lxb0 * v01.y + lxb1 * v02.y;
-        const float b1x = lxb0 * v11.x + lxb1 * v12.x, b1y = lxb0 * v11.y + lxb1 * v12.y;
-        const float b2x = lxb0 * v21.x + lxb1 * v22.x, b2y = lxb0 * v21.y + lxb1 * v22.y;
-        set_word(oaa, k, pack_act2<F16>(lya0 * a0x + lya1 * a1x, lya0 * a0y + lya1 * a1y));
-        set_word(oab, k, pack_act2<F16>(lya0 * b0x + lya1 * b1x, lya0 * b0y + lya1 * b1y));
-        set_word(oba, k, pack_act2<F16>(lyb0 * a1x + lyb1 * a2x, lyb0 * a1y + lyb1 * a2y));
-        set_word(obb, k, pack_act2<F16>(lyb0 * b1x + lyb1 * b2x, lyb0 * b1y + lyb1 * b2y));
+        const float a0x = blend2(lxa0, lxa1, v00.x, v01.x), a0y = blend2(lxa0, lxa1, v00.y, v01.y);
+        const float a1x = blend2(lxa0, lxa1, v10.x, v11.x), a1y = blend2(lxa0, lxa1, v10.y, v11.y);
+        const float a2x = blend2(lxa0, lxa1, v20.x, v21.x), a2y = blend2(lxa0, lxa1, v20.y, v21.y);
+        const float b0x = blend2(lxb0, lxb1, v01.x, v02.x), b0y = blend2(lxb0, lxb1, v01.y, v02.y);
+        const float b1x = blend2(lxb0, lxb1, v11.x, v12.x), b1y = blend2(lxb0, lxb1, v11.y, v12.y);
+        const float b2x = blend2(lxb0, lxb1, v21.x, v22.x), b2y = blend2(lxb0, lxb1, v21.y, v22.y);
+        set_word(oaa, k, pack_act2<F16>(blend2(lya0, lya1, a0x, a1x), blend2(lya0, lya1, a0y, a1y)));
+        set_word(oab, k, pack_act2<F16>(blend2(lya0, lya1, b0x, b1x), blend2(lya0, lya1, b0y, b1y)));
+        set_word(oba, k, pack_act2<F16>(blend2(lyb0, lyb1, a1x, a2x), blend2(lyb0, lyb1, a1y, a2y)));
+        set_word(obb, k, pack_act2<F16>(blend2(lyb0, lyb1, b1x, b2x), blend2(lyb0, lyb1, b1y, b2y)));
       }
       o0[0] = oaa;
       o0[C8] = oab;
@@ -625,6 +625,17 @@ int pda_conv3x3_tc(const void* src0, int c0, const void* src1, int c1, const voi
   if (!src0 || !w_packed || (!out && !out_pool) || (c1 > 0 && !src1)) return PDA_ERR_ARG;
   return conv3x3_tc(src0, c0, src1, c1, w_packed, bias, out, out_pool, relu_mask, B, H, W, cout, relu, bn_tile,
                     act_f16, range_flag, (cudaStream_t)stream);
+}
+
+int pda_conv3x3_up_tc(const void* up_src, int c0, const void* src1, int c1, const void* w_packed, const float* bias,
+                      void* out, void* out_pool, int B, int H, int W, int cout, int relu, int act_f16, int* range_flag,
+                      void* stream) {
+  if (!up_src || !src1 || !w_packed || (!out && !out_pool)) return PDA_ERR_ARG;
+  // the fused form exists in the CTA-pair kernel only; at least two pixel tiles
+  const int th = (H > 16 && cout % 256 != 0) ? 32 : 16;
+  if ((long long)((W + 7) / 8) * ((H + th - 1) / th) * B < 2) return PDA_ERR_SHAPE;
+  return conv3x3_tc2(nullptr, c0, src1, c1, w_packed, bias, out, out_pool, nullptr, B, H, W, cout, relu, 0, act_f16,
+                     range_flag, (cudaStream_t)stream, up_src);
 }
 
 int pda_set_conv_pair(int mode) { return conv_pair_mode(mode); }

@@ -258,4 +258,11 @@ __device__ __forceinline__ float2 unpack_act2(uint32_t v) {
 }
 constexpr float F16_MAX = 65504.f;
 
+// Bilinear x2 (align_corners = True, ATen's upsample_bilinear2d arithmetic) with an explicit rounding order, shared by the
+// stand-alone up-sampling kernel and the conv kernel that up-samples its first K segment on the fly: both produce the same
+// bits.  blend2(w0, w1, a, b) = w0 * a + w1 * b.
+__device__ __forceinline__ float blend2(float w0, float w1, float a, float b) {
+  return __fmaf_rn(w1, b, __fmul_rn(w0, a));
+}
+
 }  // namespace pda

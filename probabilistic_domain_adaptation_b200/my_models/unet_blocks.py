@@ -181,6 +181,17 @@ class UpConvBlock(nn.Module):
         self.conv_block = DownConvBlock(input_dim, output_dim, initializers, padding, pool=False)
 
     def forward_nhwc(self, x, bridge, seg_real=None):
+        from ..autograd_ops import _needs_grad, packed_weight
+        convs = self.conv_block.convs()
+        plain = x.shape[3] + bridge.shape[3] == convs[0].in_channels and \
+            all(c.out_channels == pad64(c.out_channels) for c in convs)  # (no zero-padded widths in this block)
+        if plain and not _needs_grad(x, bridge, *[t for c in convs for t in (c.weight, c.bias)]) \
+                and ops.can_fuse_upsample(x, bridge):
+            # no-grad path: the first conv interpolates its first K segment itself (bit-identical to the two-kernel
+            # form below); under autograd the up-sampled tensor is needed by the weight gradient anyway
+            first = ops.conv3x3_up(x, bridge, packed_weight(convs[0], dtype=bridge.dtype), convs[0].bias.detach())
+            full, _ = run_conv_stack(convs[1:], first)
+            return full
         up = upsample2x_op(x)
         assert up.shape[2] == bridge.shape[2]  # widths (unet_blocks.py:55)
         if up.shape[1] != bridge.shape[1]:

@@ -192,6 +192,37 @@ def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=Fal
     return full, pool
 
 
+# The first conv of an up-path block consumes the bilinear x2 of its low-resolution input directly (no-grad path):
+# PDA_FUSE_UPSAMPLE=0 keeps the separate up-sampling kernel (the results are bit-identical).
+FUSE_UPSAMPLE = os.environ.get("PDA_FUSE_UPSAMPLE", "1") != "0"
+
+
+def can_fuse_upsample(x_low, bridge):
+    """The fused form lives in the CTA-pair conv kernel (needs >= 2 pixel tiles of 8 x 16/32 px)."""
+    if not FUSE_UPSAMPLE or _lib.load().pda_set_conv_pair(-1) != 1:
+        return False
+    B, H, W, _ = bridge.shape
+    return x_low.shape[1] * 2 == H and x_low.shape[2] * 2 == W and B * ((W + 7) // 8) * ((H + 31) // 32) >= 2
+
+
+def conv3x3_up(x_low, bridge, w_packed, bias, relu=True):
+    """conv3x3 over cat(bilinear_x2(x_low), bridge) without materialising the up-sampled tensor."""
+    _need_cuda(x_low, bridge, w_packed, bias)
+    lib = _lib.load()
+    B, H, W, c1 = bridge.shape
+    c0, cout = x_low.shape[3], w_packed.shape[0]
+    f16 = _is_f16(bridge)
+    assert x_low.dtype == bridge.dtype == w_packed.dtype and x_low.is_contiguous() and bridge.is_contiguous()
+    assert x_low.shape[:3] == (B, H // 2, W // 2) and w_packed.shape[1] == 9 * (c0 + c1)
+    full = torch.empty((B, H, W, cout), dtype=bridge.dtype, device=bridge.device)
+    with _Timed("conv3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
+        rc = lib.pda_conv3x3_up_tc(x_low.data_ptr(), c0, bridge.data_ptr(), c1, w_packed.data_ptr(), _ptr(bias),
+                                   full.data_ptr(), 0, B, H, W, cout, int(relu), f16,
+                                   range_flag(bridge.device).data_ptr() if f16 else 0, _stream())
+    _lib.check(rc, "conv3x3_up")
+    return full
+
+
 def avgpool2(x):
     _need_cuda(x)
     lib = _lib.load()

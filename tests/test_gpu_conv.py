@@ -244,3 +244,36 @@ def test_refresh_packed_matches_single_tensor_pack():
         if ops.INFER_DTYPE == torch.float16:
             assert torch.equal(conv.__dict__["_pda_packed_f16"][1], ops.pack_conv3x3_weights(w, dtype=torch.float16))
     assert "_pda_packed" not in mod[3].__dict__          # the cin = 1 first layer is not a tensor-core conv
+
+
+@pytest.mark.parametrize("budget", [148, 4])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,h,w,c0,c1,cout", [(1, 16, 16, 128, 64, 64), (2, 20, 12, 256, 128, 128), (1, 8, 24, 512, 256, 256),
+                                             (3, 9, 4, 128, 64, 64), (1, 64, 64, 128, 64, 64), (2, 33, 17, 256, 128, 128),
+                                             (1, 16, 16, 512, 256, 256), (3, 5, 9, 64, 64, 128), (1, 100, 36, 128, 64, 128)])
+def test_fused_upsample_conv_is_bit_identical_to_upsample_then_conv(B, h, w, c0, c1, cout, dt, budget):
+    """pda_conv3x3_up_tc (the epilogue warps interpolate the first K segment into the operand slabs) against
+    pda_upsample2x_bilinear + pda_conv3x3_tc: the same bits, on ragged tiles, odd tile counts (ghost tile of the peer CTA),
+    repeated launches, and with the grid cut to two CTA pairs (budget 4) so that every pair walks MANY units -- the ring
+    phases, the patch prefetch across unit boundaries and the produce / drain interleave only show up there (a first
+    version passed every single-unit shape and dead-locked at 1024^2)."""
+    from probabilistic_domain_adaptation_b200 import _lib, ops
+    lib = _lib.load()
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 31 + h + c0)
+    x_low = torch.randn(B, h, w, c0, generator=g).to(dev).to(dt)
+    bridge = torch.randn(B, 2 * h, 2 * w, c1, generator=g).to(dev).to(dt)
+    wt = (torch.randn(cout, c0 + c1, 3, 3, generator=g) * (2.0 / (9 * (c0 + c1))) ** 0.5).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    wp = ops.pack_conv3x3_weights(wt, dtype=dt)
+    if not ops.can_fuse_upsample(x_low, bridge):
+        pytest.skip("single-tile shape: the fused form needs the CTA-pair kernel")
+    want, _ = ops.conv3x3(ops.upsample2x(x_low), bridge, wp, bias)
+    prev = lib.pda_set_sm_budget(budget)
+    try:
+        for _ in range(3):
+            got = ops.conv3x3_up(x_low, bridge, wp, bias)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want)
+    finally:
+        lib.pda_set_sm_budget(prev if prev > 0 else 148)

@@ -70,6 +70,32 @@ def test_conv3x3_writes_stay_inside_their_tensors(B, H, W, c0, c1, cout, pool, d
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,h,w,c0,c1,cout", [(2, 17, 12, 128, 64, 64), (1, 9, 20, 256, 128, 128), (1, 8, 8, 512, 256, 256)])
+def test_fused_upsample_conv_reads_and_writes_stay_inside(B, h, w, c0, c1, cout, dt):
+    """The fused form reads the low-resolution tensor through TMA patches that overhang the image (zero fill) and writes
+    the output by TMA: inputs and output all sit between canaries, the result equals upsample-then-conv bit for bit."""
+    from probabilistic_domain_adaptation_b200 import ops
+    lib, L = _lib()
+    dev = _dev()
+    g = torch.Generator().manual_seed(h * w + cout)
+    low, bridge = Guarded((B, h, w, c0), dt, dev), Guarded((B, 2 * h, 2 * w, c1), dt, dev)
+    low.t.copy_(torch.randn(B, h, w, c0, generator=g).to(dev).to(dt))
+    bridge.t.copy_(torch.randn(B, 2 * h, 2 * w, c1, generator=g).to(dev).to(dt))
+    wt = (torch.randn(cout, c0 + c1, 3, 3, generator=g) * 0.05).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    wp = ops.pack_conv3x3_weights(wt, dtype=dt)
+    want, _ = ops.conv3x3(ops.upsample2x(low.t.contiguous()), bridge.t.contiguous(), wp, bias)
+    out = Guarded((B, 2 * h, 2 * w, cout), dt, dev)
+    f16 = int(dt == torch.float16)
+    L.check(lib.pda_conv3x3_up_tc(low.t.data_ptr(), c0, bridge.t.data_ptr(), c1, wp.data_ptr(), bias.data_ptr(),
+                                  out.t.data_ptr(), 0, B, 2 * h, 2 * w, cout, 1, f16,
+                                  ops.range_flag(dev).data_ptr() if f16 else 0, ops._stream()), "conv3x3_up")
+    torch.cuda.synchronize()
+    assert out.intact() and low.intact() and bridge.intact()
+    assert torch.equal(out.t, want)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 def test_first_conv_upsample_pool_writes_stay_inside(dt):
     from probabilistic_domain_adaptation_b200 import ops
     lib, L = _lib()
