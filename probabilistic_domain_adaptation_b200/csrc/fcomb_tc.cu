@@ -11,7 +11,13 @@
 //                        memory (no swizzled stores, no generic->async proxy fence)              (producer warps)
 //                        H2_s = [A1_s | 1 1 0..] . [W2 | b2_hi b2_lo 0..]^T   128x64x80 fp16 MMA, A from TMEM for the
 //                        first 64 k, the bias block (ones) from shared memory
-//                        logit = w3 . relu(H2_s) + b3 ; p = sigmoid ; mean / consensus        (epilogue warps)
+//                        A3_s = relu(H2_s) rounded to packed fp16 (ONE cvt.rn.relu.f16x2 per two channels), written
+//                        back over the first 32 columns of the H2 accumulator it came from (FC_L3_MMA, round 2)
+//                        D3_s = A3_s . [w3_hi | w3_lo | 0..]^T   128x16x64 fp16 MMA, A from TMEM, D into columns 32..47
+//                        of the same accumulator buffer; logit = D3[0] + D3[1] + b3
+//                        p = sigmoid ; mean / consensus                                       (epilogue warps)
+//                        (FC_L3_MMA = 0: the round-1 epilogue, logit = w3 . relu(H2_s) + b3 as 64 FMNMX + 64 FFMA per
+//                        pixel-sample in fp32)
 // bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat (fcomb_bz_kernel).
 //
 // Warp-specialised persistent CTA (2 per SM): warps 0-3 = producers (own H1 in registers, write the A1 ring),
@@ -29,10 +35,31 @@ namespace pda {
 
 constexpr int FCT = 64;             // feature / hidden channels
 constexpr int FC_TILE = 128;        // pixels per tile == TMEM lanes
-constexpr int FC_TMEM_COLS = 256;   // [0,64): H1; [64,128), [128,192): H2 ring; [192,224), [224,256): A1 ring (fp16 x2)
-constexpr int FC_A1_STAGES = 2;
-constexpr int FC_A1_COL = 3 * FCT;
-constexpr int FC_THREADS = 288;
+// Tensor memory per CTA: [0,64) H1; H2 accumulator ring of FC_RING x 64 columns from 64; A1 operand ring of FC_RING x 32
+// columns (fp16 x 2 per column) behind it.  FC_GROUPS groups of producer warps and of epilogue warps take alternate
+// samples (sample counter modulo FC_GROUPS).
+//   default FC_RING = 2, FC_GROUPS = 1: 256 columns, 288 threads, TWO CTAs per SM
+//   FC_RING = 4, FC_GROUPS = 2: 512 columns, 544 threads, one CTA per SM -- the same number of warps and of samples in
+//   flight per SM, built to give every warp two sample periods for its tcgen05.ld / st round trips.  Measured
+//   1.6 x SLOWER (1.91 ms against 1.17 ms at 4 x 1024^2, S = 16): one control warp that issues the MMAs of four samples
+//   in flight in program order stalls all of them on each blocking barrier wait, and tile boundaries are no longer
+//   covered by a second CTA.  Kept as a compile-time variant for the record.
+#ifndef FC_RING
+#define FC_RING 2
+#endif
+#ifndef FC_GROUPS
+#define FC_GROUPS 1
+#endif
+static_assert((FC_RING == 2 && FC_GROUPS == 1) || (FC_RING == 4 && FC_GROUPS == 2), "supported Fcomb pipeline shapes");
+constexpr int FC_TMEM_COLS = FC_RING == 2 ? 256 : 512;
+constexpr int FC_CTAS_PER_SM = FC_RING == 2 ? 2 : 1;
+constexpr int FC_L3_LAG = FC_RING / 2;     // the last-layer MMA of sample i is queued after the second-layer MMA of i + lag
+constexpr int FC_H2_COL = FCT;
+constexpr int FC_A1_COL = FCT + FC_RING * FCT;
+constexpr int FC_PROD_WARPS = 4 * FC_GROUPS;
+constexpr int FC_EPI_WARPS = 4 * FC_GROUPS;
+constexpr int FC_CTRL_WARP = FC_PROD_WARPS + FC_EPI_WARPS;
+constexpr int FC_THREADS = 32 * (FC_CTRL_WARP + 1);
 
 // |H1| and |bz| below this bound cannot overflow the packed-fp16 add relu(H1 + bz) (2 x 32000 < 65504); a launch that
 // sees a larger value raises the overflow flag and the caller's stream re-runs the batch through the exact fp32 kernel
@@ -43,6 +70,14 @@ constexpr float FC_F16_SAFE = 32000.f;
 #ifndef FC_W3_REG
 #define FC_W3_REG 0
 #endif
+// 1: the last layer (64 -> 1) runs on the tensor core as well (see the header); 0: fp32 FMA epilogue
+#ifndef FC_L3_MMA
+#define FC_L3_MMA 1
+#endif
+
+// relu(H2) is rounded to fp16 in that mode: a launch whose bound on |H2| (max |A1| x max row-L1 of W2 + max |b2|, from
+// fcomb_bz_kernel and the per-tile H1 maximum) is not below this raises the overflow flag -> exact fp32 re-run
+constexpr float FC_H2_SAFE = 60000.f;
 
 struct FcombSmem {
   static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 x 2 B
@@ -53,13 +88,15 @@ struct FcombSmem {
   static constexpr int W2_OFF = W1L_OFF + W_BYTES;              // fp16 W2
   static constexpr int W2X_OFF = W2_OFF + W_BYTES;              // fp16 K-extension: col 0 = b2_hi, col 1 = b2_lo
   static constexpr int AX_OFF = W2X_OFF + W_BYTES;              // 8 rows x 128 B: cols 0,1 = 1.0 (aliased by all rows)
-  static constexpr int BAR_OFF = AX_OFF + 1024;
-  static constexpr int NBARS = 4 + 2 * FC_A1_STAGES + 4;
+  static constexpr int W3T_OFF = AX_OFF + 1024;                 // fp16 last-layer tile: row 0 = w3 hi, row 1 = w3 lo, 16 rows
+  static constexpr int BAR_OFF = W3T_OFF + 2048;
+  static constexpr int NBARS = 4 + 6 * FC_RING;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BZ_CHUNK = 64;                           // samples whose layer-1 bias is staged at a time
   static constexpr int W3_OFF = SLOT_OFF + 16;                  // w3[64] fp32 (per-launch copy)
   static constexpr int BZ_OFF = W3_OFF + FCT * 4;               // bz[BZ_CHUNK][64] fp16
-  static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 2 + 1024; }
+  static constexpr int PART_OFF = BZ_OFF + BZ_CHUNK * FCT * 2;  // [2][128] (psum, count) of epilogue group 1
+  static int bytes(int) { return PART_OFF + 2 * FC_TILE * 8 + 1024; }
 };
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -101,6 +138,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// relu + round two fp32 to packed fp16 (lo = even k) in one F2FP
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -134,10 +180,11 @@ __device__ __forceinline__ void stage_weight_sw128(uint8_t* dst, uint8_t* dst_lo
   }
 }
 
-__global__ void __launch_bounds__(FC_THREADS, 2)
+__global__ void __launch_bounds__(FC_THREADS, FC_CTAS_PER_SM)
 fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ bzg, const float* __restrict__ w1,
                 const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
-                const float* __restrict__ b3, int* __restrict__ oflag, int feat_f16, int P, int S, int L, int B,
+                const float* __restrict__ b3, int* __restrict__ oflag, const float* __restrict__ bounds, int feat_f16,
+                int P, int S, int L, int B,
                 int tiles_per_img, int num_tiles, float upper, float lower, float* __restrict__ mean_prob,
                 float* __restrict__ cons_weight, int64_t* __restrict__ cons_mask, float* __restrict__ logits,
                 float* __restrict__ probs) {
@@ -147,10 +194,13 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + M::BAR_OFF;
   const uint32_t f_full = bar0, f_empty = bar0 + 8, h1_full = bar0 + 16, h1_empty = bar0 + 24;
-  auto a1_full = [&](int i) { return bar0 + 32 + 8u * i; };
-  auto a1_empty = [&](int i) { return bar0 + 32 + 8u * (FC_A1_STAGES + i); };
-  auto h2_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_STAGES + i); };
-  auto h2_empty = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_STAGES + 2 + i); };
+  // per ring slot i (sample counter % FC_RING):
+  auto a1_full = [&](int i) { return bar0 + 32 + 8u * i; };                    // A1 written (4 producer warps)
+  auto a1_empty = [&](int i) { return bar0 + 32 + 8u * (FC_RING + i); };        // second-layer MMA has read it
+  auto h2_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_RING + i); };     // second-layer MMA done
+  auto h2_empty = [&](int i) { return bar0 + 32 + 8u * (3 * FC_RING + i); };    // epilogue is done with the buffer
+  auto a3_full = [&](int i) { return bar0 + 32 + 8u * (4 * FC_RING + i); };     // relu(H2) written back (4 warps)
+  auto d3_full = [&](int i) { return bar0 + 32 + 8u * (5 * FC_RING + i); };     // last-layer MMA done
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + M::SLOT_OFF);
   float* bzs = reinterpret_cast<float*>(smem + M::BZ_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -160,19 +210,19 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     mbar_init(f_full, 1);
     mbar_init(f_empty, 1);
     mbar_init(h1_full, 1);
-    mbar_init(h1_empty, 4);
-    for (int i = 0; i < FC_A1_STAGES; ++i) {
+    mbar_init(h1_empty, FC_PROD_WARPS);
+    for (int i = 0; i < FC_RING; ++i) {
       mbar_init(a1_full(i), 4);
       mbar_init(a1_empty(i), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
       mbar_init(h2_full(i), 1);
       mbar_init(h2_empty(i), 4);
+      mbar_init(a3_full(i), 4);
+      mbar_init(d3_full(i), 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmF);
   }
-  if (warp == 8) {
+  if (warp == FC_CTRL_WARP) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), FC_TMEM_COLS);
     tmem_relinquish();
   }
@@ -191,6 +241,20 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     *reinterpret_cast<uint4*>(smem + M::W2X_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
   if (tid >= 64 && tid < 64 + FCT) reinterpret_cast<float*>(smem + M::W3_OFF)[tid - 64] = w3[tid - 64];
+  if (tid >= 128 && tid < 128 + 16 * 8) {
+    // last-layer operand tile [16 n][64 k]: n = 0 -> fp16(w3), n = 1 -> fp16(w3 - fp16(w3)), other rows 0
+    const int i = tid - 128, n = i >> 3, c = i & 7;
+    uint32_t h[4] = {0u, 0u, 0u, 0u};
+    if (n < 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = w3[c * 8 + 2 * j], b = w3[c * 8 + 2 * j + 1];
+        const float ah = __half2float(__float2half_rn(a)), bh = __half2float(__float2half_rn(b));
+        h[j] = n == 0 ? pack_f16x2(a, b) : pack_f16x2(a - ah, b - bh);
+      }
+    }
+    *reinterpret_cast<uint4*>(smem + M::W3T_OFF + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+  }
   if (tid < 64) {
     const int n = tid >> 3, c = tid & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -203,29 +267,32 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
-    // ================================================================ producers
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  if (warp < FC_PROD_WARPS) {
+    // ================================================================ producers (group = warp / 4, lane quarter = warp % 4)
+    const uint32_t group = warp >> 2;
+    const int ptid = tid;  // 0 .. 255
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     uint32_t a_it = 0, t_it = 0;
     int cur_b = -1, cur_chunk = -1;
+    const float bz_max = __ldg(bounds + 0), w2_rowsum = __ldg(bounds + 1), b2_max = __ldg(bounds + 2);
     // stages bz[s0 .. s0 + BZ_CHUNK) of image b (S <= BZ_CHUNK: once per image; else once per chunk of samples)
     auto stage_bz = [&](int b, int chunk) {
-      named_bar_sync(1, 128);  // every producer is done with the previous contents
+      named_bar_sync(1, 32 * FC_PROD_WARPS);  // every producer is done with the previous contents
       const int s0 = chunk * M::BZ_CHUNK;
       const int ns = min(M::BZ_CHUNK, S - s0);
-      for (int i = tid; i < ns * (FCT / 4); i += 128) {
+      for (int i = ptid; i < ns * (FCT / 4); i += 32 * FC_PROD_WARPS) {
         const int s = i / (FCT / 4), j4 = i - s * (FCT / 4);
         const float4 v = __ldg(reinterpret_cast<const float4*>(bzg + (static_cast<size_t>(s0 + s) * B + b) * FCT) + j4);
         reinterpret_cast<uint2*>(bzs)[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 32 * FC_PROD_WARPS);
       cur_b = b;
       cur_chunk = chunk;
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img;
       if (b != cur_b || cur_chunk != 0) stage_bz(b, 0);
-      // ---- H1 -> registers (kept for all samples) as 32 packed f16x2 (saturating)
+      // ---- H1 -> registers (kept for all samples; both groups hold a copy) as 32 packed f16x2 (saturating)
       mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
       uint32_t h1[FCT / 2];
@@ -242,14 +309,18 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         }
       }
       tc_fence_before();
-      // fp16 range guard (once per tile): "not below the bound" also catches NaN
-      if (__any_sync(0xffffffffu, !(hmax < FC_F16_SAFE)) && lane == 0) atomicOr(oflag, 1);
+      // fp16 range guards (once per tile): "not below the bound" also catches NaN
+      //   |H1|, |bz| < FC_F16_SAFE: relu(H1 + bz) cannot overflow
+      //   |H2| <= (max |H1| + max |bz|) * max_c sum_k |W2[c][k]| + max |b2| < FC_H2_SAFE   (bounds[]: fcomb_bz_kernel)
+      const bool unsafe = !(hmax < FC_F16_SAFE) || (FC_L3_MMA && !((hmax + bz_max) * w2_rowsum + b2_max < FC_H2_SAFE));
+      if (__any_sync(0xffffffffu, unsafe) && lane == 0) atomicOr(oflag, 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(h1_empty);
       for (int s = 0; s < S; ++s, ++a_it) {
         if (s / M::BZ_CHUNK != cur_chunk) stage_bz(b, s / M::BZ_CHUNK);
-        const uint32_t slot = a_it % FC_A1_STAGES;
-        mbar_wait(a1_empty(slot), ((a_it / FC_A1_STAGES) & 1) ^ 1);  // the MMA that read this slot has completed
+        if ((a_it & (FC_GROUPS - 1)) != group) continue;   // the other group's sample
+        const uint32_t slot = a_it % FC_RING;
+        mbar_wait(a1_empty(slot), ((a_it / FC_RING) & 1) ^ 1);  // the MMA that read this slot has completed
         tc_fence_after();
         // A1_s = relu(H1 + bz_s): this thread's row of 64 halves = 32 TMEM columns of its lane
         const uint32_t bz_addr = sbase + M::BZ_OFF + (s % M::BZ_CHUNK) * FCT * 2;
@@ -262,6 +333,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
           a[4 * c + 2] = add_relu_f16x2(h1[4 * c + 2], bb.z);
           a[4 * c + 3] = add_relu_f16x2(h1[4 * c + 3], bb.w);
         }
+        // (computing the row BEFORE waiting for the slot was measured: no change, profiles/r02_fcomb_l3_variants.md)
         tmem_st32(lane_addr + FC_A1_COL + slot * 32, a);
         tmem_st_wait();
         tc_fence_before();
@@ -269,38 +341,93 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         if (lane == 0) mbar_arrive(a1_full(slot));
       }
     }
-  } else if (warp < 8) {
-    // ================================================================ epilogue
+  } else if (warp < FC_CTRL_WARP) {
+    // ================================================================ epilogue (group = (warp - 8) / 4, quarter = warp % 4)
+    const uint32_t group = (warp - FC_PROD_WARPS) >> 2;
     const int q = warp & 3;
     const int prow = q * 32 + lane;  // pixel row of this thread inside the tile
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t e_it = 0;
-    // last layer (w3[64], b3) lives in registers for the whole kernel: per-launch state only (an earlier version kept
-    // it in a __constant__ bank shared by every launch of the process, which let concurrent streams race)
-    float w3r[FC_W3_REG > 0 ? FC_W3_REG : 4];
-#pragma unroll
-    for (int i = 0; i < FC_W3_REG / 4; ++i) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(w3) + i);
-      w3r[4 * i] = t.x; w3r[4 * i + 1] = t.y; w3r[4 * i + 2] = t.z; w3r[4 * i + 3] = t.w;
-    }
+    float2* part = reinterpret_cast<float2*>(smem + M::PART_OFF);
+    uint32_t e_it = 0, t_it = 0;
     const float b3r = __ldg(b3);
-    const uint32_t w3s_addr = sbase + M::W3_OFF;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img;
       const int pix = (tile - b * tiles_per_img) * FC_TILE + prow;
       const bool valid = pix < P;
       const size_t gp = static_cast<size_t>(b) * P + pix;
       float psum = 0.f;
       int count = 0;
+      // second half of a sample: the last-layer MMA has put (w3_hi . a3, w3_lo . a3) into columns 32, 33 of the buffer
+      auto finish = [&](int s, uint32_t it) {
+        const uint32_t pb = it % FC_RING;
+        mbar_wait(d3_full(pb), (it / FC_RING) & 1);
+        tc_fence_after();
+        uint32_t d[2];
+        tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h2_empty(pb));  // the accumulator buffer can be overwritten
+        const float logit = (__uint_as_float(d[0]) + __uint_as_float(d[1])) + b3r;
+        const float pr = __fdividef(1.0f, 1.0f + __expf(-logit));
+        psum += pr;
+        count += (pr >= upper || pr <= lower) ? 1 : 0;
+        if (valid) {
+          if (logits) logits[(static_cast<size_t>(s) * B + b) * P + pix] = logit;
+          if (probs) probs[(static_cast<size_t>(s) * B + b) * P + pix] = pr;
+        }
+      };
+#if FC_L3_MMA
+      int pend_s = -1;          // this group's sample whose second half is still due (its counter is pend_it)
+      uint32_t pend_it = 0;
       for (int s = 0; s < S; ++s, ++e_it) {
-        const uint32_t hb = e_it & 1;
-        mbar_wait(h2_full(hb), (e_it >> 1) & 1);
+        if ((e_it & (FC_GROUPS - 1)) != group) continue;   // the other group's sample
+        const uint32_t hb = e_it % FC_RING;
+        if (FC_RING == 2 && pend_s >= 0) {
+          // ring of two: finishing the previous sample BEFORE touching this one frees its buffer for the second-layer
+          // MMA of the next sample while this warp converts
+          finish(pend_s, pend_it);
+          pend_s = -1;
+        }
+        mbar_wait(h2_full(hb), (e_it / FC_RING) & 1);
+        tc_fence_after();
+        // first half: A3 = relu(H2) as packed fp16, written over columns 0..31 of this thread's own accumulator row
+        uint32_t a3[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + FC_H2_COL + hb * FCT + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            a3[16 * half + i] = pack_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        }
+        tmem_st32(lane_addr + FC_H2_COL + hb * FCT, a3);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a3_full(hb));
+        // (deeper ring) the previous sample of this group: its last-layer MMA was queued a whole sample period ago
+        if (pend_s >= 0) finish(pend_s, pend_it);
+        pend_s = s;
+        pend_it = e_it;
+      }
+      if (pend_s >= 0) finish(pend_s, pend_it);
+#else
+      // round-1 epilogue: logit = w3 . relu(H2) + b3 in fp32 (64 FMNMX + 64 FFMA per pixel-sample), w3 read from shared
+      // memory as warp-wide broadcast LDS.128
+      static_assert(FC_L3_MMA || FC_GROUPS == 1, "the fp32 epilogue has no group split");
+      const uint32_t w3s_addr = sbase + M::W3_OFF;
+      (void)finish;
+      for (int s = 0; s < S; ++s, ++e_it) {
+        const uint32_t hb = e_it % FC_RING;
+        mbar_wait(h2_full(hb), (e_it / FC_RING) & 1);
         tc_fence_after();
         float l0 = b3r, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // b3 + four independent chains
 #pragma unroll
         for (int part = 0; part < 4; ++part) {
           uint32_t v[16];
-          tmem_ld16(lane_addr + FCT + hb * FCT + part * 16, v);
+          tmem_ld16(lane_addr + FC_H2_COL + hb * FCT + part * 16, v);
           tmem_ld_wait();
           if (part == 3) {
             // all four quarters are in registers: the accumulator buffer can be overwritten
@@ -310,18 +437,11 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int j = part * 16 + 4 * i;
-            float wa, wb, wc, wd;
-            if (j < FC_W3_REG) {
-              wa = w3r[j]; wb = w3r[j + 1]; wc = w3r[j + 2]; wd = w3r[j + 3];
-            } else {
-              const uint4 t = lds128(w3s_addr + 4 * j);
-              wa = __uint_as_float(t.x); wb = __uint_as_float(t.y); wc = __uint_as_float(t.z); wd = __uint_as_float(t.w);
-            }
-            l0 = fmaf(wa, fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), l0);
-            l1 = fmaf(wb, fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), l1);
-            l2 = fmaf(wc, fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), l2);
-            l3 = fmaf(wd, fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), l3);
+            const uint4 t = lds128(w3s_addr + 4 * (part * 16 + 4 * i));
+            l0 = fmaf(__uint_as_float(t.x), fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), l0);
+            l1 = fmaf(__uint_as_float(t.y), fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), l1);
+            l2 = fmaf(__uint_as_float(t.z), fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), l2);
+            l3 = fmaf(__uint_as_float(t.w), fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), l3);
           }
         }
         const float logit = (l0 + l1) + (l2 + l3);
@@ -333,7 +453,19 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
           if (probs) probs[(static_cast<size_t>(s) * B + b) * P + pix] = pr;
         }
       }
-      if (valid) {
+#endif
+      if (FC_GROUPS == 2) {
+        // combine the two groups' partial sums (group 1 -> shared memory -> group 0 writes the per-pixel outputs)
+        float2* pbuf = part + (t_it & 1) * FC_TILE;
+        if (group == 1) pbuf[prow] = make_float2(psum, __int_as_float(count));
+        named_bar_sync(2, 32 * FC_EPI_WARPS);
+        if (group == 0) {
+          const float2 o = pbuf[prow];
+          psum += o.x;
+          count += __float_as_int(o.y);
+        }
+      }
+      if (group == 0 && valid) {
         if (mean_prob) mean_prob[gp] = psum / static_cast<float>(S);
         if (cons_weight) cons_weight[gp] = static_cast<float>(count) / static_cast<float>(S);
         if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
@@ -346,10 +478,12 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     // F x W1 hi/lo: bf16 x bf16, or fp16 x fp16 when the trunk ran with fp16 activations
     const uint32_t idesc1 = feat_f16 ? umma_idesc_f16(128, FCT) : umma_idesc_bf16(128, FCT);
     constexpr uint32_t idesc2 = umma_idesc_f16(128, FCT);   // A1 (fp16) x W2 (fp16)
+    constexpr uint32_t idesc3 = umma_idesc_f16(128, 16);    // A3 (fp16, TMEM) x [w3_hi | w3_lo | 0 ..] (fp16)
     const uint64_t dW1 = umma_desc_k_sw128(sbase + M::W1_OFF);
     const uint64_t dW1L = umma_desc_k_sw128(sbase + M::W1L_OFF);
     const uint64_t dW2 = umma_desc_k_sw128(sbase + M::W2_OFF);
     const uint64_t dW2X = umma_desc_k_sw128(sbase + M::W2X_OFF);
+    const uint64_t dW3 = umma_desc_k_sw128(sbase + M::W3T_OFF);
     const uint64_t dF = umma_desc_k_sw128(sbase + M::F_OFF);
     const uint64_t dAX = umma_desc_k_sw128(sbase + M::AX_OFF, /*sbo_bytes=*/0);  // all 8-row groups alias one atom
     auto load_tile = [&](int tile) {
@@ -375,6 +509,19 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       }
       __syncwarp();
     };
+    // D3 = relu(H2) . w3: A from columns 0..31 of accumulator buffer (it % FC_RING), D into its columns 32..47
+    auto mma3 = [&](uint32_t it) {
+      const uint32_t pb = it % FC_RING;
+      mbar_wait(a3_full(pb), (it / FC_RING) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t ta = tmem + FC_H2_COL + pb * FCT;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ts(ta + 32, ta + 8 * k, dW3 + 2 * k, idesc3, k ? 1u : 0u);
+        umma_commit(d3_full(pb));
+      }
+      __syncwarp();
+    };
     uint32_t a_it = 0, t_it = 0;
     int tile = blockIdx.x;
     if (tile < num_tiles) {
@@ -388,30 +535,41 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         load_tile(next);
       }
       for (int s = 0; s < S; ++s, ++a_it) {
-        const uint32_t slot = a_it % FC_A1_STAGES, hb = a_it & 1;
-        mbar_wait(a1_full(slot), (a_it / FC_A1_STAGES) & 1);
-        mbar_wait(h2_empty(hb), ((a_it >> 1) & 1) ^ 1);
+        const uint32_t slot = a_it % FC_RING;
+        mbar_wait(a1_full(slot), (a_it / FC_RING) & 1);
+        mbar_wait(h2_empty(slot), ((a_it / FC_RING) & 1) ^ 1);
         tc_fence_after();
         if (leader) {
-          const uint32_t d = tmem + FCT + hb * FCT;
+          const uint32_t d = tmem + FC_H2_COL + slot * FCT;
           const uint32_t ta = tmem + FC_A1_COL + slot * 32;  // K = 16 halves = 8 columns per MMA
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16_ts(d, ta + 8 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
           umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
-          umma_commit(h2_full(hb));
+          umma_commit(h2_full(slot));
           umma_commit(a1_empty(slot));
         }
         __syncwarp();
+        // the last layer of the sample queued FC_L3_LAG steps ago (after this sample's second-layer MMA is in the queue,
+        // so that the tensor pipe has work while the epilogue converts)
+#if FC_L3_MMA
+        if (a_it >= FC_L3_LAG) mma3(a_it - FC_L3_LAG);
+#endif
         // next tile's H1 as soon as half of this tile's samples are issued (the producers copied H1 to registers at
         // the start of the tile, so the TMEM columns are free; the feature tile was prefetched above)
         if (s == (S >> 1) && next < num_tiles) mma1(t_it + 1);
       }
     }
+#if FC_L3_MMA
+    for (uint32_t l = FC_L3_LAG; l >= 1; --l)
+      if (a_it >= l) mma3(a_it - l);
+#else
+    (void)mma3;
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, FC_TMEM_COLS);
+  if (warp == FC_CTRL_WARP) tmem_dealloc(tmem, FC_TMEM_COLS);
 }
 
 // bz[s][b][j] = b1[j] + sum_d W1[j][64 + d] * z[s][b][d]: the per-(sample, image) bias that replaces the tiled-z concat.
@@ -419,17 +577,33 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
 // range (no separate memset; the tensor-core kernel ORs its own H1 range check into it afterwards).
 __global__ void __launch_bounds__(1024)
 fcomb_bz_kernel(const float* __restrict__ z, const float* __restrict__ w1, const float* __restrict__ b1,
-                float* __restrict__ bz, int SB, int L, int* __restrict__ oflag) {
+                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                float* __restrict__ bz, int SB, int L, int* __restrict__ oflag, float* __restrict__ bounds) {
+  // bounds[0] = max |bz|, [1] = max_c sum_k |W2[c][k]|, [2] = max |b2|: the tensor-core kernel bounds |H2| with them
+  __shared__ unsigned int smax[3];
+  if (threadIdx.x < 3) smax[threadIdx.x] = 0u;
+  __syncthreads();
   int over = 0;
+  float m = 0.f;
   for (int i = threadIdx.x; i < SB * FCT; i += blockDim.x) {
     const int sb = i / FCT, j = i - sb * FCT;
     float acc = b1[j];
     for (int d = 0; d < L; ++d) acc = fmaf(w1[j * (FCT + L) + FCT + d], z[sb * L + d], acc);
     bz[i] = acc;
     over |= !(fabsf(acc) < FC_F16_SAFE);
+    m = fmaxf(m, fabsf(acc));
+  }
+  atomicMax(&smax[0], __float_as_uint(m));  // non-negative floats order like their bit patterns
+  if (threadIdx.x < FCT) {
+    float rs = 0.f;
+    for (int k = 0; k < FCT; ++k) rs += fabsf(w2[threadIdx.x * FCT + k]);
+    over |= !(rs < FC_F16_SAFE) || !(fabsf(w3[threadIdx.x]) < FC_F16_SAFE);  // (also NaN / inf / fp16-unsafe weights)
+    atomicMax(&smax[1], __float_as_uint(rs));
+    atomicMax(&smax[2], __float_as_uint(fabsf(b2[threadIdx.x])));
   }
   over = __syncthreads_or(over);
   if (threadIdx.x == 0) *oflag = over ? 1 : 0;
+  if (threadIdx.x < 3) bounds[threadIdx.x] = __uint_as_float(smax[threadIdx.x]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -441,7 +615,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 using namespace pda;
 
 // scratch (fp32 words, caller-allocated per call -> no state shared between launches / streams / graphs):
-// [0] overflow flag (int), [4 ..) bz[S][B][64]
+// [0] overflow flag (int), [1..3] range bounds (max |bz|, max row-L1 of W2, max |b2|), [4 ..) bz[S][B][64]
 extern "C" long long pda_fcomb_scratch_floats(int S, int B) { return 4 + (long long)S * B * FCT; }
 
 extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const float* w1, const float* b1,
@@ -473,17 +647,17 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   const int tiles_per_img = (P + FC_TILE - 1) / FC_TILE;
   const long long num_tiles = (long long)tiles_per_img * B;
   if (num_tiles > 0x7fffffffLL || (long long)S * B * FCT > 0x7fffffffLL) return PDA_ERR_SHAPE;
-  // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise)
-  // (2 CTAs of 288 threads and 2 x 256 TMEM columns fit; shared memory decides)
+  // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise);
+  // tensor memory (FC_TMEM_COLS of 512 columns per CTA) and shared memory decide
   int per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm < 1) return PDA_ERR_SHAPE;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > FC_CTAS_PER_SM) per_sm = FC_CTAS_PER_SM;
   const int grid = (int)(num_tiles < 148 * per_sm ? num_tiles : 148 * per_sm);
   int* oflag = reinterpret_cast<int*>(scratch);
   float* bz = scratch + 4;
   PDA_COUNT(2);
-  fcomb_bz_kernel<<<1, 1024, 0, st>>>(z, w1, b1, bz, S * B, latent, oflag);
-  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, w3, b3, oflag, feat_f16, P, S, latent, B, tiles_per_img,
+  fcomb_bz_kernel<<<1, 1024, 0, st>>>(z, w1, b1, w2, b2, w3, bz, S * B, latent, oflag, scratch + 1);
+  fcomb_tc_kernel<<<grid, FC_THREADS, smem, st>>>(tm, bz, w1, w2, b2, w3, b3, oflag, scratch + 1, feat_f16, P, S, latent, B, tiles_per_img,
                                                   (int)num_tiles, upper, lower, mean_prob, cons_weight, cons_mask,
                                                   logits, probs);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
