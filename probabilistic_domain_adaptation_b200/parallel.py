@@ -7,6 +7,8 @@ gloo in the CPU tests).
   distributed code; the wrapper works on the bare module because ProbabilisticUnet.forward returns None and the
   loss comes from methods (elbo), which DistributedDataParallel would hide.
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -78,6 +80,10 @@ class GradAllReducer:
             for p in b["params"]:
                 self._bucket_of[p] = bi
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        from . import training
+        ref = weakref.WeakMethod(self._late_target)           # (a forgotten reducer must not be kept alive by the registry)
+        self._probe = lambda p: (ref() or (lambda _p: None))(p)
+        training._LAUNCHED.append(self._probe)
         self._avg = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
 
     def _add_bucket(self, params):
@@ -104,6 +110,14 @@ class GradAllReducer:
             self._launch(b)
 
     def _launch(self, b):
+        # regulariser gradients parked by training.L2NormSumFn: one multi-tensor add per bucket instead of one ATen add
+        # per parameter inside the autograd engine
+        from . import training
+        reg_p, reg_g = training.take_reg_grads(b["params"])
+        if reg_p:
+            with torch.no_grad():
+                torch._foreach_add_([p.grad for p in reg_p], reg_g)
+        b["launched"] = True
         grads = [p.grad for p in b["params"]]
         if b["wire"] is not None and self.world > 1:
             torch._foreach_copy_(b["wire_views"], grads)       # fp32 -> bf16 while packing
@@ -114,6 +128,24 @@ class GradAllReducer:
         if self.world > 1:
             op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
             b["work"] = dist.all_reduce(buf, op=op, group=self.group, async_op=True)
+
+    def _late_target(self, p):
+        """The flat-gradient view of p if p's bucket has already been copied / handed to the all-reduce in this backward
+        pass (training.flush_reg_grads adds a late regulariser gradient there, after the reduction), else None."""
+        bi = self._bucket_of.get(p)
+        if bi is None:
+            return None
+        b = self.buckets[bi]
+        if not b.get("launched"):
+            return None
+        if b["work"] is not None:
+            b["work"].wait()
+            b["work"] = None
+            if b["wire"] is not None:
+                b["flat"].copy_(b["wire"])                     # widen the averaged bf16 gradients
+            if not self._avg:
+                b["flat"].div_(self.world)
+        return b["views"][b["params"].index(p)]
 
     def finish(self):
         for b in self.buckets:
@@ -137,11 +169,15 @@ class GradAllReducer:
             for p, v in zip(b["params"], b["views"]):
                 p.grad = v
             b["pending"] = len(b["params"])
+            b["launched"] = False
 
     def remove(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        from . import training
+        if self._probe in training._LAUNCHED:
+            training._LAUNCHED.remove(self._probe)
         if self._prev_budget is not None:
             from . import _lib
             _lib.load().pda_set_sm_budget(self._prev_budget)

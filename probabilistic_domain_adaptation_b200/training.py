@@ -6,6 +6,8 @@ backward).  Activations and their gradients are NHWC bf16; parameter gradients a
 own layout (OIHW), so torch optimizers / GradScaler work unchanged.  autograd itself (graph, accumulation
 into .grad) is the plumbing; every tensor-sized arithmetic step is a libpda_b200 kernel.
 """
+import os
+
 import torch
 
 from . import ops
@@ -275,6 +277,7 @@ class L2NormSumFn(torch.autograd.Function):
         out, norms = ops.multi_tensor_l2norm_fwd(cache["fwd"], len(params))
         ctx.cache = cache
         ctx.shapes = [p.shape for p in params]
+        ctx.params = params
         ctx.save_for_backward(norms)
         return out
 
@@ -284,7 +287,72 @@ class L2NormSumFn(torch.autograd.Function):
         c = ctx.cache
         flat = ops.multi_tensor_l2norm_bwd(c["bwd"], norms, g, c["total"])
         grads = [flat[o:o + s.numel()].view(s) for o, s in zip(c["offsets"], ctx.shapes)]
+        if DEFER_L2_GRADS:
+            # Every regularised parameter also receives a data gradient: returned from here, the engine would sum the
+            # two with one ATen add PER PARAMETER (56 launches per step).  The gradients are parked instead and added
+            # to param.grad in bulk (one multi-tensor add per gradient bucket / per backward): same .grad afterwards.
+            _defer_reg_grads(ctx.params, grads)
+            return (None,) * (1 + len(grads))
         return (None, *grads)
+
+
+# ---- regulariser gradients added in bulk --------------------------------------------------------------------------
+# (PDA_DEFER_L2_GRADS=0 restores gradients returned through the engine -- needed only by callers that differentiate the
+# regulariser with torch.autograd.grad instead of .backward(), which never touches param.grad)
+DEFER_L2_GRADS = os.environ.get("PDA_DEFER_L2_GRADS", "1") != "0"
+_PENDING_REG = {}        # parameter -> its parked regulariser gradient (a view of one flat buffer per module)
+_LAUNCHED = []           # callables (param) -> flat view | None of live GradAllReducers (see parallel.py)
+
+
+def _defer_reg_grads(params, grads):
+    first = not _PENDING_REG
+    for p, g in zip(params, grads):
+        if p.requires_grad:
+            prev = _PENDING_REG.get(p)
+            _PENDING_REG[p] = g if prev is None else prev + g
+    if first and _PENDING_REG:
+        torch.autograd.Variable._execution_engine.queue_callback(flush_reg_grads)
+
+
+def take_reg_grads(params):
+    """-> (params that have a parked regulariser gradient, those gradients); the entries are removed.  Called by
+    GradAllReducer when a bucket is complete, before it copies / reduces the bucket."""
+    ps, gs = [], []
+    for p in params:
+        g = _PENDING_REG.pop(p, None)
+        if g is not None:
+            ps.append(p)
+            gs.append(g)
+    return ps, gs
+
+
+def flush_reg_grads():
+    """End of the backward pass (engine callback): whatever is still parked goes into param.grad with one multi-tensor
+    add.  A parameter whose gradient bucket was already handed to a GradAllReducer (the regulariser node ran later than
+    the bucket's last data gradient -- not the order the step bodies of this package produce) gets it added to the
+    reduced flat gradient instead, after that reduction has completed."""
+    if not _PENDING_REG:
+        return
+    items = list(_PENDING_REG.items())
+    _PENDING_REG.clear()
+    dst, src = [], []
+    for p, g in items:
+        late = None
+        for probe in _LAUNCHED:
+            late = probe(p)
+            if late is not None:
+                break
+        if late is not None:
+            dst.append(late)
+            src.append(g)
+        elif p.grad is None:
+            p.grad = g.clone()
+        else:
+            dst.append(p.grad)
+            src.append(g)
+    if dst:
+        with torch.no_grad():
+            torch._foreach_add_(dst, src)
 
 
 _L2_CACHES = {}   # (storage pointer, numel) of every tensor -> pointer tables; bounded (oldest entry evicted)

@@ -195,6 +195,50 @@ def test_l2_regularisation_forward_backward():
         assert torch.allclose(l2_regularisation(m), ref, rtol=1e-6)
 
 
+@pytest.mark.parametrize("with_reducer", [False, True])
+def test_l2_gradients_added_in_bulk_equal_the_engine_sum(with_reducer):
+    """The regulariser's gradients are parked during backward and added to param.grad with multi-tensor adds (one per
+    gradient bucket, or one at the end of the backward pass) instead of 56 engine-side adds: param.grad after
+    loss.backward() [+ reducer.finish()] must equal data gradient + regulariser gradient, also when the regulariser is
+    used twice in one loss, and nothing may stay parked."""
+    from probabilistic_domain_adaptation_b200 import training
+    from probabilistic_domain_adaptation_b200.my_models.utils import l2_regularisation
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer
+    dev = _dev()
+    torch.manual_seed(1)
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 2, 1)).to(dev)
+    x = torch.randn(2, 4, 8, 8, device=dev)
+
+    def loss_fn(reg):
+        return m(x).square().mean() + 1e-2 * reg(m) + 3e-3 * reg(m[0])
+
+    def ref_reg(mod):
+        out = None
+        for p in mod.parameters():
+            out = p.norm(2) if out is None else out + p.norm(2)
+        return out
+
+    loss_fn(ref_reg).backward()
+    want = [p.grad.clone() for p in m.parameters()]
+    for p in m.parameters():
+        p.grad = None
+    assert training.DEFER_L2_GRADS
+    red = GradAllReducer(m, bucket_mb=1e-4) if with_reducer else None   # tiny buckets: several launches per backward
+    try:
+        for _ in range(2):                                               # second pass: gradients start from None again
+            for p in m.parameters():
+                p.grad = None
+            loss_fn(l2_regularisation).backward()
+            if red is not None:
+                red.finish()
+            assert not training._PENDING_REG
+            for w, p in zip(want, m.parameters()):
+                assert torch.allclose(p.grad, w, rtol=1e-5, atol=1e-9)
+    finally:
+        if red is not None:
+            red.remove()
+
+
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 @pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 8), (3, 5, 9), (5, 136, 200)])
 def test_fcomb_backward(shape, precision):
