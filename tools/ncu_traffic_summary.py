@@ -41,9 +41,14 @@ def main():
     for _ in range(2):  # prior encoder, U-Net contracting path share the shapes
         nets += [(64, 64, 0), (64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2),
                  (256, 256, 2), (256, 512, 3), (512, 512, 3), (512, 512, 3)]
-    nets += [(768, 256, 2), (256, 256, 2), (256, 256, 2), (384, 128, 1), (128, 128, 1), (128, 128, 1), (192, 64, 0),
-             (64, 64, 0), (64, 64, 0)]
+    nets += [(256, 256, 2), (256, 256, 2), (128, 128, 1), (128, 128, 1), (64, 64, 0), (64, 64, 0)]
     alg = sum((cin + cout) * 2.0 * px / 4 ** lvl + 9.0 * cin * cout * 2 for cin, cout, lvl in nets)
+    # first conv of an up block with the bilinear x2 fused in: the low-resolution tensor (c_low channels at level
+    # lvl + 1) and the bridge (c_br channels at level lvl) are read, cout channels written
+    fused = [(512, 256, 256, 2), (256, 128, 128, 1), (128, 64, 64, 0)]
+    alg += sum(c_low * 2.0 * px / 4 ** (lvl + 1) + (c_br + cout) * 2.0 * px / 4 ** lvl + 9.0 * (c_low + c_br) * cout * 2
+               for c_low, c_br, cout, lvl in fused)
+    nets = nets + fused
     out = {
         "build": tag, "workload": {"tiles": T, "tile": HW, "samples": S},
         "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on one inference step "
