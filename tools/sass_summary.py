@@ -25,7 +25,7 @@ def main():
             cur = m.group(1)
             kernels[cur] = []
             continue
-        if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        if cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             kernels[cur].append(line.rstrip())
     print("# SASS summary of the shipped `libpda_b200.so` (`cuobjdump -sass`, sm_100a)\n")
     print("Counts of instructions per kernel.  `UTCHMMA` = `tcgen05.mma`, `LDTM`/`STTM` = `tcgen05.ld`/`st`, `UTMALDG`/`UTMASTG`"
