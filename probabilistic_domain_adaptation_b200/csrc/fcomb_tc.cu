@@ -35,29 +35,29 @@ namespace pda {
 
 constexpr int FCT = 64;             // feature / hidden channels
 constexpr int FC_TILE = 128;        // pixels per tile == TMEM lanes
-// Tensor memory per CTA: [0,64) H1; H2 accumulator ring of FC_RING x 64 columns from 64; A1 operand ring of FC_RING x 32
-// columns (fp16 x 2 per column) behind it.  FC_GROUPS groups of producer warps and of epilogue warps take alternate
-// samples (sample counter modulo FC_GROUPS).
-//   default FC_RING = 2, FC_GROUPS = 1: 256 columns, 288 threads, TWO CTAs per SM
-//   FC_RING = 4, FC_GROUPS = 2: 512 columns, 544 threads, one CTA per SM -- the same number of warps and of samples in
-//   flight per SM, built to give every warp two sample periods for its tcgen05.ld / st round trips.  Measured
-//   1.6 x SLOWER (1.91 ms against 1.17 ms at 4 x 1024^2, S = 16): one control warp that issues the MMAs of four samples
-//   in flight in program order stalls all of them on each blocking barrier wait, and tile boundaries are no longer
-//   covered by a second CTA.  Kept as a compile-time variant for the record.
-#ifndef FC_RING
-#define FC_RING 2
+// Tensor memory per CTA (256 columns, two CTAs per SM): H2 accumulator ring of FC_H2_RING x 64 columns from 0; A1 operand
+// ring of FC_A1_RING x 32 columns (fp16 x 2 per column) behind it; H1 (64 columns).
+//   FC_H2_RING = 2 (default): H1 in its own 64 columns, its MMA prefetched in the middle of the previous tile.
+//   FC_H2_RING = 3: three accumulator buffers (the epilogue converts sample s while the last-layer MMA of s - 1 is in
+//   flight and the second-layer MMA of s + 1 already has a free buffer).  3 x 64 + 2 x 32 = 256 leaves no columns for H1:
+//   it ALIASES the A1 ring (FC_H1_ALIAS) -- the layer-1 MMA of the next tile runs when the tile's last second-layer MMA
+//   has read the ring, the producers copy H1 to registers and only then write A1 rows again.  Correct (same parity
+//   numbers) and exactly as fast as two buffers (1.11-1.17 ms against 1.12-1.15 ms, same box): kept as an option.
+// What was measured about this kernel's bound is collected in profiles/r02_fcomb_l3_variants.md.
+#ifndef FC_H2_RING
+#define FC_H2_RING 2
 #endif
-#ifndef FC_GROUPS
-#define FC_GROUPS 1
-#endif
-static_assert((FC_RING == 2 && FC_GROUPS == 1) || (FC_RING == 4 && FC_GROUPS == 2), "supported Fcomb pipeline shapes");
-constexpr int FC_TMEM_COLS = FC_RING == 2 ? 256 : 512;
-constexpr int FC_CTAS_PER_SM = FC_RING == 2 ? 2 : 1;
-constexpr int FC_L3_LAG = FC_RING / 2;     // the last-layer MMA of sample i is queued after the second-layer MMA of i + lag
-constexpr int FC_H2_COL = FCT;
-constexpr int FC_A1_COL = FCT + FC_RING * FCT;
-constexpr int FC_PROD_WARPS = 4 * FC_GROUPS;
-constexpr int FC_EPI_WARPS = 4 * FC_GROUPS;
+constexpr int FC_A1_RING = 2;
+constexpr bool FC_H1_ALIAS = FC_H2_RING == 3;
+static_assert(FC_H2_RING == 2 || FC_H2_RING == 3, "supported accumulator ring depths");
+constexpr int FC_TMEM_COLS = 256;
+constexpr int FC_CTAS_PER_SM = 2;
+constexpr int FC_H2_COL = 0;
+constexpr int FC_A1_COL = FC_H2_RING * FCT;
+constexpr int FC_H1_COL = FC_H1_ALIAS ? FC_A1_COL : FC_A1_COL + FC_A1_RING * 32;
+static_assert(FC_H1_COL + FCT <= FC_TMEM_COLS && FC_A1_COL + FC_A1_RING * 32 <= FC_TMEM_COLS, "tensor memory budget");
+constexpr int FC_PROD_WARPS = 4;
+constexpr int FC_EPI_WARPS = 4;
 constexpr int FC_CTRL_WARP = FC_PROD_WARPS + FC_EPI_WARPS;
 constexpr int FC_THREADS = 32 * (FC_CTRL_WARP + 1);
 
@@ -79,6 +79,16 @@ constexpr float FC_F16_SAFE = 32000.f;
 // fcomb_bz_kernel and the per-tile H1 maximum) is not below this raises the overflow flag -> exact fp32 re-run
 constexpr float FC_H2_SAFE = 60000.f;
 
+// -DFC_PROFILE: cycle counters of the three roles (CTA 0, lane 0 of one warp per role), read with pda_fcomb_profile_read
+#ifdef FC_PROFILE
+__device__ unsigned long long fc_prof[16];
+#define FC_T0() long long _t0 = clock64()
+#define FC_ACC(i) do { long long _t1 = clock64(); if (blockIdx.x == 0 && lane == 0) fc_prof[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+#else
+#define FC_T0() do {} while (0)
+#define FC_ACC(i) do {} while (0)
+#endif
+
 struct FcombSmem {
   static constexpr int A_BYTES = FC_TILE * 128;                 // 128 rows x 64 x 2 B
   static constexpr int W_BYTES = FCT * 128;                     // 64 rows x 64 x 2 B
@@ -90,13 +100,12 @@ struct FcombSmem {
   static constexpr int AX_OFF = W2X_OFF + W_BYTES;              // 8 rows x 128 B: cols 0,1 = 1.0 (aliased by all rows)
   static constexpr int W3T_OFF = AX_OFF + 1024;                 // fp16 last-layer tile: row 0 = w3 hi, row 1 = w3 lo, 16 rows
   static constexpr int BAR_OFF = W3T_OFF + 2048;
-  static constexpr int NBARS = 4 + 6 * FC_RING;
+  static constexpr int NBARS = 4 + 2 * FC_A1_RING + 4 * FC_H2_RING;
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BZ_CHUNK = 64;                           // samples whose layer-1 bias is staged at a time
   static constexpr int W3_OFF = SLOT_OFF + 16;                  // w3[64] fp32 (per-launch copy)
   static constexpr int BZ_OFF = W3_OFF + FCT * 4;               // bz[BZ_CHUNK][64] fp16
-  static constexpr int PART_OFF = BZ_OFF + BZ_CHUNK * FCT * 2;  // [2][128] (psum, count) of epilogue group 1
-  static int bytes(int) { return PART_OFF + 2 * FC_TILE * 8 + 1024; }
+  static int bytes(int) { return BZ_OFF + BZ_CHUNK * FCT * 2 + 1024; }
 };
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -194,13 +203,13 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + M::BAR_OFF;
   const uint32_t f_full = bar0, f_empty = bar0 + 8, h1_full = bar0 + 16, h1_empty = bar0 + 24;
-  // per ring slot i (sample counter % FC_RING):
-  auto a1_full = [&](int i) { return bar0 + 32 + 8u * i; };                    // A1 written (4 producer warps)
-  auto a1_empty = [&](int i) { return bar0 + 32 + 8u * (FC_RING + i); };        // second-layer MMA has read it
-  auto h2_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_RING + i); };     // second-layer MMA done
-  auto h2_empty = [&](int i) { return bar0 + 32 + 8u * (3 * FC_RING + i); };    // epilogue is done with the buffer
-  auto a3_full = [&](int i) { return bar0 + 32 + 8u * (4 * FC_RING + i); };     // relu(H2) written back (4 warps)
-  auto d3_full = [&](int i) { return bar0 + 32 + 8u * (5 * FC_RING + i); };     // last-layer MMA done
+  // A1 ring slot i = sample counter % FC_A1_RING; accumulator buffer i = sample counter % FC_H2_RING
+  auto a1_full = [&](int i) { return bar0 + 32 + 8u * i; };                                        // A1 written (4 producer warps)
+  auto a1_empty = [&](int i) { return bar0 + 32 + 8u * (FC_A1_RING + i); };                         // second-layer MMA has read it
+  auto h2_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_RING + i); };                      // second-layer MMA done
+  auto h2_empty = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_RING + FC_H2_RING + i); };        // epilogue is done with the buffer
+  auto a3_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_RING + 2 * FC_H2_RING + i); };     // relu(H2) written back (4 warps)
+  auto d3_full = [&](int i) { return bar0 + 32 + 8u * (2 * FC_A1_RING + 3 * FC_H2_RING + i); };     // last-layer MMA done
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + M::SLOT_OFF);
   float* bzs = reinterpret_cast<float*>(smem + M::BZ_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -211,9 +220,11 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     mbar_init(f_empty, 1);
     mbar_init(h1_full, 1);
     mbar_init(h1_empty, FC_PROD_WARPS);
-    for (int i = 0; i < FC_RING; ++i) {
+    for (int i = 0; i < FC_A1_RING; ++i) {
       mbar_init(a1_full(i), 4);
       mbar_init(a1_empty(i), 1);
+    }
+    for (int i = 0; i < FC_H2_RING; ++i) {
       mbar_init(h2_full(i), 1);
       mbar_init(h2_empty(i), 4);
       mbar_init(a3_full(i), 4);
@@ -268,8 +279,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
   const uint32_t tmem = *tmem_slot;
 
   if (warp < FC_PROD_WARPS) {
-    // ================================================================ producers (group = warp / 4, lane quarter = warp % 4)
-    const uint32_t group = warp >> 2;
+    // ================================================================ producers (lane quarter = warp)
     const int ptid = tid;  // 0 .. 255
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     uint32_t a_it = 0, t_it = 0;
@@ -292,7 +302,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img;
       if (b != cur_b || cur_chunk != 0) stage_bz(b, 0);
-      // ---- H1 -> registers (kept for all samples; both groups hold a copy) as 32 packed f16x2 (saturating)
+      // ---- H1 -> registers (kept for all samples) as 32 packed f16x2 (saturating)
       mbar_wait(h1_full, t_it & 1);
       tc_fence_after();
       uint32_t h1[FCT / 2];
@@ -300,7 +310,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + half * 32, v);
+        tmem_ld32(lane_addr + FC_H1_COL + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -318,10 +328,11 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       if (lane == 0) mbar_arrive(h1_empty);
       for (int s = 0; s < S; ++s, ++a_it) {
         if (s / M::BZ_CHUNK != cur_chunk) stage_bz(b, s / M::BZ_CHUNK);
-        if ((a_it & (FC_GROUPS - 1)) != group) continue;   // the other group's sample
-        const uint32_t slot = a_it % FC_RING;
-        mbar_wait(a1_empty(slot), ((a_it / FC_RING) & 1) ^ 1);  // the MMA that read this slot has completed
+        const uint32_t slot = a_it % FC_A1_RING;
+        FC_T0();
+        mbar_wait(a1_empty(slot), ((a_it / FC_A1_RING) & 1) ^ 1);  // the MMA that read this slot has completed
         tc_fence_after();
+        if (warp == 0) FC_ACC(0);
         // A1_s = relu(H1 + bz_s): this thread's row of 64 halves = 32 TMEM columns of its lane
         const uint32_t bz_addr = sbase + M::BZ_OFF + (s % M::BZ_CHUNK) * FCT * 2;
         uint32_t a[32];
@@ -339,36 +350,31 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_full(slot));
+        if (warp == 0) FC_ACC(1);
       }
     }
   } else if (warp < FC_CTRL_WARP) {
-    // ================================================================ epilogue (group = (warp - 8) / 4, quarter = warp % 4)
-    const uint32_t group = (warp - FC_PROD_WARPS) >> 2;
+    // ================================================================ epilogue (lane quarter = warp % 4)
     const int q = warp & 3;
     const int prow = q * 32 + lane;  // pixel row of this thread inside the tile
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    float2* part = reinterpret_cast<float2*>(smem + M::PART_OFF);
-    uint32_t e_it = 0, t_it = 0;
+    uint32_t e_it = 0;
     const float b3r = __ldg(b3);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t_it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int pix = (tile - b * tiles_per_img) * FC_TILE + prow;
       const bool valid = pix < P;
       const size_t gp = static_cast<size_t>(b) * P + pix;
       float psum = 0.f;
       int count = 0;
-      // second half of a sample: the last-layer MMA has put (w3_hi . a3, w3_lo . a3) into columns 32, 33 of the buffer
-      auto finish = [&](int s, uint32_t it) {
-        const uint32_t pb = it % FC_RING;
-        mbar_wait(d3_full(pb), (it / FC_RING) & 1);
-        tc_fence_after();
-        uint32_t d[2];
-        tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h2_empty(pb));  // the accumulator buffer can be overwritten
-        const float logit = (__uint_as_float(d[0]) + __uint_as_float(d[1])) + b3r;
+#if FC_L3_MMA
+      // Two tensor-memory round trips (tcgen05.ld / st + wait) per sample: one wait for the loads of this sample's 64
+      // accumulator columns AND the previous sample's two last-layer columns, one for the store of relu(H2) -- the
+      // straightforward order has four.  (Measured neutral, like the ring depth: see the profile note.)
+      int pend_s = -1;          // the sample whose last-layer columns are still due (its counter is pend_it)
+      uint32_t pend_it = 0;
+      auto finish_math = [&](int s, float d0, float d1) {
+        const float logit = (d0 + d1) + b3r;
         const float pr = __fdividef(1.0f, 1.0f + __expf(-logit));
         psum += pr;
         count += (pr >= upper || pr <= lower) ? 1 : 0;
@@ -377,51 +383,63 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
           if (probs) probs[(static_cast<size_t>(s) * B + b) * P + pix] = pr;
         }
       };
-#if FC_L3_MMA
-      int pend_s = -1;          // this group's sample whose second half is still due (its counter is pend_it)
-      uint32_t pend_it = 0;
       for (int s = 0; s < S; ++s, ++e_it) {
-        if ((e_it & (FC_GROUPS - 1)) != group) continue;   // the other group's sample
-        const uint32_t hb = e_it % FC_RING;
-        if (FC_RING == 2 && pend_s >= 0) {
-          // ring of two: finishing the previous sample BEFORE touching this one frees its buffer for the second-layer
-          // MMA of the next sample while this warp converts
-          finish(pend_s, pend_it);
-          pend_s = -1;
-        }
-        mbar_wait(h2_full(hb), (e_it / FC_RING) & 1);
+        const uint32_t hb = e_it % FC_H2_RING;
+        FC_T0();
+        mbar_wait(h2_full(hb), (e_it / FC_H2_RING) & 1);
+        const uint32_t pb = pend_it % FC_H2_RING;
+        if (pend_s >= 0) mbar_wait(d3_full(pb), (pend_it / FC_H2_RING) & 1);  // queued right behind this sample's MMA
         tc_fence_after();
-        // first half: A3 = relu(H2) as packed fp16, written over columns 0..31 of this thread's own accumulator row
-        uint32_t a3[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + FC_H2_COL + hb * FCT + half * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            a3[16 * half + i] = pack_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        if (warp == 4) FC_ACC(2);
+        uint32_t v0[32], v1[32], d[2] = {0u, 0u};
+        tmem_ld32(lane_addr + FC_H2_COL + hb * FCT, v0);
+        tmem_ld32(lane_addr + FC_H2_COL + hb * FCT + 32, v1);
+        if (pend_s >= 0) tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
+        tmem_ld_wait();
+        if (pend_s >= 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h2_empty(pb));  // the previous sample's accumulator buffer can be overwritten
         }
-        tmem_st32(lane_addr + FC_H2_COL + hb * FCT, a3);
+        // A3 = relu(H2) as packed fp16 (packed in place: result i only overwrites inputs that are already consumed),
+        // written over columns 0..31 of this thread's own accumulator row
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v0[i] = pack_relu_f16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v0[16 + i] = pack_relu_f16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+        tmem_st32(lane_addr + FC_H2_COL + hb * FCT, v0);
+        if (pend_s >= 0) finish_math(pend_s, __uint_as_float(d[0]), __uint_as_float(d[1]));   // under the store's latency
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a3_full(hb));
-        // (deeper ring) the previous sample of this group: its last-layer MMA was queued a whole sample period ago
-        if (pend_s >= 0) finish(pend_s, pend_it);
+        if (warp == 4) FC_ACC(3);
         pend_s = s;
         pend_it = e_it;
       }
-      if (pend_s >= 0) finish(pend_s, pend_it);
+      {
+        // the tile's last sample
+        const uint32_t pb = pend_it % FC_H2_RING;
+        FC_T0();
+        mbar_wait(d3_full(pb), (pend_it / FC_H2_RING) & 1);
+        tc_fence_after();
+        if (warp == 4) FC_ACC(4);
+        uint32_t d[2];
+        tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h2_empty(pb));
+        finish_math(pend_s, __uint_as_float(d[0]), __uint_as_float(d[1]));
+        if (warp == 4) FC_ACC(5);
+      }
 #else
       // round-1 epilogue: logit = w3 . relu(H2) + b3 in fp32 (64 FMNMX + 64 FFMA per pixel-sample), w3 read from shared
       // memory as warp-wide broadcast LDS.128
-      static_assert(FC_L3_MMA || FC_GROUPS == 1, "the fp32 epilogue has no group split");
       const uint32_t w3s_addr = sbase + M::W3_OFF;
-      (void)finish;
       for (int s = 0; s < S; ++s, ++e_it) {
-        const uint32_t hb = e_it % FC_RING;
-        mbar_wait(h2_full(hb), (e_it / FC_RING) & 1);
+        const uint32_t hb = e_it % FC_H2_RING;
+        mbar_wait(h2_full(hb), (e_it / FC_H2_RING) & 1);
         tc_fence_after();
         float l0 = b3r, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // b3 + four independent chains
 #pragma unroll
@@ -454,18 +472,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         }
       }
 #endif
-      if (FC_GROUPS == 2) {
-        // combine the two groups' partial sums (group 1 -> shared memory -> group 0 writes the per-pixel outputs)
-        float2* pbuf = part + (t_it & 1) * FC_TILE;
-        if (group == 1) pbuf[prow] = make_float2(psum, __int_as_float(count));
-        named_bar_sync(2, 32 * FC_EPI_WARPS);
-        if (group == 0) {
-          const float2 o = pbuf[prow];
-          psum += o.x;
-          count += __float_as_int(o.y);
-        }
-      }
-      if (group == 0 && valid) {
+      if (valid) {
         if (mean_prob) mean_prob[gp] = psum / static_cast<float>(S);
         if (cons_weight) cons_weight[gp] = static_cast<float>(count) / static_cast<float>(S);
         if (cons_mask) cons_mask[gp] = (count == S) ? 1 : 0;
@@ -501,18 +508,18 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       tc_fence_after();
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + FC_H1_COL, dF + 2 * k, dW1 + 2 * k, idesc1, k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dF + 2 * k, dW1L + 2 * k, idesc1, 1u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + FC_H1_COL, dF + 2 * k, dW1L + 2 * k, idesc1, 1u);
         umma_commit(h1_full);
         umma_commit(f_empty);
       }
       __syncwarp();
     };
-    // D3 = relu(H2) . w3: A from columns 0..31 of accumulator buffer (it % FC_RING), D into its columns 32..47
+    // D3 = relu(H2) . w3: A from columns 0..31 of accumulator buffer (it % FC_H2_RING), D into its columns 32..47
     auto mma3 = [&](uint32_t it) {
-      const uint32_t pb = it % FC_RING;
-      mbar_wait(a3_full(pb), (it / FC_RING) & 1);
+      const uint32_t pb = it % FC_H2_RING;
+      mbar_wait(a3_full(pb), (it / FC_H2_RING) & 1);
       tc_fence_after();
       if (leader) {
         const uint32_t ta = tmem + FC_H2_COL + pb * FCT;
@@ -522,7 +529,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       }
       __syncwarp();
     };
-    uint32_t a_it = 0, t_it = 0;
+    uint32_t a_it = 0, t_it = 0, m3_it = 0;   // m3_it: next sample whose last-layer MMA is due
     int tile = blockIdx.x;
     if (tile < num_tiles) {
       load_tile(tile);
@@ -535,34 +542,50 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         load_tile(next);
       }
       for (int s = 0; s < S; ++s, ++a_it) {
-        const uint32_t slot = a_it % FC_RING;
-        mbar_wait(a1_full(slot), (a_it / FC_RING) & 1);
-        mbar_wait(h2_empty(slot), ((a_it / FC_RING) & 1) ^ 1);
+        const uint32_t slot = a_it % FC_A1_RING, hb = a_it % FC_H2_RING;
+        FC_T0();
+        mbar_wait(a1_full(slot), (a_it / FC_A1_RING) & 1);
+        FC_ACC(8);
+        mbar_wait(h2_empty(hb), ((a_it / FC_H2_RING) & 1) ^ 1);
         tc_fence_after();
+        FC_ACC(9);
         if (leader) {
-          const uint32_t d = tmem + FC_H2_COL + slot * FCT;
+          const uint32_t d = tmem + FC_H2_COL + hb * FCT;
           const uint32_t ta = tmem + FC_A1_COL + slot * 32;  // K = 16 halves = 8 columns per MMA
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16_ts(d, ta + 8 * k, dW2 + 2 * k, idesc2, k ? 1u : 0u);
           umma_bf16(d, dAX, dW2X, idesc2, 1u);  // + b2 (hi + lo)
-          umma_commit(h2_full(slot));
+          umma_commit(h2_full(hb));
           umma_commit(a1_empty(slot));
         }
         __syncwarp();
-        // the last layer of the sample queued FC_L3_LAG steps ago (after this sample's second-layer MMA is in the queue,
-        // so that the tensor pipe has work while the epilogue converts)
 #if FC_L3_MMA
-        if (a_it >= FC_L3_LAG) mma3(a_it - FC_L3_LAG);
+        // the last layer of the previous sample (after this sample's second-layer MMA is in the queue, so that the
+        // tensor pipe has work while the epilogue converts)
+        FC_ACC(10);
+        while (m3_it < a_it) mma3(m3_it++);
+        FC_ACC(11);
 #endif
-        // next tile's H1 as soon as half of this tile's samples are issued (the producers copied H1 to registers at
-        // the start of the tile, so the TMEM columns are free; the feature tile was prefetched above)
-        if (s == (S >> 1) && next < num_tiles) mma1(t_it + 1);
+        if (!FC_H1_ALIAS) {
+          // next tile's H1 as soon as half of this tile's samples are issued (the producers copied H1 to registers at
+          // the start of the tile, so its TMEM columns are free; the feature tile was prefetched above)
+          if (s == (S >> 1) && next < num_tiles) mma1(t_it + 1);
+        }
       }
-    }
+      if (FC_H1_ALIAS && next < num_tiles) {
+        // H1 shares its columns with the A1 ring: the second-layer MMAs of this tile's last samples must have read
+        // their rows (their a1_empty commits) before the layer-1 MMA of the next tile overwrites them
+        for (uint32_t back = 1; back <= (uint32_t)FC_A1_RING && back <= a_it; ++back) {
+          const uint32_t it = a_it - back;
+          mbar_wait(a1_empty(it % FC_A1_RING), (it / FC_A1_RING) & 1);
+        }
+        mma1(t_it + 1);
+      }
 #if FC_L3_MMA
-    for (uint32_t l = FC_L3_LAG; l >= 1; --l)
-      if (a_it >= l) mma3(a_it - l);
-#else
+      while (m3_it < a_it) mma3(m3_it++);   // the tile's last sample (the epilogue writes the tile's outputs after it)
+#endif
+    }
+#if !FC_L3_MMA
     (void)mma3;
 #endif
   }
@@ -614,6 +637,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 using namespace pda;
 
+#ifdef FC_PROFILE
+// [0] producer wait slot, [1] producer work, [2] epilogue wait H2, [3] convert, [4] wait D3, [5] finish,
+// [8] control wait A1, [9] control wait H2 buffer, [10] issue MMA2, [11] last-layer MMA incl. its wait
+extern "C" int pda_fcomb_profile_read(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, fc_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return PDA_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(fc_prof, z, sizeof(z)) != cudaSuccess) return PDA_ERR_CUDA;
+  }
+  return PDA_OK;
+}
+#endif
+
 // scratch (fp32 words, caller-allocated per call -> no state shared between launches / streams / graphs):
 // [0] overflow flag (int), [1..3] range bounds (max |bz|, max row-L1 of W2, max |b2|), [4 ..) bz[S][B][64]
 extern "C" long long pda_fcomb_scratch_floats(int S, int B) { return 4 + (long long)S * B * FCT; }
@@ -648,7 +684,7 @@ extern "C" int pda_fcomb_mc_consensus(const void* feat, const float* z, const fl
   const long long num_tiles = (long long)tiles_per_img * B;
   if (num_tiles > 0x7fffffffLL || (long long)S * B * FCT > 0x7fffffffLL) return PDA_ERR_SHAPE;
   // persistent grid: exactly the number of CTAs that are resident at once (a partial second wave would serialise);
-  // tensor memory (FC_TMEM_COLS of 512 columns per CTA) and shared memory decide
+  // tensor memory (256 of the 512 columns per CTA) and shared memory decide
   int per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm < 1) return PDA_ERR_SHAPE;
   if (per_sm > FC_CTAS_PER_SM) per_sm = FC_CTAS_PER_SM;

@@ -19,6 +19,71 @@ __device__ __forceinline__ void umma_acc(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// same with the A operand in tensor memory (K = 16 bf16 = 8 columns per MMA), as the fused Fcomb kernel issues it
+__device__ __forceinline__ void umma_acc_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+
+// Small-N / TMEM-A rates: `iters` groups of 4 K-steps on ONE accumulator (the Fcomb pattern: 64-deep K, one D).
+template <int N, bool A_TM>
+__global__ void __launch_bounds__(128, 1) umma_small_kernel(int iters, unsigned long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const uint32_t sbase = smem_u32(smem);
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3F803F80u ^ ((i * 2654435761u) & 0x007F007Fu);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  // some finite data in the TMEM A region (columns 256..287)
+  tmem_st32_fill(tmem + 256 + (static_cast<uint32_t>((threadIdx.x >> 5) * 32) << 16), 0x3C003C00u);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    const uint64_t da = umma_desc_k_sw128(sbase);
+    const uint64_t db = umma_desc_k_sw128(sbase + 64 * 1024);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (A_TM) umma_acc_ts(tmem, tmem + 256 + 8 * k, db + 2ull * k, idesc);
+          else umma_acc(tmem, da + 2ull * k, db + 2ull * k, idesc);
+        }
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && leader) cycles[0] = (unsigned long long)(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
 template <int ACCS, int N, int A_MN, int B_MN, int M = 128>
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, unsigned long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
@@ -193,6 +258,31 @@ int main() {
     const double bytes_per_mma = r.m * 16 * 2 + r.n * 16 * 2;
     printf("| %s | %.0f | %.3f | %.0f | %.1f | %.0f |\n", r.name, mmas, ms, flop / (ms * 1e-3) / 1e12, (double)cyc / mmas,
            bytes_per_mma * mmas / (double)cyc);
+  }
+  // small N and the A operand in tensor memory (the fused Fcomb kernel's MMAs)
+  {
+    struct SRow { const char* name; int n; void (*fn)(int, unsigned long long*); };
+    std::vector<SRow> srows = {
+        {"N=64  A in shared memory", 64, umma_small_kernel<64, false>}, {"N=64  A in tensor memory", 64, umma_small_kernel<64, true>},
+        {"N=32  A in shared memory", 32, umma_small_kernel<32, false>}, {"N=32  A in tensor memory", 32, umma_small_kernel<32, true>},
+        {"N=16  A in shared memory", 16, umma_small_kernel<16, false>}, {"N=16  A in tensor memory", 16, umma_small_kernel<16, true>},
+        {"N=128 A in tensor memory", 128, umma_small_kernel<128, true>}, {"N=256 A in tensor memory", 256, umma_small_kernel<256, true>},
+    };
+    printf("\n| M = 128, K-major B, one accumulator, 4 K-steps per group | MMAs per CTA | cycles per MMA |\n|---|---|---|\n");
+    for (auto& r : srows) {
+      cudaFuncSetAttribute(r.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      int iters = 2000;
+      void* args[] = {&iters, &d_cyc};
+      for (int w = 0; w < 3; ++w) cudaLaunchKernel((const void*)r.fn, dim3(sms), dim3(128), args, smem, 0);
+      cudaError_t err = cudaDeviceSynchronize();
+      if (err != cudaSuccess) {
+        printf("| %s | launch failed: %s |\n", r.name, cudaGetErrorString(err));
+        return 1;
+      }
+      unsigned long long cyc = 0;
+      cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost);
+      printf("| %s | %d | %.1f |\n", r.name, iters * 4, (double)cyc / (iters * 4.0));
+    }
   }
   // M = 64 accumulator layout
   float* d_out;
