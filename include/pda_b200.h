@@ -86,6 +86,11 @@ int pda_conv3x3_up_tc(const void* up_src, int c0, const void* src1, int c1, cons
  * queries.  Returns the previous mode.  Results are bit-identical between the two. */
 int pda_set_conv_pair(int mode);
 
+/* Kernel selection for pda_conv3x3_first with cout = 64: 1 (default) = tensor-core kernel (kind::tf32 with split operands:
+ * fp32-equivalent accuracy, csrc/conv_first_tc.cu), 0 = CUDA-core kernel.  mode < 0 only queries.  Returns the previous
+ * mode. */
+int pda_set_first_conv_tc(int mode);
+
 /* SMs the persistent tensor-core kernels (conv, weight gradient, Fcomb backward) may occupy (default 148).  Data-parallel
  * training leaves a few SMs to NCCL so that the gradient all-reduce runs next to the backward kernels instead of
  * between them.  sms <= 0 only queries.  Returns the previous value. */

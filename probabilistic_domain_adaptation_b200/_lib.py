@@ -25,6 +25,7 @@ SIGNATURES = {
     "pda_conv3x3_tc": [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "pda_conv3x3_up_tc": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "pda_set_conv_pair": [_I],
+    "pda_set_first_conv_tc": [_I],
     "pda_set_sm_budget": [_I],
     "pda_conv3x3_bf16_simt": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_avgpool2": [_P, _P, _I, _I, _I, _I, _I, _P],

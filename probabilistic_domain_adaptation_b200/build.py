@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpda_b200.so")
 STAMP = os.path.join(PKG, ".libpda_b200.stamp")
 SOURCES = ["conv3x3_tc.cu", "conv3x3_tc2.cu", "misc_kernels.cu", "fcomb.cu", "fcomb_tc.cu", "wgrad_tc.cu", "train_kernels.cu", "fcomb_bwd_tc.cu",
-           "augment_kernels.cu"]
+           "augment_kernels.cu", "conv_first_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-DPDA_BUILD",

@@ -32,6 +32,8 @@ struct ConvArgs {
                               // saturates at +-65504)
 };
 
+int conv3x3_first_tc(const float* x0, const float* x1, const float* w, const float* bias, void* out, int B, int H, int W,
+                     int relu, int act_f16, cudaStream_t st);  // csrc/conv_first_tc.cu (cout = 64)
 void* get_encode_tiled();  // cuTensorMapEncodeTiled driver entry point (or nullptr)
 int make_act_tensor_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h, int box_c,
                         int swizzle128 = 1);

@@ -1,6 +1,10 @@
 // HBM-bound helper kernels of the PUNet path: weight packing, first-layer direct conv, 2x2 average pool,
 // bilinear x2 upsample, Gaussian head (global mean + 1x1), latent sampling, KL, multi-tensor EMA,
 // and a plain CUDA-core conv3x3 used as the on-GPU cross-check of the tcgen05 kernel.
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "conv.cuh"
 #include "ptx.cuh"
 
@@ -595,6 +599,18 @@ int pda_pack_conv3x3_weights_multi(const int64_t* table, int n_chunks, void* str
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
 }
 
+// 1: the first conv layer (cout = 64) runs on the tensor core; initial value from PDA_FIRST_TC.  set < 0: query only.
+static int first_conv_tc_mode(int set) {
+  static std::atomic<int> mode{[] {
+    const char* e = getenv("PDA_FIRST_TC");
+    return e ? atoi(e) : 1;
+  }()};
+  if (set >= 0) return mode.exchange(set);
+  return mode.load();
+}
+
+int pda_set_first_conv_tc(int mode) { return first_conv_tc_mode(mode); }
+
 int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const float* bias, void* out, int B, int H,
                       int W, int cout, int relu, int act_f16, void* stream) {
   if (!x0 || !w || !bias || !out) return PDA_ERR_ARG;
@@ -606,8 +622,11 @@ int pda_conv3x3_first(const float* x0, const float* x1, const float* w, const fl
   const int cin = x1 ? 2 : 1;
   const size_t smem = sizeof(float) * (cin * 9 * cout + cout);
   PDA_COUNT(1);
-  const int grid = grid_for(quads * groups, 256, 148 * 6);
   cudaStream_t st = (cudaStream_t)stream;
+  // cout = 64 (every script configuration): the tensor-core kernel (tf32 with split operands, csrc/conv_first_tc.cu);
+  // PDA_FIRST_TC=0 / pda_set_first_conv_tc(0) keep the CUDA-core kernel below
+  if (first_conv_tc_mode(-1) && cout == 64) return conv3x3_first_tc(x0, x1, w, bias, out, B, H, W, relu, act_f16, st);
+  const int grid = grid_for(quads * groups, 256, 148 * 6);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (x1) {
     if (act_f16) conv_first_kernel<2, true><<<grid, 256, smem, st>>>(x0, x1, w, bias, o, B, H, W, cout, relu);

@@ -277,3 +277,35 @@ def test_fused_upsample_conv_is_bit_identical_to_upsample_then_conv(B, h, w, c0,
             assert torch.equal(got, want)
     finally:
         lib.pda_set_sm_budget(prev if prev > 0 else 148)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,W,cin", [(1, 5, 7, 1), (2, 37, 129, 2), (3, 16, 8, 1), (1, 130, 131, 2), (4, 64, 64, 1)])
+def test_first_conv_tensor_core_kernel_matches_cuda_core_kernel(B, H, W, cin, dt):
+    """The first layer on the tensor core (kind::tf32 MMA with hi / lo split operands, one pixel per TMEM lane) against
+    the CUDA-core kernel that does the same conv with fp32 FMAs: equal up to the summation order in fp32 and the final
+    16-bit rounding -- on images smaller than one 128-pixel tile, widths that are not a multiple of anything, several
+    images per tile, and twice in a row (barrier phases / TMEM state of a previous launch)."""
+    from probabilistic_domain_adaptation_b200 import _lib, ops
+    lib = _lib.load()
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + cin)
+    x0 = (torch.randn(B, 1, H, W, generator=g) * 3.0).to(dev)
+    x1 = (torch.randn(B, 1, H, W, generator=g) * 3.0).to(dev) if cin == 2 else None
+    w = (torch.randn(64, cin, 3, 3, generator=g) * 0.4).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    prev = lib.pda_set_first_conv_tc(0)
+    try:
+        want = ops.conv3x3_first(x0, x1, w, b, dtype=dt)
+        lib.pda_set_first_conv_tc(1)
+        for _ in range(2):
+            got = ops.conv3x3_first(x0, x1, w, b, dtype=dt)
+            torch.cuda.synchronize()
+            ulp = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10   # spacing of the 16-bit format relative to the value
+            err = (got.float() - want.float()).abs()
+            # at most one unit in the last place of the 16-bit result; near the ReLU threshold the split-operand sum may
+            # differ by ~1e-5 absolute (2^-21 of the products' magnitude)
+            assert bool((err <= ulp * want.float().abs() + 1e-4).all()), float(err.max())
+            assert float((got != want).float().mean()) < 0.02     # and that only where a sum sits on a rounding boundary
+    finally:
+        lib.pda_set_first_conv_tc(prev)
