@@ -45,7 +45,7 @@ constexpr int FC_TILE = 128;        // pixels per tile == TMEM lanes
 //   numbers) and exactly as fast as two buffers (1.11-1.17 ms against 1.12-1.15 ms, same box): kept as an option.
 // What was measured about this kernel's bound is collected in profiles/r02_fcomb_l3_variants.md.
 #ifndef FC_H2_RING
-#define FC_H2_RING 2
+#define FC_H2_RING 3
 #endif
 constexpr int FC_A1_RING = 2;
 constexpr bool FC_H1_ALIAS = FC_H2_RING == 3;
@@ -82,8 +82,9 @@ constexpr float FC_H2_SAFE = 60000.f;
 // -DFC_PROFILE: cycle counters of the three roles (CTA 0, lane 0 of one warp per role), read with pda_fcomb_profile_read
 #ifdef FC_PROFILE
 __device__ unsigned long long fc_prof[16];
-#define FC_T0() long long _t0 = clock64()
-#define FC_ACC(i) do { long long _t1 = clock64(); if (blockIdx.x == 0 && lane == 0) fc_prof[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+// (only CTA 0 / lane 0 reads the clock: clock reads in every thread of every CTA slowed the kernel down 3x)
+#define FC_T0() long long _t0 = (blockIdx.x == 0 && lane == 0) ? clock64() : 0
+#define FC_ACC(i) do { if (blockIdx.x == 0 && lane == 0) { long long _t1 = clock64(); fc_prof[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } } while (0)
 #else
 #define FC_T0() do {} while (0)
 #define FC_ACC(i) do {} while (0)
@@ -357,10 +358,12 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       int count = 0;
 #if FC_L3_MMA
       // Two tensor-memory round trips (tcgen05.ld / st + wait) per sample: one wait for the loads of this sample's 64
-      // accumulator columns AND the previous sample's two last-layer columns, one for the store of relu(H2) -- the
-      // straightforward order has four.  (Measured neutral, like the ring depth: see the profile note.)
-      int pend_s = -1;          // the sample whose last-layer columns are still due (its counter is pend_it)
-      uint32_t pend_it = 0;
+      // accumulator columns AND an earlier sample's two last-layer columns, one for the store of relu(H2).
+      // FC_LAG = FC_H2_RING - 1 samples are in flight behind the one being converted: with three buffers the last-layer
+      // columns read in iteration s are those of sample s - 2, whose MMA finished a whole iteration ago -- with two
+      // buffers (lag 1) the warp waits out that MMA's round trip at the top of every iteration (cycle counters of
+      // -DFC_PROFILE: 340 of 1080 cycles per sample).
+      constexpr int FC_LAG = FC_H2_RING - 1;
       auto finish_math = [&](int s, float d0, float d1) {
         const float logit = (d0 + d1) + b3r;
         const float pr = __fdividef(1.0f, 1.0f + __expf(-logit));
@@ -373,21 +376,22 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
       };
       for (int s = 0; s < S; ++s, ++e_it) {
         const uint32_t hb = e_it % FC_H2_RING;
+        const bool due = s >= FC_LAG;                       // sample s - FC_LAG of this tile has its columns ready
+        const uint32_t pit = e_it - FC_LAG, pb = pit % FC_H2_RING;
         FC_T0();
         mbar_wait(h2_full(hb), (e_it / FC_H2_RING) & 1);
-        const uint32_t pb = pend_it % FC_H2_RING;
-        if (pend_s >= 0) mbar_wait(d3_full(pb), (pend_it / FC_H2_RING) & 1);  // queued right behind this sample's MMA
+        if (due) mbar_wait(d3_full(pb), (pit / FC_H2_RING) & 1);
         tc_fence_after();
         if (warp == 4) FC_ACC(2);
         uint32_t v0[32], v1[32], d[2] = {0u, 0u};
         tmem_ld32(lane_addr + FC_H2_COL + hb * FCT, v0);
         tmem_ld32(lane_addr + FC_H2_COL + hb * FCT + 32, v1);
-        if (pend_s >= 0) tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
+        if (due) tmem_ld2(lane_addr + FC_H2_COL + pb * FCT + 32, d);
         tmem_ld_wait();
-        if (pend_s >= 0) {
+        if (due) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(h2_empty(pb));  // the previous sample's accumulator buffer can be overwritten
+          if (lane == 0) mbar_arrive(h2_empty(pb));  // that sample's accumulator buffer can be overwritten
         }
         // A3 = relu(H2) as packed fp16 (packed in place: result i only overwrites inputs that are already consumed),
         // written over columns 0..31 of this thread's own accumulator row
@@ -396,20 +400,18 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
 #pragma unroll
         for (int i = 0; i < 16; ++i) v0[16 + i] = pack_relu_f16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
         tmem_st32(lane_addr + FC_H2_COL + hb * FCT, v0);
-        if (pend_s >= 0) finish_math(pend_s, __uint_as_float(d[0]), __uint_as_float(d[1]));   // under the store's latency
+        if (due) finish_math(s - FC_LAG, __uint_as_float(d[0]), __uint_as_float(d[1]));   // under the store's latency
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a3_full(hb));
         if (warp == 4) FC_ACC(3);
-        pend_s = s;
-        pend_it = e_it;
       }
-      {
-        // the tile's last sample
-        const uint32_t pb = pend_it % FC_H2_RING;
+      // the tile's last FC_LAG samples
+      for (int s = (S > FC_LAG ? S - FC_LAG : 0); s < S; ++s) {
+        const uint32_t pit = e_it - (uint32_t)(S - s), pb = pit % FC_H2_RING;
         FC_T0();
-        mbar_wait(d3_full(pb), (pend_it / FC_H2_RING) & 1);
+        mbar_wait(d3_full(pb), (pit / FC_H2_RING) & 1);
         tc_fence_after();
         if (warp == 4) FC_ACC(4);
         uint32_t d[2];
@@ -418,7 +420,7 @@ fcomb_tc_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(h2_empty(pb));
-        finish_math(pend_s, __uint_as_float(d[0]), __uint_as_float(d[1]));
+        finish_math(s, __uint_as_float(d[0]), __uint_as_float(d[1]));
         if (warp == 4) FC_ACC(5);
       }
 #else
