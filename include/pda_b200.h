@@ -211,6 +211,16 @@ int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, c
                            float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate,
                            int scratch_is_zero, void* stream);
 
+/* Deterministic variant (bit-identical results from run to run for a fixed shape and SM budget): every CTA of the stream-K
+ * schedule stores its partial accumulators to its own slot of `scratch` (plain stores; no memset, no atomics) and a
+ * second kernel sums the slots of each 64 x 64 x 9 item in CTA order while re-laying out to OIHW.
+ * scratch: fp32 [pda_conv3x3_wgrad_det_scratch_floats(c0 + c1, cout, B, H, W)], contents irrelevant on entry.
+ * (torch.use_deterministic_algorithms-style opt-in: the host side selects it with PDA_WGRAD_DETERMINISTIC=1.) */
+long long pda_conv3x3_wgrad_det_scratch_floats(int ctot, int cout, int B, int H, int W);
+int pda_conv3x3_wgrad_bf16_det(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
+                               float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate,
+                               void* stream);
+
 /* dZ = (dFull + 0.25 * dPool[y/2][x/2]) * (Y > 0): ReLU backward fused with the backward of the 2x2 average pool that
  * consumes Y (unet_blocks.py:17,20).  NHWC bf16; dfull or dpool may be NULL; y == NULL skips the ReLU mask
  * (plain AvgPool2d backward).  dbias (fp32 [C], may be NULL) receives the conv bias gradient sum_pixels dZ. */

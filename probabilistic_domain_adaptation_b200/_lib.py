@@ -47,6 +47,8 @@ SIGNATURES = {
     "pda_multi_tensor_ema_warmup": [_P, _I, _c.c_double, _P, _P],
     "pda_conv3x3_wgrad_scratch_floats": [_I, _I],
     "pda_conv3x3_wgrad_bf16": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pda_conv3x3_wgrad_det_scratch_floats": [_I, _I, _I, _I, _I],
+    "pda_conv3x3_wgrad_bf16_det": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "pda_relu_pool_bwd_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "pda_upsample2x_bilinear_bwd_bf16": [_P, _P, _I, _I, _I, _I, _P],
     "pda_conv3x3_first_bwd_scratch_floats": [_I, _I, _I, _I, _I],
@@ -68,7 +70,7 @@ SIGNATURES = {
     "pda_fcomb_bwd_fp32": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {"pda_error_string": _c.c_char_p, "pda_launch_count": _c.c_longlong, "pda_reset_launch_count": None,
-             "pda_fcomb_scratch_floats": _c.c_longlong, "pda_conv3x3_wgrad_scratch_floats": _c.c_longlong, "pda_conv3x3_first_bwd_scratch_floats": _c.c_longlong}
+             "pda_fcomb_scratch_floats": _c.c_longlong, "pda_conv3x3_wgrad_scratch_floats": _c.c_longlong, "pda_conv3x3_wgrad_det_scratch_floats": _c.c_longlong, "pda_conv3x3_first_bwd_scratch_floats": _c.c_longlong}
 
 _lib = None
 

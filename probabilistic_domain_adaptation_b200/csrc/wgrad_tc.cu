@@ -49,7 +49,13 @@ struct WgradArgs {
   float* scratch;  // [9][ctot][cout] fp32, all zero at launch
   float* dbias;    // [cout] fp32 scratch behind it, zero at launch, or nullptr: bias gradient = column sums of dZ, from
                    // one extra "ones" MMA on the items of input-channel chunk 0
+  float* part;     // deterministic mode (else nullptr): per-CTA partial accumulators [grid][slots_per_cta][WG_SLOT_FLOATS],
+                   // plain stores instead of atomics; wgrad_reduce_kernel sums them in CTA order
+  int slots_per_cta;
 };
+
+// one partial-accumulator slot: the M = 128 accumulator [192 cols][128 rows], the M = 64 one [192 cols][64 rows], 64 bias sums
+constexpr int WG_SLOT_FLOATS = 192 * 128 + 192 * 64 + 64;
 
 struct WgradSmem {
   // ONE dZ buffer of 16-pixel rows (px x0 - 1 .. x0 + 14, TMA zero-fills outside the image) serves the three column
@@ -204,7 +210,45 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_consta
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t flushes = 0;
     int cur_item = -1;
+    const int first_item = (int)(s0 / p.num_tiles);
+    // deterministic mode: the accumulators of (this CTA, item) go to the CTA's own slot with plain, coalesced stores
+    auto flush_det = [&](int item) {
+      const int ch = item / p.n64;
+      mbar_wait(acc_full, flushes & 1);
+      tc_fence_after();
+      float* slot = p.part + (static_cast<size_t>(blockIdx.x) * p.slots_per_cta + (item - first_item)) * WG_SLOT_FLOATS;
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+        const bool live = part == 0 || lane < 16;
+        float* dst0 = part == 0 ? slot + q * 32 + lane : slot + 192 * 128 + 16 * q + lane;
+        const int rows = part == 0 ? 128 : 64;
+#pragma unroll 1
+        for (int c32 = 0; c32 < 6; ++c32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + part * L::D2_COL + c32 * 32, v);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst0[static_cast<size_t>(c32 * 32 + j) * rows] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      if (p.dbias != nullptr && ch == 0) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + L::BIAS_COL, v);
+        tmem_ld_wait();
+        if (lane < 16) slot[192 * 128 + 192 * 64 + 16 * q + lane] = __uint_as_float(v[0]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      ++flushes;
+    };
     auto flush = [&](int item) {
+      if (p.part != nullptr) {
+        flush_det(item);
+        return;
+      }
       const int nb = item % p.n64, ch = item / p.n64;
       mbar_wait(acc_full, flushes & 1);
       tc_fence_after();
@@ -302,6 +346,77 @@ wgrad_scatter_kernel(float* __restrict__ scratch, float* __restrict__ dw, int co
   }
 }
 
+// Deterministic mode: dW OIHW (and the bias gradient) from the per-CTA partial slots, summed in CTA order (a fixed order
+// for a fixed shape and SM budget: bit-identical from run to run; no memset, no atomics).  Same 32 (ci) x 32 (co) x 9 taps
+// tiling through shared memory as wgrad_scatter_kernel.  The CTAs that hold a piece of item i are those whose step range
+// [total c / G, total (c + 1) / G) meets [i T, (i + 1) T); inside CTA c the item sits in slot i - (first item of c).
+// CI_T = input channels per block: 32, or 8 for layers with so few 32 x 32 tiles that the sum over up to 148 slots per item
+// would run on a handful of SMs (64 -> 64: 4 blocks; measured 190 us for the reduction alone).
+template <int CI_T>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ dbias, int cout, int ctot,
+                    int n64, int num_tiles, int grid_ctas, int slots_per_cta, int accumulate) {
+  constexpr int KR = CI_T / 8;   // input channels per warp
+  __shared__ float tile[9][CI_T][33];
+  const int ci0 = blockIdx.x * CI_T, co0 = blockIdx.y * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = (ci0 >> 6) * n64 + (co0 >> 6);
+  const int ci_in = ci0 & 63, co_in = co0 & 63;
+  const long long T = num_tiles, total = (long long)n64 * (ctot >> 6) * T;
+  const long long lo = (long long)item * T, hi = lo + T;
+  int c_first = (int)(lo * grid_ctas / total);
+  while (c_first > 0 && total * c_first / grid_ctas > lo) --c_first;
+  while (total * (c_first + 1) / grid_ctas <= lo) ++c_first;
+  float acc[9][KR];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int k = 0; k < KR; ++k) acc[tap][k] = 0.f;
+  float bsum = 0.f;
+  const bool bias_block = dbias != nullptr && blockIdx.x == 0 && threadIdx.x < 32;   // (ci0 = 0: an item of chunk 0)
+  int c_end = c_first + 1;               // one past the last CTA whose range starts before the item ends
+  while (c_end < grid_ctas && total * c_end / grid_ctas < hi) ++c_end;
+  // (unrolled: the loads of four slots are in flight together -- the loop is latency-bound otherwise; the ADDS stay in
+  // CTA order)
+#pragma unroll 4
+  for (int c = c_first; c < c_end; ++c) {
+    const long long cs0 = total * c / grid_ctas;
+    const float* slot = part + (static_cast<size_t>(c) * slots_per_cta + (item - (int)(cs0 / T))) * WG_SLOT_FLOATS;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - 3 * ky;
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        const int col = ky * 64 + ci_in + warp + 8 * k;
+        const float v = kx == 0 ? slot[192 * 128 + col * 64 + co_in + lane]
+                                : slot[col * 128 + (kx == 2 ? 0 : 64) + co_in + lane];
+        acc[tap][k] += v;
+      }
+    }
+    if (bias_block) bsum += slot[192 * 128 + 192 * 64 + co_in + threadIdx.x];
+  }
+  if (bias_block) dbias[co0 + threadIdx.x] = accumulate ? dbias[co0 + threadIdx.x] + bsum : bsum;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int k = 0; k < KR; ++k) tile[tap][warp + 8 * k][lane] = acc[tap][k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co_l = warp + 8 * k;
+    float* dst = dw + (static_cast<size_t>(co0 + co_l) * ctot + ci0) * 9;
+#pragma unroll
+    for (int e0 = 0; e0 < 9 * CI_T; e0 += 32) {
+      const int e = e0 + lane;
+      if (e < 9 * CI_T) {
+        const int ci_l = e / 9, tap = e - 9 * ci_l;
+        const float v = tile[tap][ci_l][co_l];
+        dst[e] = accumulate ? dst[e] + v : v;
+      }
+    }
+  }
+}
+
 // db[c] = sum over pixels of dZ[p][c]   (dZ: [npix][C] bf16); db must be zero-initialised.
 // Thread t owns channel pair (t % C2) for pixels (t / C2) + k * rows; the rows of a block are reduced through shared
 // memory so that a block issues one atomic per channel.
@@ -340,9 +455,49 @@ extern "C" long long pda_conv3x3_wgrad_scratch_floats(int ctot, int cout) {
   return 9LL * cout * ctot + cout;
 }
 
+static int wgrad_grid(int ctot, int cout, int B, int H, int W, long long* steps_out, int* tiles_out) {
+  const long long nt = (long long)((W + 7) / 8) * ((H + 15) / 16) * B;
+  const long long steps = (long long)(cout >> 6) * (ctot >> 6) * nt;
+  if (steps_out) *steps_out = steps;
+  if (tiles_out) *tiles_out = (int)nt;
+  const int sms = sm_budget(0);
+  return (int)(steps < sms ? steps : sms);
+}
+// slots a CTA may need: the items its contiguous step range can touch
+static int wgrad_slots_per_cta(long long steps, int grid, int num_tiles) {
+  const long long per = (steps + grid - 1) / grid;
+  return (int)((per + num_tiles - 1) / num_tiles) + 1;
+}
+
+// deterministic variant: scratch = per-CTA partial accumulators (size depends on the shape AND the SM budget in force)
+extern "C" long long pda_conv3x3_wgrad_det_scratch_floats(int ctot, int cout, int B, int H, int W) {
+  if (ctot <= 0 || cout <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  long long steps;
+  int nt;
+  const int grid = wgrad_grid(ctot, cout, B, H, W, &steps, &nt);
+  return (long long)grid * wgrad_slots_per_cta(steps, grid, nt) * WG_SLOT_FLOATS;
+}
+
+static int wgrad_launch(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
+                        float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate,
+                        int scratch_is_zero, int deterministic, void* stream_);
+
+extern "C" int pda_conv3x3_wgrad_bf16_det(const void* src0, int c0, const void* src1, int c1, const void* dz,
+                                          float* scratch, float* dw_oihw, float* dbias, int B, int H, int W, int cout,
+                                          int accumulate, void* stream_) {
+  return wgrad_launch(src0, c0, src1, c1, dz, scratch, dw_oihw, dbias, B, H, W, cout, accumulate, 0, 1, stream_);
+}
+
 extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz,
                                       float* scratch, float* dw_oihw, float* dbias, int B, int H, int W, int cout,
                                       int accumulate, int scratch_is_zero, void* stream_) {
+  return wgrad_launch(src0, c0, src1, c1, dz, scratch, dw_oihw, dbias, B, H, W, cout, accumulate, scratch_is_zero, 0,
+                      stream_);
+}
+
+static int wgrad_launch(const void* src0, int c0, const void* src1, int c1, const void* dz, float* scratch,
+                        float* dw_oihw, float* dbias, int B, int H, int W, int cout, int accumulate,
+                        int scratch_is_zero, int deterministic, void* stream_) {
   if (!src0 || !dz || !scratch || !dw_oihw || (c1 > 0 && !src1)) return PDA_ERR_ARG;
   if (c0 <= 0 || (c0 & 63) || (c1 & 63) || (cout & 63) || B <= 0 || H <= 0 || W <= 0) return PDA_ERR_SHAPE;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -359,6 +514,8 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   a.scratch = scratch;
   // the bias sums are accumulated in the cout floats BEHIND the weight scratch
   a.dbias = dbias ? scratch + 9ull * cout * ctot : nullptr;
+  a.part = nullptr;
+  a.slots_per_cta = 0;
   CUtensorMap tX0, tX1, tDZ;
   int r = make_act_tensor_map(&tX0, src0, B, H, W, c0, 8, 18, 64);
   if (r) return r;
@@ -371,7 +528,7 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   r = make_act_tensor_map(&tDZ, dz, B, H, W, cout, 16, 16, 64);
   if (r) return r;
   // scratch_is_zero: the caller keeps this scratch across calls; the scatter kernel leaves it all-zero again (no memset)
-  if (!scratch_is_zero &&
+  if (!deterministic && !scratch_is_zero &&
       cudaMemsetAsync(scratch, 0, sizeof(float) * pda_conv3x3_wgrad_scratch_floats(ctot, cout), stream) != cudaSuccess)
     return PDA_ERR_CUDA;
   static int configured[64];
@@ -383,10 +540,24 @@ extern "C" int pda_conv3x3_wgrad_bf16(const void* src0, int c0, const void* src1
   const long long steps = (long long)a.items * a.num_tiles;
   const int sms = sm_budget(0);
   const int grid = (int)(steps < sms ? steps : sms);
+  if (deterministic) {
+    a.part = scratch;
+    a.slots_per_cta = wgrad_slots_per_cta(steps, grid, a.num_tiles);
+    a.dbias = dbias;   // (only tested for null-ness by the kernel in this mode)
+  }
   PDA_COUNT(1);
   wgrad3x3_tc_kernel<<<grid, 192, WgradSmem::DYN_BYTES, stream>>>(tX0, tX1, tDZ, a);
   if (cudaGetLastError() != cudaSuccess) return PDA_ERR_CUDA;
   PDA_COUNT(1);
+  if (deterministic) {
+    if ((ctot / 32) * (cout / 32) < 148)
+      wgrad_reduce_kernel<8><<<dim3(ctot / 8, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, dbias, cout, ctot, a.n64,
+                                                                            a.num_tiles, grid, a.slots_per_cta, accumulate);
+    else
+      wgrad_reduce_kernel<32><<<dim3(ctot / 32, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, dbias, cout, ctot, a.n64,
+                                                                              a.num_tiles, grid, a.slots_per_cta, accumulate);
+    return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
+  }
   wgrad_scatter_kernel<<<dim3(ctot / 32, cout / 32), 256, 0, stream>>>(scratch, dw_oihw, cout, ctot, accumulate, dbias,
                                                                        scratch_is_zero);
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;

@@ -374,6 +374,12 @@ def multi_tensor_ema(table, momentum, iteration_dev=None):
 WGRAD_PERSISTENT_SCRATCH = False
 
 
+# PDA_WGRAD_DETERMINISTIC=1 (or ops.WGRAD_DETERMINISTIC = True): the weight-gradient kernel stores per-CTA partial sums and a
+# second kernel adds them in a fixed order instead of fp32 atomics -- bit-identical gradients from run to run (the
+# conv weight gradients are the only non-deterministic sums of a training step besides the Fcomb backward's)
+WGRAD_DETERMINISTIC = os.environ.get("PDA_WGRAD_DETERMINISTIC", "0") == "1"
+
+
 def wgrad_scratch(owner, ctot, cout, dev):
     """The persistent, self-cleaning scratch of one conv layer's weight-gradient kernel (zeroed once, here; the kernel
     leaves it all zero again after every launch, so no memset runs per step).  Kept on the nn.Conv2d container."""
@@ -395,6 +401,16 @@ def conv3x3_wgrad(src0, src1, dz, want_bias=True, owner=None):
     assert dz.shape[:3] == src0.shape[:3] and dz.is_contiguous() and src0.is_contiguous()
     assert src0.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16
     dev = src0.device
+    if WGRAD_DETERMINISTIC:
+        scratch = torch.empty(lib.pda_conv3x3_wgrad_det_scratch_floats(c0 + c1, cout, B, H, W), dtype=torch.float32,
+                              device=dev)
+        dw = torch.empty((cout, c0 + c1, 3, 3), dtype=torch.float32, device=dev)
+        db = torch.empty((cout,), dtype=torch.float32, device=dev) if want_bias else None
+        with _Timed("wgrad3x3_tc", 2.0 * 9 * (c0 + c1) * cout * B * H * W):
+            rc = lib.pda_conv3x3_wgrad_bf16_det(src0.data_ptr(), c0, _ptr(src1), c1, dz.data_ptr(), scratch.data_ptr(),
+                                                dw.data_ptr(), _ptr(db), B, H, W, cout, 0, _stream())
+        _lib.check(rc, "conv3x3_wgrad_det")
+        return dw, db
     if owner is not None and WGRAD_PERSISTENT_SCRATCH:
         scratch, is_zero = wgrad_scratch(owner, c0 + c1, cout, dev), 1
     else:

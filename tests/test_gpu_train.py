@@ -423,3 +423,36 @@ def test_optimizer_step_reduces_loss():
         losses.append(loss.item())
     print("losses", [round(v, 4) for v in losses])
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", [(1, 18, 10, 64, 0, 64), (2, 34, 24, 128, 64, 128), (3, 16, 8, 64, 0, 256),
+                                             (4, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 256)])
+def test_deterministic_weight_gradient_mode(B, H, W, c0, c1, cout):
+    """PDA_WGRAD_DETERMINISTIC: per-CTA partial accumulators + ordered reduction instead of fp32 atomics.  Equal to the
+    atomic path up to summation order, bit-identical across repeated launches, and its scratch may hold garbage on entry
+    (no memset).  Shapes with one item shared by all CTAs (64 -> 64), many items per CTA (768 -> 256 at 8 x 8) and ragged
+    tiles."""
+    from probabilistic_domain_adaptation_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(cout + W + c0)
+    x = torch.randn(B, H, W, c0, generator=g).to(dev).to(torch.bfloat16)
+    s1 = torch.randn(B, H, W, c1, generator=g).to(dev).to(torch.bfloat16) if c1 else None
+    dz = torch.randn(B, H, W, cout, generator=g).to(dev).to(torch.bfloat16)
+    want_dw, want_db = ops.conv3x3_wgrad(x, s1, dz, want_bias=True)
+    prev = ops.WGRAD_DETERMINISTIC
+    ops.WGRAD_DETERMINISTIC = True
+    try:
+        first = None
+        for i in range(4):
+            junk = torch.full((1 << 22,), float("nan"), device=dev)   # poison freed memory the next scratch may reuse
+            del junk
+            dw, db = ops.conv3x3_wgrad(x, s1, dz, want_bias=True)
+            torch.cuda.synchronize()
+            assert torch.allclose(dw, want_dw, rtol=1e-4, atol=1e-3 * float(want_dw.abs().max()))
+            assert torch.allclose(db, want_db, rtol=1e-4, atol=1e-3 * float(want_db.abs().max()))
+            if first is None:
+                first = (dw.clone(), db.clone())
+            else:
+                assert torch.equal(dw, first[0]) and torch.equal(db, first[1]), i
+    finally:
+        ops.WGRAD_DETERMINISTIC = prev
