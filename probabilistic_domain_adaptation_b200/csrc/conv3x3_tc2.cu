@@ -22,6 +22,9 @@
 #include "conv.cuh"
 #include "ptx.cuh"
 
+#ifndef PDA_PDL_TRIGGER_EARLY
+#define PDA_PDL_TRIGGER_EARLY 0
+#endif
 #ifndef PDA_CONV_WIDE_DEFAULT
 #define PDA_CONV_WIDE_DEFAULT 0
 #endif
@@ -221,6 +224,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), L::TMEM_COLS);
     tmem_relinquish_pair();
   }
+  // Programmatic dependent launch: the on-chip set-up above overlaps the tail of the previous kernel in the stream (when
+  // this launch carries the attribute; otherwise both instructions are no-ops); no global memory is touched before the
+  // wait -- the bias below may have been written by the optimizer kernel just before.
+#if PDA_PDL_TRIGGER_EARLY
+  griddep_launch();
+#endif
+  griddep_wait();
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.cout; i += CONV2_THREADS - 64) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   }
@@ -636,6 +646,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the last store
   }
 
+#if !PDA_PDL_TRIGGER_EARLY
+  // this CTA's work is done: the next kernel of the stream may be scheduled onto the SMs that free up while the slowest
+  // CTAs of this grid finish (it still waits for this grid's completion before touching memory).  Triggering at the START
+  // of the kernel let a third kernel become resident while the first was still running and failed on the GPU
+  // (conv -> fused-upsampling conv -> conv chains: "unspecified launch failure"); at the end, at most two grids overlap.
+  griddep_launch();
+#endif
   // both CTAs are done with each other's shared memory / barriers and with their tensor memory
   tc_fence_before();
   __syncthreads();
@@ -664,7 +681,7 @@ static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const 
   cfg.blockDim = dim3(CONV2_THREADS);
   cfg.dynamicSmemBytes = L::DYN_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
@@ -686,6 +703,21 @@ static int launch_conv2_fmt(const CUtensorMap& a0, const CUtensorMap& a1, const 
   if (cap > sm_budget(0) / 2) cap = sm_budget(0) / 2;
   const int pairs = (int)(units < cap ? units : cap);
   cfg.gridDim = dim3(2 * pairs);
+  {
+    // programmatic dependent launch, OFF by default (PDA_PDL=1 switches it on): this kernel's CTAs may be scheduled while
+    // the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches global
+    // memory.  Measured on the inference and the training step (same box, two passes each): no difference outside the
+    // run-to-run noise of +-1 % -- the CUDA-graph replay already hides the launch latency and the prologue is ~1 us.
+    static const int pdl = [] {
+      const char* e = getenv("PDA_PDL");
+      return e ? atoi(e) : 0;
+    }();
+    if (pdl) {
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 2;
+    }
+  }
   PDA_COUNT(1);
   if (cudaLaunchKernelEx(&cfg, kern, a0, a1, b, o, args) != cudaSuccess) return PDA_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? PDA_OK : PDA_ERR_CUDA;
