@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--pair", default="0,1")
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--size", type=int, default=1024, help="input tile size (the layer table is for 1024)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -41,6 +42,8 @@ def main():
     print("| layer | GFLOP | " + " | ".join(f"pair={m}: us | TFLOP/s" for m in modes) + " |")
     print("|---|---|" + "---|---|" * len(modes))
     for name, hw, c0, c1, cout, pool in LAYERS:
+        hw = hw * args.size // 1024
+        name = name.split('@')[0] + f'@{hw}'
         s0 = torch.randn(args.batch, hw, hw, c0, generator=g).to(dev).to(dt)
         s1 = torch.randn(args.batch, hw, hw, c1, generator=g).to(dev).to(dt) if c1 else None
         w = (torch.randn(cout, c0 + c1, 3, 3, generator=g) * 0.02).to(dev)
