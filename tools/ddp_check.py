@@ -24,7 +24,7 @@ def main():
     model = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 0.0, rl_swap=False).to(dev).train()
     broadcast_parameters(model, 0)
     g = torch.Generator().manual_seed(0)
-    B = 4
+    B = max(4, 2 * world)     # at least two images per rank
     x = torch.randn(B, 1, 64, 64, generator=g).to(dev)
     y = (torch.rand(B, 1, 64, 64, generator=g) > 0.5).float().to(dev)
     eps = torch.randn(B, 6, generator=g).to(dev)
