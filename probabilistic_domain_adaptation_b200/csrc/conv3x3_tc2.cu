@@ -26,7 +26,7 @@
 #define PDA_PDL_TRIGGER_EARLY 0
 #endif
 #ifndef PDA_CONV_WIDE_DEFAULT
-#define PDA_CONV_WIDE_DEFAULT 0
+#define PDA_CONV_WIDE_DEFAULT 1
 #endif
 #ifndef PDA_UPS_A_STAGES64
 #define PDA_UPS_A_STAGES64 2
@@ -102,17 +102,19 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-// WIDE: one slab of 16-pixel rows per 64-channel chunk serves all three kx taps (the tap's A operand starts kx pixels =
-// kx * 128 B into the row) instead of three column-shifted 8-pixel slabs: one TMA load and 2/3 of the shared-memory fill
-// traffic per chunk.  Bit-identical results; measured within +-3 % of the 8-pixel slabs on every layer
-// (profiles/r02_conv_wide_slab.md), so the fill traffic is not what limits these kernels: kept as an option
-// (PDA_CONV_WIDE=1), not the default.
+// WIDE (default): ONE slab of 10-pixel rows per 64-channel chunk serves all three kx taps (the tap's A operand starts kx
+// pixels = kx * 128 B into the row; the 1280-byte pitch need not be a whole number of swizzle atoms) instead of three
+// column-shifted 8-pixel slabs: one TMA load and 42 % of the shared-memory fill traffic per chunk, one more stage of
+// look-ahead.  Bit-identical results.  Measured per layer at 4 x 1024^2 (profiles/r02_conv_wide_slab.md): +1..4 % on
+// nine of the ten layer shapes (64 -> 64: 958 -> 997 TFLOP/s), -2.6 % on the single-chunk 64 -> 128 layer, which keeps
+// the 8-pixel slabs; the first version with 16-pixel rows and two stages was neutral.  PDA_CONV_WIDE=0 selects the
+// 8-pixel slabs everywhere.
 template <int BN, int MT, bool RES, bool WIDE = false, bool UPS = false>
 struct Conv2Cfg {
   static constexpr int SLAB_ROWS = 16 * MT + 2;
   // one slab row: 16 or 8 px x 128 B.  UPS: PDA_UPS_ROW_PX pixels -- the pitch need not be a whole number of 1024-byte
   // swizzle atoms because both TMA and the MMA unit derive the swizzle from shared-memory ADDRESS bits
-  static constexpr int ROW_BYTES = UPS ? PDA_UPS_ROW_PX * 128 : (WIDE ? 2048 : 1024);
+  static constexpr int ROW_BYTES = (UPS || WIDE) ? PDA_UPS_ROW_PX * 128 : 1024;   // (WIDE used 16-pixel rows at first)
   // UPS: the low-resolution patch one slab interpolates from (rows x 7 px x 64 channels, unswizzled), double-buffered
   static constexpr int PATCH_ROWS = 8 * MT + 3;
   static constexpr int PATCH_PX = 7;
@@ -124,7 +126,7 @@ struct Conv2Cfg {
   static constexpr int B_BYTES = BH * 128;             // this CTA's half of one (tap, chunk) weight tile
   // (UPS, N = 64: a third slab stage -- PDA_UPS_A_STAGES64 = 3, paid for with two of the eight weight stages -- measured
   // no faster: that layer is bound by the shared-memory port, which the software producer's reads and writes share)
-  static constexpr int A_STAGES = WIDE ? (MT == 2 ? ((UPS && BN == 64) ? PDA_UPS_A_STAGES64 : 2) : 3) : 4;
+  static constexpr int A_STAGES = UPS ? (MT == 2 ? (BN == 64 ? PDA_UPS_A_STAGES64 : 2) : 3) : (WIDE ? (MT == 2 ? 3 : 4) : 4);
   static constexpr int B_STAGES =
       RES ? 9 : (BN == 256 ? 4 : (MT == 2 ? (BN == 128 ? 5 : ((UPS && PDA_UPS_A_STAGES64 == 3) ? 6 : 8)) : 6));
   static constexpr int A_OFF = 0;
@@ -769,11 +771,13 @@ int conv3x3_tc2(const void* src0, int c0, const void* src1, int c1, const void* 
       const char* e = getenv("PDA_CONV_WIDE");  // 0: three 8-px slabs per chunk; 1: one 16-px slab per chunk
       return e ? atoi(e) : PDA_CONV_WIDE_DEFAULT;
     }();
-    a.wide = wide_mode != 0 || up_src != nullptr;
+    // one 10-pixel slab per chunk (default) except for the single-chunk 64 -> 128 layer, the one shape that measured
+    // slower with it (profiles/r02_conv_wide_slab.md)
+    a.wide = (wide_mode != 0 && !(c0 + c1 == 64 && cout != 64)) || up_src != nullptr;
     a.wide_base_offset = 0;
   }
   a.up_src = up_src;
-  const int box_w = up_src != nullptr ? PDA_UPS_ROW_PX : (a.wide ? 16 : 8);
+  const int box_w = a.wide ? PDA_UPS_ROW_PX : 8;
   CUtensorMap tA0, tA1, tB;
   int r;
   if (up_src == nullptr) {
