@@ -21,11 +21,14 @@
 // bz_s = b1 + W1z . z_s is the per-(sample, image) bias that replaces the tiled-z concat (fcomb_bz_kernel).
 //
 // Warp-specialised persistent CTA (2 per SM): warps 0-3 = producers (own H1 in registers, write the A1 ring),
-// warps 4-7 = epilogue (TMEM -> relu -> w3 dot with w3 held in registers -> sigmoid / counters),
-// warp 8 = control (TMA of the feature tile, all tcgen05.mma).  Three mbarrier pipelines (F tile, A1 ring of 2 and
-// H2 accumulator ring of 2, both in TMEM) let the three roles run concurrently; nothing but the outputs leaves the SM.
-// Measured (profiles/r01e_fcomb_variants.md): 1.62 ms -> 0.99 ms at 4 x 1024^2 px, S = 16 against the version that
-// staged A1 in shared memory with fp32 adds; the kernel is now issue-bound (67 % of the issue slots).
+// warps 4-7 = epilogue (TMEM -> relu -> packed fp16 -> TMEM, later the two last-layer columns -> sigmoid / counters),
+// warp 8 = control (TMA of the feature tile, all tcgen05.mma).  mbarrier pipelines for the F tile, the A1 ring of 2 and
+// the H2 accumulator ring of 3 (all in TMEM; H1 shares its columns with the A1 ring) let the three roles run
+// concurrently; nothing but the outputs leaves the SM.
+// Measured: 1.62 ms -> 0.99 ms at 4 x 1024^2 px, S = 16 against the version that staged A1 in shared memory with fp32
+// adds (profiles/r01e_fcomb_variants.md); the last layer as an MMA another 8 %; what paces the kernel now is the
+// epilogue warps' per-sample chain of one tensor-memory load and one store round trip (~700 cycles, one warp per TMEM
+// lane quarter): profiles/r02_fcomb_l3_variants.md lists every experiment with same-box A/B numbers.
 #include <cuda_fp16.h>
 
 #include "conv.cuh"
