@@ -69,3 +69,59 @@ def test_bucketed_gradient_average_world2():
     loss.backward()
     for p, g in zip(net.parameters(), out[0]["grads"]):
         assert torch.allclose(p.grad, g, atol=1e-6)
+
+
+class _ParkedReg(torch.autograd.Function):
+    """A regulariser stand-in: value sum_t c_t * sum(p_t); its backward parks the gradients (training._defer_reg_grads)
+    instead of returning them, like training.L2NormSumFn does on the GPU."""
+
+    @staticmethod
+    def forward(ctx, coef, *params):
+        ctx.coef, ctx.params = coef, params
+        return sum(c * p.sum() for c, p in zip(coef, params))
+
+    @staticmethod
+    def backward(ctx, g):
+        from probabilistic_domain_adaptation_b200 import training
+        training._defer_reg_grads(ctx.params, [torch.full_like(p, c) * g for c, p in zip(ctx.coef, ctx.params)])
+        return (None,) * (1 + len(ctx.params))
+
+
+def test_parked_regulariser_gradients_reach_param_grad():
+    """Host logic of the bulk regulariser-gradient path (CPU tensors): the parked gradients are added to param.grad at
+    the end of backward, or by a GradAllReducer bucket before it is copied -- in both cases param.grad equals data
+    gradient + regulariser gradient, repeatedly, and nothing stays parked."""
+    from probabilistic_domain_adaptation_b200 import training
+    from probabilistic_domain_adaptation_b200.parallel import GradAllReducer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    params = list(net.parameters())
+    coef = [0.5, -1.0, 2.0, 0.25]
+    x = torch.randn(4, 6)
+
+    def loss_fn():
+        return net(x).square().sum() + 3.0 * _ParkedReg.apply(coef, *params)
+
+    for p in params:
+        p.grad = None
+    net(x).square().sum().backward()
+    want = [p.grad.clone() + 3.0 * c for p, c in zip(params, coef)]
+    for with_reducer in (False, True):
+        red = GradAllReducer(net, bucket_mb=1e-5) if with_reducer else None
+        try:
+            for _ in range(2):
+                for p in params:
+                    p.grad = None
+                loss_fn().backward()
+                if red is not None:
+                    red.finish()
+                assert not training._PENDING_REG
+                for w, p in zip(want, params):
+                    assert torch.allclose(p.grad, w, rtol=1e-6, atol=1e-6)
+        finally:
+            if red is not None:
+                red.remove()
+    # a parameter that receives ONLY the regulariser gradient
+    extra = torch.nn.Parameter(torch.ones(3))
+    (net(x).sum() + _ParkedReg.apply([4.0], extra)).backward()
+    assert torch.equal(extra.grad, torch.full((3,), 4.0)) and not training._PENDING_REG
