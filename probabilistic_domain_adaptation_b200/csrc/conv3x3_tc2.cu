@@ -134,7 +134,7 @@ struct Conv2Cfg {
   static constexpr int STG_OFF = B_OFF + B_STAGES * B_BYTES;   // 8 epilogue warps x 4 KB output staging
   static constexpr int P_OFF = STG_OFF + 8 * 4096;
   static constexpr int BAR_OFF = P_OFF + P_STAGES * PATCH_BYTES;
-  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4 + P_STAGES;
+  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4 + P_STAGES + (UPS ? A_STAGES : 0);
   static constexpr int SLOT_OFF = BAR_OFF + NBARS * 8;
   static constexpr int BIAS_OFF = SLOT_OFF + 16;
   static constexpr int MAX_COUT = 512;
@@ -160,8 +160,8 @@ constexpr int CONV2_THREADS = 320;
 //     in this mode: one arrival per CTA for every chunk, software-produced or TMA-loaded)
 //   * slab rows are PDA_UPS_ROW_PX = 10 pixels (the three kx taps read pixels kx .. kx + 7), not the WIDE layout's 16
 //   * per unit they first produce the unit's segment-0 chunks, then drain the PREVIOUS unit's accumulators
-//   * a party that skips a stage use (the TMA warp skips the produced chunks, the producer the loaded ones) still waits
-//     on the stage's empty barrier for it: a parity wait cannot tell phase n from phase n + 2
+//   * the MMA warp hands a consumed stage back on the barrier of the producer that owns the stage's NEXT use (TMA warp or
+//     epilogue warps): neither producer ever watches the other's uses go by (see the note at nchunk_sw)
 // Measured at the 4 x 1024^2 up-path shapes (tools/conv_up_bench.py): 0.66 / 0.76 / 1.10 ms (upsample2x + conv) ->
 // 0.57 / 0.60 / 0.88 ms.
 template <int BN, int MT, bool RES, bool F16, bool WIDE, bool UPS>
@@ -181,6 +181,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   auto acc_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 2 + s); };
   auto p_full = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 4 + s); };
+  // UPS: "stage s is free and its NEXT use is a software-produced chunk" (a_empty(s): ... a TMA-loaded chunk)
+  auto a_empty_sw = [&](int s) { return bar0 + 8u * (2 * L::A_STAGES + 2 * L::B_STAGES + 4 + L::P_STAGES + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::SLOT_OFF);
   float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFF);
 
@@ -216,6 +218,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_init(acc_empty(s), 16);  // one arrive per epilogue warp of BOTH CTAs (leader's barrier)
     }
     for (int s = 0; s < L::P_STAGES; ++s) mbar_init(p_full(s), 1);
+    if (UPS)
+      for (int s = 0; s < L::A_STAGES; ++s) mbar_init(a_empty_sw(s), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -242,6 +246,23 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // UPS: a slab stage is shared by two producers -- the TMA warp (chunks of segment 1) and the epilogue warps (the
+  // interpolated chunks of segment 0).  A producer that merely WATCHED the other's uses of a stage go by on one shared
+  // "empty" barrier could fall two phases behind (a parity wait cannot tell phase n from n + 2: premature pass) or, if it
+  // observed every use, arrive late at a use that had already been consumed and wait for a completion only its own next
+  // chunk could cause (dead-lock; seen when the kernel shared the GPU with another stream or a programmatically dependent
+  // launch).  So the MMA warp releases a stage on the barrier of the producer that OWNS THE STAGE'S NEXT USE
+  // (a_empty: TMA warp, a_empty_sw: epilogue warps): each producer sees exactly one completion per own use -- the plain
+  // single-producer protocol, twice.  Chunk g of the CTA's sequence (g = unit index * chunks + ch) uses stage
+  // g % A_STAGES and is software-produced iff g % chunks < c0 / 64.
+  const int nchunk_sw = UPS ? (p.c0 >> 6) : 0;
+  // first_free: stages whose very first use belongs to this producer (no release precedes it)
+  auto first_free_mask = [&](bool sw) {
+    uint32_t m = 0;
+    for (int s2 = 0; s2 < L::A_STAGES; ++s2)
+      if (((s2 % chunks) < nchunk_sw) == sw) m |= 1u << s2;
+    return m;
+  };
   // this CTA's pixel tile of pair-unit u (the peer of an odd tile count re-computes the last tile and discards it)
   auto unit_tile = [&](int u, int& nb, int& img, int& ty, int& tx, bool& ghost) {
     nb = u % n_blocks;
@@ -259,6 +280,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const bool leader_lane = elect_one();
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
+    uint32_t ups_first = first_free_mask(false), ups_ph = 0;
     if (RES) {
       // this CTA's half of the whole weight matrix of the (single) n-block: 9 taps x 1 chunk, loaded once
       const uint32_t bar = mapa_shared(b_full(0), 0);
@@ -279,12 +301,20 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const int c = ch << 6;
         for (int kx = 0; kx < 3; ++kx) {
           if ((!WIDE || kx == 0) && UPS && c < p.c0) {
-            // produced by the epilogue warps.  The wait keeps this warp within one phase of the stage's barrier: a
-            // parity wait cannot tell phase n from phase n + 2, so a party that skips uses must still observe them.
-            mbar_wait(a_empty(as), aph ^ 1);
+            // produced by the epilogue warps: not this warp's stage use
             if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
           } else if (!WIDE || kx == 0) {
-            mbar_wait(a_empty(as), aph ^ 1);
+            if (UPS) {
+              // own uses of this stage only (see the note at nchunk_sw)
+              if ((ups_first >> as) & 1u) {
+                ups_first &= ~(1u << as);
+              } else {
+                mbar_wait(a_empty(as), (ups_ph >> as) & 1u);
+                ups_ph ^= 1u << as;
+              }
+            } else {
+              mbar_wait(a_empty(as), aph ^ 1);
+            }
             if (leader_lane) {
               const uint32_t bar = mapa_shared(a_full(as), 0);
               if (rank == 0) mbar_expect_tx(a_full(as), 2 * L::A_TX);
@@ -371,7 +401,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               }
             }
             if (!WIDE || kx == 2) {
-              if (leader_lane) umma_commit_pair(a_empty(as));
+              if (leader_lane) {
+                // UPS: the stage goes back to the producer of its next use (chunk ch + A_STAGES of the sequence)
+                const bool next_sw = UPS && ((ch + L::A_STAGES) % chunks) < nchunk_sw;
+                umma_commit_pair(next_sw ? a_empty_sw(as) : a_empty(as));
+              }
               __syncwarp();
               if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
             }
@@ -548,6 +582,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int col_rows_begin = col_seg * RSEG;          // threads 240..255: past the last row, no items
       int as = 0;
       uint32_t aph = 0;
+      uint32_t sw_first = first_free_mask(true), sw_ph = 0;
       uint32_t it = 0, j = 0;
       int prev_u = -1;
       for (int u = pair; u < units; u += npairs, ++it) {
@@ -567,7 +602,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         for (int ch = 0; ch < nchunk0; ++ch, ++j) {
           const uint32_t ps = j & 1;
           mbar_wait(p_full(ps), (j >> 1) & 1);
-          mbar_wait(a_empty(as), aph ^ 1);
+          // own uses of this stage only (see the note at nchunk_sw): the stage's first use needs no release
+          if ((sw_first >> as) & 1u) {
+            sw_first &= ~(1u << as);
+          } else {
+            mbar_wait(a_empty_sw(as), (sw_ph >> as) & 1u);
+            sw_ph ^= 1u << as;
+          }
           uint8_t* slab = smem + L::A_OFF + as * L::A_BYTES;
           const uint8_t* patch = smem + L::P_OFF + ps * L::PATCH_BYTES;
           // A thread owns one (pixel column px of the 10 the taps read, 8-channel group g) and a run of consecutive slab
@@ -636,10 +677,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
         if (prev_u >= 0) drain(prev_u, it - 1);
         prev_u = u;
-        // the chunks the TMA warp loads: observe every use of the stage (see the note in the TMA warp), after the drain so
-        // that the waits cost nothing -- the next unit's first chunk needs a later use of the same stages anyway
+        // the chunks the TMA warp loads are not this producer's stage uses: only the stage index moves on
         for (int ch = nchunk0; ch < chunks; ++ch) {
-          mbar_wait(a_empty(as), aph ^ 1);
           if (++as == L::A_STAGES) { as = 0; aph ^= 1; }
         }
       }
@@ -650,9 +689,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
 #if !PDA_PDL_TRIGGER_EARLY
   // this CTA's work is done: the next kernel of the stream may be scheduled onto the SMs that free up while the slowest
-  // CTAs of this grid finish (it still waits for this grid's completion before touching memory).  Triggering at the START
-  // of the kernel let a third kernel become resident while the first was still running and failed on the GPU
-  // (conv -> fused-upsampling conv -> conv chains: "unspecified launch failure"); at the end, at most two grids overlap.
+  // CTAs of this grid finish (it still waits for this grid's completion before touching memory).  (Triggering at the START
+  // of the kernel is what first exposed the slab-ring protocol bug of the fused up-sampling mode -- see the note at
+  // nchunk_sw; with the trigger here at most two grids overlap.)
   griddep_launch();
 #endif
   // both CTAs are done with each other's shared memory / barriers and with their tensor memory

@@ -197,11 +197,16 @@ def conv3x3(src0, src1, w_packed, bias, relu=True, want_full=True, want_pool=Fal
 FUSE_UPSAMPLE = os.environ.get("PDA_FUSE_UPSAMPLE", "1") != "0"
 
 
+_FUSE_DEBUG_MASK = int(os.environ["PDA_FUSE_MASK"]) if "PDA_FUSE_MASK" in os.environ else None
+
+
 def can_fuse_upsample(x_low, bridge):
     """The fused form lives in the CTA-pair conv kernel (needs >= 2 pixel tiles of 8 x 16/32 px)."""
     if not FUSE_UPSAMPLE or _lib.load().pda_set_conv_pair(-1) != 1:
         return False
-    B, H, W, _ = bridge.shape
+    B, H, W, c1 = bridge.shape
+    if _FUSE_DEBUG_MASK is not None and not (_FUSE_DEBUG_MASK & (c1 // 64)):   # PDA_FUSE_MASK: debugging aid that fuses
+        return False                                                           # only the layers with 64 * mask bridge channels
     return x_low.shape[1] * 2 == H and x_low.shape[2] * 2 == W and B * ((W + 7) // 8) * ((H + 31) // 32) >= 2
 
 

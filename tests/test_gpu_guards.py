@@ -207,3 +207,36 @@ def test_repeated_launches_are_bit_identical():
             ref = (mean.clone(), mask.clone())
         else:
             assert torch.equal(mean, ref[0]) and torch.equal(mask, ref[1]), i
+
+
+def test_two_models_on_two_streams_run_the_whole_inference_concurrently():
+    """Two models run their MC inference (all conv layers, the fused up-sampling convs, Fcomb) on two CUDA streams at the
+    same time, at a size where every kernel fills the GPU, so that the CTAs of the two launches interleave: results must
+    be bit-identical to the serial runs.  Regression test for the slab-ring protocol of the fused up-sampling conv: with a
+    single "stage free" barrier shared by its two producers, a producer that reached a skipped use late waited for a
+    completion only its own next chunk could cause -- dead-lock as soon as the kernel did not have the GPU to itself
+    (bounded wait -> launch error after 2 s)."""
+    from oracle import punet_oracle as po
+    from probabilistic_domain_adaptation_b200 import ProbabilisticUnet, consensus
+    dev = _dev()
+    models = []
+    for seed in (0, 1):
+        m = ProbabilisticUnet(1, 1, [64, 128, 256, 512], 6, 3, 1.0).to(dev).eval()
+        m.load_state_dict(po.make_state_dict(seed, last_layer_gain=8.0))
+        models.append(m)
+    x, _, eps, _ = po.synthetic_inputs(2, 512, 512, s=8)
+    x, eps = x.to(dev), eps.to(dev)
+    serial = [consensus.sample_from_teacher(m, x, 8, do_consensus_masking=True, eps=eps) for m in models]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for it in range(12):
+        outs = []
+        for m, st in zip(models, streams):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                outs.append(consensus.sample_from_teacher(m, x, 8, do_consensus_masking=True, eps=eps))
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for o, ref in zip(outs, serial):
+            assert torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1]), it

@@ -1,7 +1,7 @@
-"""Reproduction tool for the single-stream limitation: two models run their MC inference on two
-CUDA streams at the same time.  python tools/two_stream_stress.py <image size> <iterations>.  Up to 384 x 384 (2 images)
-the results are bit-identical to the serial run; from 512 x 512 on a bounded mbarrier wait expires after ~2 s in some
-runs (launch error instead of a hang)."""
+"""Stress tool: two models run their MC inference on two CUDA streams at the same time, so that
+the CTAs of different launches interleave.  python tools/two_stream_stress.py <image size> <iterations>.  Results must be
+bit-identical to the serial run.  (Before the slab-ring protocol fix of the fused up-sampling conv this failed from
+2 x 512 x 512 on: a bounded mbarrier wait expired after ~2 s.)"""
 import sys, time, torch
 sys.path.insert(0, '.')
 from oracle import punet_oracle as po
